@@ -1,0 +1,176 @@
+"""NumPy restatement of the device RNG contract (TEST INFRASTRUCTURE ONLY).
+
+This is *not* a restatement of reference code: the reference draws from NumPy's
+PCG64 (`/root/reference/src/models/bivariate/mcmc.py:486`).  It restates the
+counter-based Philox4x32-10 contract of ``mcmc_clv_model_b200/csrc/clv_rng.cuh``
+so that the GPU's "strict f64" Philox mode can be replayed through the oracle
+(and through the reference's own block functions) variate for variate.
+
+Contract
+--------
+key     = (lo32(seed + chain), hi32(seed + chain))
+counter = (customer_gid, sweep, slot, domain)
+domain  : 0 sampler level-1, 1 level-2 draw, 2 forecast, 3 synthetic generator
+"""
+from __future__ import annotations
+
+import numpy as np
+
+M0 = np.uint64(0xD2511F53)
+M1 = np.uint64(0xCD9E8D57)
+W0 = 0x9E3779B9
+W1 = 0xBB67AE85
+MASK32 = np.uint64(0xFFFFFFFF)
+
+DOM_SAMPLER, DOM_LEVEL2, DOM_FORECAST, DOM_GENERATOR = 0, 1, 2, 3
+
+TWO_PI = 6.283185307179586476925286766559
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10.  All inputs broadcastable, treated as uint32.
+    Returns four uint32 arrays."""
+    c0, c1, c2, c3 = np.broadcast_arrays(
+        *(np.asarray(v, dtype=np.uint64) & MASK32 for v in (c0, c1, c2, c3))
+    )
+    c0, c1, c2, c3 = (c.copy() for c in (c0, c1, c2, c3))
+    k0 = int(k0) & 0xFFFFFFFF
+    k1 = int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = M0 * c0
+        p1 = M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & MASK32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & MASK32
+        n0 = hi1 ^ c1 ^ np.uint64(k0)
+        n2 = hi0 ^ c3 ^ np.uint64(k1)
+        c0, c1, c2, c3 = n0, lo1, n2, lo0
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+    return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
+
+
+def chain_key(seed: int, chain: int):
+    s = (int(seed) + int(chain)) & 0xFFFFFFFFFFFFFFFF
+    return s & 0xFFFFFFFF, s >> 32
+
+
+def u53(a, b):
+    """53-bit uniform strictly inside (0,1) from two uint32 words."""
+    a = np.asarray(a, dtype=np.uint64)
+    b = np.asarray(b, dtype=np.uint64)
+    m = (a >> np.uint64(5)) * np.uint64(1 << 26) + (b >> np.uint64(6))  # 53 bits
+    return (m.astype(np.float64) + 0.5) * (2.0 ** -53)
+
+
+def u32(a):
+    """32-bit uniform strictly inside (0,1) (strict-f64 mode)."""
+    return (np.asarray(a, dtype=np.float64) + 0.5) * (2.0 ** -32)
+
+
+def t3_from_words(ra, rb, rc):
+    """Student-t(3) without rejection: N0 / sqrt((N1^2 - 2 ln U3)/3)."""
+    u1, u2, u3 = u32(ra), u32(rb), u32(rc)
+    r = np.sqrt(-2.0 * np.log(u1))
+    ang = TWO_PI * u2
+    n0 = r * np.cos(ang)
+    n1 = r * np.sin(ang)
+    chi2 = n1 * n1 + (-2.0 * np.log(u3))
+    return n0 / np.sqrt(chi2 / 3.0)
+
+
+def normal_pair_u53(r0, r1, r2, r3):
+    ua, ub = u53(r0, r1), u53(r2, r3)
+    r = np.sqrt(-2.0 * np.log(ua))
+    ang = TWO_PI * ub
+    return r * np.cos(ang), r * np.sin(ang)
+
+
+# ---------------------------------------------------------------------------
+# sampler domain
+# ---------------------------------------------------------------------------
+def sampler_variates(seed, chain, gids, sweep, n_mh_steps, with_eta=False):
+    """All per-customer variates of one sweep in strict-f64 mode.
+
+    Returns dict: u_z, e_tau, u_tau (N,), t3_l, t3_m, u_acc (S,N), [n_eta (N,)].
+    e_tau and u_tau derive from the same 53-bit uniform (only one is consumed,
+    depending on z)."""
+    k0, k1 = chain_key(seed, chain)
+    gids = np.asarray(gids, dtype=np.uint64)
+    r = philox4x32_10(gids, sweep, 0, DOM_SAMPLER, k0, k1)
+    u_z = u53(r[0], r[1])
+    u_t = u53(r[2], r[3])
+    out = dict(u_z=u_z, u_tau=u_t, e_tau=-np.log(u_t))
+    S = n_mh_steps
+    t3_l = np.empty((S, gids.size))
+    t3_m = np.empty((S, gids.size))
+    u_acc = np.empty((S, gids.size))
+    for s in range(S):
+        a = philox4x32_10(gids, sweep, 1 + 2 * s, DOM_SAMPLER, k0, k1)
+        b = philox4x32_10(gids, sweep, 2 + 2 * s, DOM_SAMPLER, k0, k1)
+        t3_l[s] = t3_from_words(a[0], a[1], a[2])
+        t3_m[s] = t3_from_words(a[3], b[0], b[1])
+        u_acc[s] = u32(b[2])
+    out.update(t3_l=t3_l, t3_m=t3_m, u_acc=u_acc)
+    if with_eta:
+        e = philox4x32_10(gids, sweep, 1 + 2 * S, DOM_SAMPLER, k0, k1)
+        out["n_eta"] = normal_pair_u53(e[0], e[1], e[2], e[3])[0]
+    return out
+
+
+# ---------------------------------------------------------------------------
+# level-2 domain
+# ---------------------------------------------------------------------------
+def level2_normal(seed, chain, sweep, idx):
+    k0, k1 = chain_key(seed, chain)
+    r = philox4x32_10(np.asarray([idx]), sweep, 0, DOM_LEVEL2, k0, k1)
+    return float(normal_pair_u53(r[0], r[1], r[2], r[3])[0][0])
+
+
+def level2_chi2(seed, chain, sweep, idx, df):
+    """chi2(df) = 2*Gamma(df/2) by Marsaglia-Tsang (df >= 2), f64."""
+    k0, k1 = chain_key(seed, chain)
+    a = 0.5 * float(df)
+    d = a - 1.0 / 3.0
+    c = 1.0 / np.sqrt(9.0 * d)
+    attempt = 0
+    while True:
+        ra = philox4x32_10(np.asarray([idx]), sweep, 2 * attempt, DOM_LEVEL2, k0, k1)
+        rb = philox4x32_10(np.asarray([idx]), sweep, 2 * attempt + 1, DOM_LEVEL2, k0, k1)
+        x = float(normal_pair_u53(ra[0], ra[1], ra[2], ra[3])[0][0])
+        u = float(u53(rb[0], rb[1])[0])
+        attempt += 1
+        v = 1.0 + c * x
+        if v <= 0.0:
+            continue
+        v = v * v * v
+        if np.log(u) < 0.5 * x * x + d - d * v + d * np.log(v):
+            return 2.0 * d * v
+
+
+def level2_variates(seed, chain, sweep, D, K, nu_n):
+    """Variates of one level-2 draw: Bartlett normals, chi2, beta normals.
+    Index plan: [0, n_tril) normals; [16, 16+D) chi2; [32, 32+D*K) beta normals."""
+    n_tril = D * (D - 1) // 2
+    iw_norm = np.array([level2_normal(seed, chain, sweep, j) for j in range(n_tril)])
+    iw_chi2 = np.array(
+        [level2_chi2(seed, chain, sweep, 16 + i, nu_n - D + 1 + i) for i in range(D)]
+    )
+    beta_norm = np.array([level2_normal(seed, chain, sweep, 32 + j) for j in range(D * K)])
+    return dict(iw_norm=iw_norm, iw_chi2=iw_chi2, beta_norm=beta_norm)
+
+
+# ---------------------------------------------------------------------------
+# forecast domain
+# ---------------------------------------------------------------------------
+def forecast_uniform(seed, gids, draw):
+    k0, k1 = chain_key(seed, 0)
+    r = philox4x32_10(np.asarray(gids, dtype=np.uint64), draw, 0, DOM_FORECAST, k0, k1)
+    return u53(r[0], r[1])
+
+
+def forecast_spend_normal(seed, gid, draw, j):
+    """j-th per-transaction normal of cell (draw, gid)."""
+    k0, k1 = chain_key(seed, 0)
+    r = philox4x32_10(np.asarray([gid], dtype=np.uint64), draw, 1 + j // 2, DOM_FORECAST, k0, k1)
+    c, s = normal_pair_u53(r[0], r[1], r[2], r[3])
+    return float(c[0] if j % 2 == 0 else s[0])
