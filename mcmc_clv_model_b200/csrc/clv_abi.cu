@@ -1,0 +1,1050 @@
+// clv_abi.cu — host side of libclv_b200.so: the C-ABI declared in include/clv_b200.h.
+// Owns device memory, orders the kernels of one Gibbs sweep, streams kept draws back to the host,
+// and (customer-sharded mode) all-reduces the int64 level-2 statistics over NCCL each sweep.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/clv_b200.h"
+#include "clv_kernels.cuh"
+#include "clv_forecast.cuh"
+
+using namespace clv;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct NcclUid { char internal[128]; };
+typedef void* nccl_comm_t;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclUid*) = nullptr;
+  int (*CommInitRank)(nccl_comm_t*, int, NcclUid, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    // prefer a copy already mapped into the process (torch's bundled NCCL), else the system one
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "libnccl lacks required symbols"; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+constexpr int NCCL_INT64 = 4, NCCL_SUM = 0;
+
+}  // namespace
+
+struct clv_sampler {
+  clv_config cfg{};
+  std::string err;
+  int D = 2, K = 1, S = 20, chains = 1, ncol = 4, P = 5;
+  long long N = 0;
+  bool have_data = false, have_hyper = false, inited = false;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  // hyper (host)
+  std::vector<double> beta0, A0, gamma0;
+  double nu0 = 0;
+  // device
+  ModelConst* d_mc = nullptr;
+  ModelConst h_mc{};
+  ChainParams* d_params = nullptr;
+  int* d_x = nullptr;
+  double *d_tx = nullptr, *d_T = nullptr, *d_Xc = nullptr, *d_logs = nullptr;
+  double *d_ll = nullptr, *d_lm = nullptr, *d_le = nullptr, *d_z = nullptr, *d_tau = nullptr;
+  unsigned long long* d_acc = nullptr;
+  int* d_err = nullptr;
+  // per-run buffers
+  long long* d_loglik = nullptr; long long loglik_cap = 0;
+  double* d_level2 = nullptr; long long level2_cap = 0;
+  double* d_draws[2] = {nullptr, nullptr}; long long draws_cap_bytes[2] = {0, 0};
+  cudaEvent_t ev_chunk_ready[2] = {nullptr, nullptr}, ev_copy_done[2] = {nullptr, nullptr};
+  // resident draws of the last run (single-chunk runs only)
+  long long resident_draws = 0;
+  // injected staging
+  double* d_inj = nullptr; long long inj_cap = 0;
+  // bookkeeping
+  long long sweeps_done = 0, launches = 0;
+  int grid_x = 1;
+  // comm
+  nccl_comm_t comm = nullptr; int world = 1, rank = 0;
+  // timing
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_sweep, ev_l2;
+  double t_sweep_ms = 0, t_l2_ms = 0; long long t_n = 0;
+};
+
+namespace {
+
+int fail(clv_sampler* h, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  g_last_error = buf;
+  return code;
+}
+
+#define CK(h, call)                                                                                  \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return fail(h, CLV_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+// ---- small dense host linear algebra (K <= 16) ------------------------------------------------
+bool chol_host(const double* A, double* L, int n) {
+  std::fill(L, L + n * n, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = A[i * n + j];
+      for (int m = 0; m < j; ++m) s -= L[i * n + m] * L[j * n + m];
+      if (i == j) {
+        if (!(s > 0.0)) return false;
+        L[i * n + i] = std::sqrt(s);
+      } else {
+        L[i * n + j] = s / L[j * n + j];
+      }
+    }
+  return true;
+}
+
+// inverse of an SPD matrix through its Cholesky factor
+bool spd_inverse(const double* A, double* Ainv, int n) {
+  std::vector<double> L(n * n), Li(n * n, 0.0);
+  if (!chol_host(A, L.data(), n)) return false;
+  for (int c = 0; c < n; ++c) {               // Li = L^-1 (lower)
+    for (int r = c; r < n; ++r) {
+      double s = (r == c) ? 1.0 : 0.0;
+      for (int m = c; m < r; ++m) s -= L[r * n + m] * Li[m * n + c];
+      Li[r * n + c] = s / L[r * n + r];
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double s = 0.0;
+      for (int m = std::max(i, j); m < n; ++m) s += Li[m * n + i] * Li[m * n + j];
+      Ainv[i * n + j] = s;
+    }
+  return true;
+}
+
+int ceil_log2(double v) {
+  int e = 0;
+  double p = 1.0;
+  while (p < v && e < 1000) { p *= 2.0; ++e; }
+  return e;
+}
+
+SweepArgs base_args(clv_sampler* h) {
+  SweepArgs a{};
+  a.mc = h->d_mc;
+  a.params = h->d_params;
+  a.x = h->d_x; a.t_x = h->d_tx; a.T_cal = h->d_T; a.Xc = h->d_Xc; a.log_s = h->d_logs;
+  a.ll = h->d_ll; a.lm = h->d_lm; a.le = h->d_le; a.z = h->d_z; a.tau = h->d_tau;
+  a.acc = h->d_acc;
+  a.loglik_acc = h->d_loglik;
+  a.loglik_stride = 1;
+  a.draws = nullptr; a.chunk_cap = 1; a.slot = -1; a.draw_index = 0;
+  a.sweep = 0; a.chain_offset = (uint32_t)h->cfg.chain_offset; a.seed = h->cfg.seed;
+  a.store_zt = 0;
+  return a;
+}
+
+cudaEvent_t pool_event(clv_sampler* h) {
+  if (h->ev_used == h->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev_pool.push_back(e);
+  }
+  return h->ev_pool[h->ev_used++];
+}
+
+template <int D>
+void launch_sweep_kernel(clv_sampler* h, const SweepArgs& a, int mode) {
+  dim3 grid(h->grid_x, h->chains), block(SWEEP_THREADS);
+  if (mode == MODE_FAST) k_sweep<D, MODE_FAST><<<grid, block, 0, h->stream>>>(a);
+  else if (mode == MODE_STRICT) k_sweep<D, MODE_STRICT><<<grid, block, 0, h->stream>>>(a);
+  else k_sweep<D, MODE_INJECT><<<grid, block, 0, h->stream>>>(a);
+}
+
+int allreduce_acc(clv_sampler* h) {
+  if (!h->comm) return 0;
+  int r = g_nccl.AllReduce(h->d_acc, h->d_acc, (size_t)h->chains * NSTAT_MAX, NCCL_INT64, NCCL_SUM, h->comm, h->stream);
+  if (r != 0) return fail(h, CLV_ERR_COMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return 0;
+}
+
+// One Gibbs sweep in the reference's block order (bi:387-399 / tri:512-536).
+int enqueue_sweep(clv_sampler* h, SweepArgs a, Level2Args l2, int mode) {
+  auto do_l2 = [&]() {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timing) { e0 = pool_event(h); e1 = pool_event(h); cudaEventRecord(e0, h->stream); }
+    if (h->D == 2) k_level2<2><<<h->chains, 32, 0, h->stream>>>(l2);
+    else k_level2<3><<<h->chains, 32, 0, h->stream>>>(l2);
+    if (h->timing) { cudaEventRecord(e1, h->stream); h->ev_l2.push_back({e0, e1}); }
+    h->launches++;
+  };
+  auto do_sweep = [&]() {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timing) { e0 = pool_event(h); e1 = pool_event(h); cudaEventRecord(e0, h->stream); }
+    if (h->D == 2) launch_sweep_kernel<2>(h, a, mode);
+    else launch_sweep_kernel<3>(h, a, mode);
+    if (h->timing) { cudaEventRecord(e1, h->stream); h->ev_sweep.push_back({e0, e1}); }
+    h->launches++;
+  };
+  if (h->D == 2) {
+    if (int r = allreduce_acc(h)) return r;
+    do_l2();
+    do_sweep();
+  } else {
+    do_sweep();
+    if (int r = allreduce_acc(h)) return r;
+    do_l2();
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, CLV_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  h->sweeps_done++;
+  return 0;
+}
+
+Level2Args base_l2(clv_sampler* h) {
+  Level2Args l{};
+  l.mc = h->d_mc; l.params = h->d_params; l.acc = h->d_acc;
+  l.level2_draws = h->d_level2; l.n_draws = 1; l.draw_index = -1;
+  l.sweep = 0; l.chain_offset = (uint32_t)h->cfg.chain_offset; l.seed = h->cfg.seed;
+  l.injected = 0; l.iw_norm = l.iw_chi2 = l.beta_norm = nullptr;
+  l.error_flag = h->d_err;
+  return l;
+}
+
+int collect_timing(clv_sampler* h) {
+  for (auto& p : h->ev_sweep) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); h->t_sweep_ms += ms; h->t_n++; }
+  for (auto& p : h->ev_l2) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); h->t_l2_ms += ms; }
+  h->ev_sweep.clear(); h->ev_l2.clear(); h->ev_used = 0;
+  return 0;
+}
+
+int check_device_error(clv_sampler* h) {
+  int flag = 0;
+  CK(h, cudaMemcpyAsync(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (h->timing) collect_timing(h);
+  if (flag) return fail(h, CLV_ERR_NUMERIC, "level-2 scale matrix not positive definite or non-finite (sweep <= %lld)", h->sweeps_done);
+  return 0;
+}
+
+int recompute_stats(clv_sampler* h) {
+  CK(h, cudaMemsetAsync(h->d_acc, 0, sizeof(unsigned long long) * h->chains * NSTAT_MAX, h->stream));
+  if (h->D == 2) {   // bivariate: the next sweep starts with a level-2 draw from the current state (bi:393)
+    SweepArgs a = base_args(h);
+    dim3 grid(h->grid_x, h->chains);
+    k_stats_only<2><<<grid, SWEEP_THREADS, 0, h->stream>>>(a);
+    h->launches++;
+    CK(h, cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int clv_abi_version(void) { return CLV_ABI_VERSION; }
+
+const char* clv_last_error(const clv_sampler* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int clv_create(clv_sampler** out, const clv_config* cfg) {
+  if (!out || !cfg) return fail(nullptr, CLV_ERR_ARG, "clv_create: null argument");
+  *out = nullptr;
+  if (cfg->model_dim != 2 && cfg->model_dim != 3) return fail(nullptr, CLV_ERR_ARG, "model_dim must be 2 or 3");
+  if (cfg->n_cov < 1 || cfg->n_cov > CLV_MAX_K) return fail(nullptr, CLV_ERR_ARG, "n_cov must be in [1, %d]", CLV_MAX_K);
+  if (cfg->n_chains < 1 || cfg->n_chains > 65535) return fail(nullptr, CLV_ERR_ARG, "n_chains must be in [1, 65535]");
+  if (cfg->n_mh_steps < 0 || cfg->n_mh_steps > 30000) return fail(nullptr, CLV_ERR_ARG, "n_mh_steps out of range");
+  if (cfg->n_local < 1 || cfg->n_global < cfg->n_local || cfg->gid_offset < 0 ||
+      cfg->gid_offset + cfg->n_local > cfg->n_global || cfg->n_global > 0xFFFFFFFFll)
+    return fail(nullptr, CLV_ERR_ARG, "bad n_local/n_global/gid_offset");
+  if (cfg->rng_mode < 0 || cfg->rng_mode > 2) return fail(nullptr, CLV_ERR_ARG, "bad rng_mode");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, CLV_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, CLV_ERR_ARG, "device %d out of range (have %d)", cfg->device, ndev);
+  clv_sampler* h = new clv_sampler();
+  h->cfg = *cfg;
+  h->D = cfg->model_dim; h->K = cfg->n_cov; h->S = cfg->n_mh_steps; h->chains = cfg->n_chains;
+  h->N = cfg->n_local; h->ncol = h->D == 2 ? 4 : 5; h->P = h->D * h->K + h->D * (h->D + 1) / 2;
+  auto bail = [&](int code) { std::string m = h->err; clv_destroy(h); g_last_error = m; return code; };
+#define CKC(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { fail(h, CLV_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2)); return bail(CLV_ERR_CUDA); } } while (0)
+  CKC(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CKC(cudaGetDeviceProperties(&prop, cfg->device));
+  h->sm_count = prop.multiProcessorCount;
+  CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    CKC(cudaEventCreateWithFlags(&h->ev_chunk_ready[b], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->ev_copy_done[b], cudaEventDisableTiming));
+  }
+  const size_t N = (size_t)h->N, C = (size_t)h->chains;
+  CKC(dmalloc(&h->d_mc, 1));
+  CKC(dmalloc(&h->d_params, C));
+  CKC(dmalloc(&h->d_x, N));
+  CKC(dmalloc(&h->d_tx, N));
+  CKC(dmalloc(&h->d_T, N));
+  CKC(dmalloc(&h->d_Xc, N * (size_t)std::max(h->K - 1, 1)));
+  CKC(dmalloc(&h->d_logs, h->D == 3 ? N : 1));
+  CKC(dmalloc(&h->d_ll, C * N));
+  CKC(dmalloc(&h->d_lm, C * N));
+  CKC(dmalloc(&h->d_le, h->D == 3 ? C * N : 1));
+  CKC(dmalloc(&h->d_z, C * N));
+  CKC(dmalloc(&h->d_tau, C * N));
+  CKC(dmalloc(&h->d_acc, C * NSTAT_MAX));
+  CKC(dmalloc(&h->d_err, 1));
+  CKC(cudaMemset(h->d_err, 0, sizeof(int)));
+  CKC(cudaMemset(h->d_acc, 0, sizeof(unsigned long long) * C * NSTAT_MAX));
+  CKC(cudaMemset(h->d_params, 0, sizeof(ChainParams) * C));
+  {
+    double rk[RK_TABLE + 1];
+    rk[0] = 0.0;
+    for (int k = 1; k <= RK_TABLE; ++k) rk[k] = 1.0 / (double)k;
+    CKC(cudaMemcpyToSymbol(c_rk, rk, sizeof rk));
+  }
+  // grid: a few resident waves of 128-thread blocks, grid-stride over customer tiles
+  long long ntiles = (h->N + SWEEP_THREADS - 1) / SWEEP_THREADS;
+  long long want = ((long long)h->sm_count * 32 + h->chains - 1) / h->chains;
+  h->grid_x = (int)std::max<long long>(1, std::min(ntiles, want));
+#undef CKC
+  *out = h;
+  return CLV_OK;
+}
+
+void clv_destroy(clv_sampler* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  void* ptrs[] = {h->d_mc, h->d_params, h->d_x, h->d_tx, h->d_T, h->d_Xc, h->d_logs, h->d_ll, h->d_lm, h->d_le,
+                  h->d_z, h->d_tau, h->d_acc, h->d_err, h->d_loglik, h->d_level2, h->d_draws[0], h->d_draws[1], h->d_inj};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (int b = 0; b < 2; ++b) {
+    if (h->ev_chunk_ready[b]) cudaEventDestroy(h->ev_chunk_ready[b]);
+    if (h->ev_copy_done[b]) cudaEventDestroy(h->ev_copy_done[b]);
+  }
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  delete h;
+}
+
+int clv_set_data(clv_sampler* h, const int32_t* x, const double* t_x, const double* T_cal, const double* X,
+                 const double* log_s) {
+  if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
+  if (!x || !t_x || !T_cal || !X) return fail(h, CLV_ERR_ARG, "clv_set_data: null column");
+  if (h->D == 3 && !log_s) return fail(h, CLV_ERR_ARG, "clv_set_data: log_s is required for the trivariate model");
+  CK(h, cudaSetDevice(h->cfg.device));
+  const size_t N = (size_t)h->N;
+  CK(h, cudaMemcpyAsync(h->d_x, x, N * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_tx, t_x, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_T, T_cal, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (h->D == 3) CK(h, cudaMemcpyAsync(h->d_logs, log_s, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (h->K > 1) {
+    // row-major N x K (column 0 = intercept) -> SoA covariate columns; strided 2-D copies, one per column
+    for (int k = 1; k < h->K; ++k)
+      CK(h, cudaMemcpy2DAsync(h->d_Xc + (size_t)(k - 1) * N, sizeof(double), X + k, (size_t)h->K * sizeof(double),
+                              sizeof(double), N, cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->have_data = true;
+  h->inited = false;
+  return CLV_OK;
+}
+
+int clv_set_hyper(clv_sampler* h, const double* beta0, const double* A0, double nu0, const double* gamma0) {
+  if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
+  if (!beta0 || !A0 || !gamma0) return fail(h, CLV_ERR_ARG, "clv_set_hyper: null argument");
+  h->beta0.assign(beta0, beta0 + h->K * h->D);
+  h->A0.assign(A0, A0 + h->K * h->K);
+  h->gamma0.assign(gamma0, gamma0 + h->D * h->D);
+  h->nu0 = nu0;
+  h->have_hyper = true;
+  h->inited = false;
+  return CLV_OK;
+}
+
+int clv_init_state(clv_sampler* h, const clv_init_stats* st) {
+  if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
+  if (!st || !st->xtx) return fail(h, CLV_ERR_ARG, "clv_init_state: stats (with xtx) are required");
+  if (!h->have_data || !h->have_hyper) return fail(h, CLV_ERR_STATE, "clv_init_state: call clv_set_data and clv_set_hyper first");
+  if (!(st->lam_init > 0.0) || !std::isfinite(st->lam_init) || !(st->mean_mu_init > 0.0))
+    return fail(h, CLV_ERR_NUMERIC, "clv_init_state: lam_init / mean_mu_init must be positive and finite");
+  CK(h, cudaSetDevice(h->cfg.device));
+  const int K = h->K, D = h->D;
+  ModelConst& mc = h->h_mc;
+  std::memset(&mc, 0, sizeof mc);
+  mc.D = D; mc.K = K; mc.S = h->S; mc.compat = h->cfg.compat;
+  mc.N = h->N; mc.N_global = h->cfg.n_global; mc.gid_offset = h->cfg.gid_offset;
+  // prior mean with the data-dependent intercept row (bi:373-374, tri:497-499)
+  std::vector<double> B0(h->beta0);
+  B0[0] = std::log(st->lam_init);
+  B0[1] = std::log(st->mean_mu_init);
+  if (D == 3) B0[2] = st->mean_log_s;
+  for (int d = 0; d < D; ++d) mc.center[d] = B0[d];
+  // fixed point: |y - c| <= 140 (clip at +-70, bi:323-324), |x_k| <= max_abs_x
+  double mx = std::max(1.0, st->max_abs_x);
+  double bound = 140.0 * std::max(140.0, mx);
+  int bits = 62 - ceil_log2((double)h->cfg.n_global + 1.0) - ceil_log2(bound);
+  bits = std::max(4, std::min(bits, 50));
+  mc.fx_scale = std::ldexp(1.0, bits); mc.fx_inv = std::ldexp(1.0, -bits);
+  int lbits = std::max(4, std::min(62 - ceil_log2((double)h->cfg.n_global + 1.0) - 20, 40));
+  mc.ll_scale = std::ldexp(1.0, lbits); mc.ll_inv = std::ldexp(1.0, -lbits);
+  // V = (X'X + A0)^-1, chol(V)
+  std::vector<double> G(K * K);
+  for (int t = 0; t < K * K; ++t) G[t] = st->xtx[t] + h->A0[t];
+  if (!spd_inverse(G.data(), mc.V, K)) return fail(h, CLV_ERR_NUMERIC, "X'X + A0 is not positive definite");
+  if (!chol_host(mc.V, mc.LV, K)) return fail(h, CLV_ERR_NUMERIC, "(X'X + A0)^-1 is not positive definite");
+  // centred prior mean B0c = B0 - e0 c'
+  for (int k = 0; k < K; ++k)
+    for (int d = 0; d < D; ++d) mc.B0c[k * D + d] = B0[k * D + d] - (k == 0 ? mc.center[d] : 0.0);
+  for (int k = 0; k < K; ++k)
+    for (int d = 0; d < D; ++d) {
+      double s = 0.0;
+      for (int m = 0; m < K; ++m) s += h->A0[k * K + m] * mc.B0c[m * D + d];
+      mc.A0B0c[k * D + d] = s;
+    }
+  for (int d = 0; d < D; ++d)
+    for (int e = 0; e < D; ++e) {
+      double s = h->gamma0[d * D + e];
+      for (int k = 0; k < K; ++k) s += mc.B0c[k * D + d] * mc.A0B0c[k * D + e];
+      mc.Q0[d * D + e] = s;
+    }
+  mc.nu_n = h->nu0 + (double)h->cfg.n_global;
+  mc.omega2 = (D == 3) ? st->omega2 : 1.0;
+  if (D == 3 && !(mc.omega2 > 0.0)) return fail(h, CLV_ERR_NUMERIC, "omega2 = var(log_s) must be positive");
+  CK(h, cudaMemcpyAsync(h->d_mc, &mc, sizeof mc, cudaMemcpyHostToDevice, h->stream));
+  // initial level-1 state (bi:368-370, tri:489-493) and level-2 placeholders (bi:379, tri:504)
+  const size_t N = (size_t)h->N;
+  std::vector<double> tx(N), buf(N);
+  CK(h, cudaMemcpyAsync(tx.data(), h->d_tx, N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  std::vector<ChainParams> cps(h->chains);
+  for (int c = 0; c < h->chains; ++c) {
+    std::memset(&cps[c], 0, sizeof(ChainParams));
+    for (int t = 0; t < K * D; ++t) cps[c].beta[t] = B0[t];
+    for (int t = 0; t < D * D; ++t) cps[c].Sigma[t] = h->gamma0[t];
+  }
+  const double ll0 = std::log(st->lam_init);
+  for (size_t i = 0; i < N; ++i) buf[i] = ll0;
+  for (int c = 0; c < h->chains; ++c)
+    CK(h, cudaMemcpyAsync(h->d_ll + (size_t)c * N, buf.data(), N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < N; ++i) buf[i] = std::log(1.0 / (tx[i] + 0.5 / st->lam_init));
+  for (int c = 0; c < h->chains; ++c)
+    CK(h, cudaMemcpyAsync(h->d_lm + (size_t)c * N, buf.data(), N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (D == 3) CK(h, cudaMemsetAsync(h->d_le, 0, sizeof(double) * N * h->chains, h->stream));   // eta = 1 (tri:493)
+  CK(h, cudaMemsetAsync(h->d_z, 0, sizeof(double) * N * h->chains, h->stream));
+  CK(h, cudaMemsetAsync(h->d_tau, 0, sizeof(double) * N * h->chains, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_params, cps.data(), sizeof(ChainParams) * h->chains, cudaMemcpyHostToDevice, h->stream));
+  if (D == 2) k_derive_params<2><<<(h->chains + 63) / 64, 64, 0, h->stream>>>(h->d_mc, h->d_params, h->chains);
+  else k_derive_params<3><<<(h->chains + 63) / 64, 64, 0, h->stream>>>(h->d_mc, h->d_params, h->chains);
+  h->launches++;
+  CK(h, cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
+  h->inited = true;
+  if (int r = recompute_stats(h)) return r;
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->sweeps_done = 0;
+  h->resident_draws = 0;
+  return CLV_OK;
+}
+
+int clv_comm_unique_id(void* out128) {
+  if (!out128) return fail(nullptr, CLV_ERR_ARG, "null argument");
+  std::string err;
+  if (!g_nccl.load(err)) return fail(nullptr, CLV_ERR_COMM, "%s", err.c_str());
+  NcclUid id;
+  int r = g_nccl.GetUniqueId(&id);
+  if (r != 0) return fail(nullptr, CLV_ERR_COMM, "ncclGetUniqueId failed (%d)", r);
+  std::memcpy(out128, &id, sizeof id);
+  return CLV_OK;
+}
+
+int clv_comm_init(clv_sampler* h, const void* unique_id128, int rank, int world) {
+  if (!h || !unique_id128) return fail(h, CLV_ERR_ARG, "null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail(h, CLV_ERR_ARG, "bad rank/world");
+  if (h->cfg.sweep_mode == CLV_SWEEP_PERSISTENT) return fail(h, CLV_ERR_ARG, "persistent sweep mode is single-shard only");
+  std::string err;
+  if (!g_nccl.load(err)) return fail(h, CLV_ERR_COMM, "%s", err.c_str());
+  CK(h, cudaSetDevice(h->cfg.device));
+  NcclUid id;
+  std::memcpy(&id, unique_id128, sizeof id);
+  int r = g_nccl.CommInitRank(&h->comm, world, id, rank);
+  if (r != 0) return fail(h, CLV_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  h->world = world; h->rank = rank;
+  return CLV_OK;
+}
+
+int64_t clv_sweeps_done(const clv_sampler* h) { return h ? h->sweeps_done : -1; }
+int64_t clv_kernel_launches(const clv_sampler* h) { return h ? h->launches : -1; }
+
+int clv_set_timing(clv_sampler* h, int on) {
+  if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
+  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  collect_timing(h);
+  h->timing = on != 0;
+  h->t_sweep_ms = h->t_l2_ms = 0; h->t_n = 0;
+  return CLV_OK;
+}
+
+int clv_kernel_time_ms(clv_sampler* h, double* sweep_ms, double* l2_ms, int64_t* n) {
+  if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
+  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  collect_timing(h);
+  if (sweep_ms) *sweep_ms = h->t_sweep_ms;
+  if (l2_ms) *l2_ms = h->t_l2_ms;
+  if (n) *n = h->t_n;
+  h->t_sweep_ms = h->t_l2_ms = 0; h->t_n = 0;
+  return CLV_OK;
+}
+
+int clv_advance(clv_sampler* h, int64_t n_sweeps, int sync) {
+  if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
+  if (!h->inited) return fail(h, CLV_ERR_STATE, "clv_advance: call clv_init_state first");
+  if (h->cfg.rng_mode == CLV_RNG_INJECTED) return fail(h, CLV_ERR_ARG, "handle is in injected-RNG mode; use clv_sweep_injected");
+  CK(h, cudaSetDevice(h->cfg.device));
+  for (int64_t s = 0; s < n_sweeps; ++s) {
+    SweepArgs a = base_args(h);
+    Level2Args l2 = base_l2(h);
+    a.sweep = l2.sweep = (uint32_t)(h->sweeps_done + 1);
+    if (int r = enqueue_sweep(h, a, l2, h->cfg.rng_mode)) return r;
+    if (h->timing && (s & 1023) == 1023) { CK(h, cudaStreamSynchronize(h->stream)); collect_timing(h); }
+  }
+  if (sync) return check_device_error(h);
+  return CLV_OK;
+}
+
+static int ensure_run_buffers(clv_sampler* h, long long n_draws, bool want_level1, long long* chunk_cap) {
+  const long long C = h->chains;
+  if (h->loglik_cap < C * n_draws) {
+    if (h->d_loglik) cudaFree(h->d_loglik);
+    h->d_loglik = nullptr;
+    CK(h, dmalloc(&h->d_loglik, (size_t)(C * n_draws)));
+    h->loglik_cap = C * n_draws;
+  }
+  if (h->level2_cap < C * n_draws * h->P) {
+    if (h->d_level2) cudaFree(h->d_level2);
+    h->d_level2 = nullptr;
+    CK(h, dmalloc(&h->d_level2, (size_t)(C * n_draws * h->P)));
+    h->level2_cap = C * n_draws * h->P;
+  }
+  CK(h, cudaMemsetAsync(h->d_loglik, 0, sizeof(long long) * C * n_draws, h->stream));
+  *chunk_cap = 0;
+  if (!want_level1) return 0;
+  const long long per_draw = C * h->N * h->ncol * (long long)sizeof(double);
+  size_t free_b = 0, total_b = 0;
+  CK(h, cudaMemGetInfo(&free_b, &total_b));
+  long long have = h->draws_cap_bytes[0] + h->draws_cap_bytes[1];
+  long long budget = (long long)((double)(free_b + have) * 0.70);
+  if (const char* env = getenv("CLV_DRAW_BUFFER_BYTES")) budget = std::min(budget, atoll(env));
+  long long cap = n_draws;
+  int nbuf = 1;
+  if (per_draw * n_draws > budget) {
+    nbuf = 2;
+    cap = std::max<long long>(1, budget / (2 * per_draw));
+  }
+  for (int b = 0; b < 2; ++b) {
+    long long need = (b < nbuf) ? cap * per_draw : 0;
+    if (h->draws_cap_bytes[b] < need) {
+      if (h->d_draws[b]) cudaFree(h->d_draws[b]);
+      h->d_draws[b] = nullptr; h->draws_cap_bytes[b] = 0;
+      cudaError_t e = cudaMalloc((void**)&h->d_draws[b], (size_t)need);
+      if (e != cudaSuccess) return fail(h, CLV_ERR_CUDA, "cannot allocate %lld bytes for the draw buffer: %s", need, cudaGetErrorString(e));
+      h->draws_cap_bytes[b] = need;
+    }
+  }
+  *chunk_cap = cap;
+  return 0;
+}
+
+int clv_run(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* level1, double* level2,
+            double* loglik, clv_progress_cb cb, void* user, int64_t trace) {
+  if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
+  if (!h->inited) return fail(h, CLV_ERR_STATE, "clv_run: call clv_init_state first");
+  if (h->cfg.rng_mode == CLV_RNG_INJECTED) return fail(h, CLV_ERR_ARG, "handle is in injected-RNG mode; use clv_sweep_injected");
+  if (burnin < 0 || mcmc < 1 || thin < 1) return fail(h, CLV_ERR_ARG, "clv_run: need burnin >= 0, mcmc >= 1, thin >= 1");
+  if (!level2) return fail(h, CLV_ERR_ARG, "clv_run: level2 output is required");
+  CK(h, cudaSetDevice(h->cfg.device));
+  const long long n_draws = (mcmc - 1) / thin + 1;      // bi:360
+  const long long C = h->chains, N = h->N, nc = h->ncol;
+  long long cap = 0;
+  if (int r = ensure_run_buffers(h, n_draws, level1 != nullptr, &cap)) return r;
+  const long long total = burnin + mcmc;
+  int buf = 0;
+  long long chunk_base = 0;
+  bool used[2] = {false, false};
+  auto flush = [&](long long filled) -> int {
+    // chunk [chunk_base, chunk_base+filled) of every chain -> host, on the copy stream
+    CK(h, cudaEventRecord(h->ev_chunk_ready[buf], h->stream));
+    CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_chunk_ready[buf], 0));
+    for (long long c = 0; c < C; ++c)
+      CK(h, cudaMemcpyAsync(level1 + ((size_t)c * n_draws + chunk_base) * N * nc, h->d_draws[buf] + (size_t)c * cap * N * nc,
+                            (size_t)filled * N * nc * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(h, cudaEventRecord(h->ev_copy_done[buf], h->copy_stream));
+    used[buf] = true;
+    return 0;
+  };
+  for (long long step = 1; step <= total; ++step) {
+    SweepArgs a = base_args(h);
+    Level2Args l2 = base_l2(h);
+    a.sweep = l2.sweep = (uint32_t)(h->sweeps_done + 1);
+    l2.n_draws = n_draws;
+    a.loglik_stride = n_draws;
+    const bool kept = step > burnin && (step - 1 - burnin) % thin == 0;      // bi:402
+    if (kept) {
+      const long long draw = (step - 1 - burnin) / thin;
+      a.draw_index = l2.draw_index = draw;
+      a.slot = 0;
+      if (level1) {
+        a.draws = h->d_draws[buf];
+        a.chunk_cap = cap;
+        a.slot = draw - chunk_base;
+      }
+      a.store_zt = 0;
+    }
+    if (step == total) a.store_zt = 1;
+    if (int r = enqueue_sweep(h, a, l2, h->cfg.rng_mode)) return r;
+    if (kept && level1) {
+      const long long draw = (step - 1 - burnin) / thin;
+      const long long filled = draw - chunk_base + 1;
+      if (filled == cap || draw == n_draws - 1) {
+        if (int r = flush(filled)) return r;
+        chunk_base += filled;
+        if (draw != n_draws - 1) {
+          buf ^= 1;
+          if (used[buf]) CK(h, cudaStreamWaitEvent(h->stream, h->ev_copy_done[buf], 0));
+        }
+      }
+    }
+    if (trace > 0 && step % trace == 0) {                                      // bi:384-385
+      if (int r = check_device_error(h)) return r;
+      if (cb) cb(user, step, total);
+    } else if (h->timing && (step & 1023) == 0) {
+      CK(h, cudaStreamSynchronize(h->stream));
+      collect_timing(h);
+    }
+  }
+  if (int r = check_device_error(h)) return r;
+  CK(h, cudaMemcpyAsync(level2, h->d_level2, sizeof(double) * C * n_draws * h->P, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<long long> ll((size_t)(C * n_draws));
+  CK(h, cudaMemcpyAsync(ll.data(), h->d_loglik, sizeof(long long) * C * n_draws, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, cudaStreamSynchronize(h->copy_stream));
+  if (loglik)
+    for (size_t t = 0; t < ll.size(); ++t) loglik[t] = (double)ll[t] * h->h_mc.ll_inv;
+  h->resident_draws = (level1 && cap >= n_draws) ? n_draws : 0;
+  return CLV_OK;
+}
+
+int clv_get_state(clv_sampler* h, int chain, double* ll, double* lm, double* le, double* z, double* tau,
+                  double* beta, double* Sigma) {
+  if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
+  if (!h->inited) return fail(h, CLV_ERR_STATE, "state not initialised");
+  if (chain < 0 || chain >= h->chains) return fail(h, CLV_ERR_ARG, "chain out of range");
+  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  const size_t N = (size_t)h->N, o = (size_t)chain * N;
+  if (ll) CK(h, cudaMemcpy(ll, h->d_ll + o, N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (lm) CK(h, cudaMemcpy(lm, h->d_lm + o, N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (le && h->D == 3) CK(h, cudaMemcpy(le, h->d_le + o, N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (z) CK(h, cudaMemcpy(z, h->d_z + o, N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (tau) CK(h, cudaMemcpy(tau, h->d_tau + o, N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (beta || Sigma) {
+    ChainParams cp;
+    CK(h, cudaMemcpy(&cp, h->d_params + chain, sizeof cp, cudaMemcpyDeviceToHost));
+    if (beta) std::memcpy(beta, cp.beta, sizeof(double) * h->K * h->D);
+    if (Sigma) std::memcpy(Sigma, cp.Sigma, sizeof(double) * h->D * h->D);
+  }
+  return CLV_OK;
+}
+
+int clv_set_state(clv_sampler* h, int chain, const double* ll, const double* lm, const double* le,
+                  const double* beta, const double* Sigma) {
+  if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
+  if (!h->inited) return fail(h, CLV_ERR_STATE, "state not initialised");
+  if (chain < 0 || chain >= h->chains) return fail(h, CLV_ERR_ARG, "chain out of range");
+  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  const size_t N = (size_t)h->N, o = (size_t)chain * N;
+  if (ll) CK(h, cudaMemcpy(h->d_ll + o, ll, N * sizeof(double), cudaMemcpyHostToDevice));
+  if (lm) CK(h, cudaMemcpy(h->d_lm + o, lm, N * sizeof(double), cudaMemcpyHostToDevice));
+  if (le && h->D == 3) CK(h, cudaMemcpy(h->d_le + o, le, N * sizeof(double), cudaMemcpyHostToDevice));
+  if (beta || Sigma) {
+    ChainParams cp;
+    CK(h, cudaMemcpy(&cp, h->d_params + chain, sizeof cp, cudaMemcpyDeviceToHost));
+    if (beta) std::memcpy(cp.beta, beta, sizeof(double) * h->K * h->D);
+    if (Sigma) std::memcpy(cp.Sigma, Sigma, sizeof(double) * h->D * h->D);
+    CK(h, cudaMemcpy(h->d_params + chain, &cp, sizeof cp, cudaMemcpyHostToDevice));
+    if (h->D == 2) k_derive_params<2><<<(h->chains + 63) / 64, 64, 0, h->stream>>>(h->d_mc, h->d_params, h->chains);
+    else k_derive_params<3><<<(h->chains + 63) / 64, 64, 0, h->stream>>>(h->d_mc, h->d_params, h->chains);
+    h->launches++;
+  }
+  if (int r = recompute_stats(h)) return r;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return CLV_OK;
+}
+
+int clv_sweep_injected(clv_sampler* h, const clv_injected* v, int keep, double* level1, double* level2,
+                       double* loglik) {
+  if (!h || !v) return fail(h, CLV_ERR_ARG, "null argument");
+  if (!h->inited) return fail(h, CLV_ERR_STATE, "clv_sweep_injected: call clv_init_state first");
+  if (h->comm) return fail(h, CLV_ERR_ARG, "injected sweeps are single-shard only");
+  const int D = h->D, K = h->K, S = h->S;
+  if (!v->u_z || !v->e_tau || !v->u_tau || !v->iw_chi2 || !v->beta_norm || (S > 0 && (!v->t3_l || !v->t3_m || !v->u_acc)) ||
+      (D == 3 && !v->n_eta) || !v->iw_norm)
+    return fail(h, CLV_ERR_ARG, "clv_sweep_injected: missing variate array");
+  CK(h, cudaSetDevice(h->cfg.device));
+  const long long C = h->chains, N = h->N;
+  const long long n_cn = C * N, n_csn = C * S * N, ntril = D * (D - 1) / 2;
+  const long long tot = 3 * n_cn + 3 * n_csn + (D == 3 ? n_cn : 0) + C * (ntril + D + D * K);
+  if (h->inj_cap < tot) {
+    if (h->d_inj) cudaFree(h->d_inj);
+    h->d_inj = nullptr;
+    CK(h, dmalloc(&h->d_inj, (size_t)tot));
+    h->inj_cap = tot;
+  }
+  long long cap = 0;
+  if (int r = ensure_run_buffers(h, 1, keep && level1, &cap)) return r;
+  double* p = h->d_inj;
+  auto up = [&](const double* src, long long n) -> const double* {
+    double* dst = p;
+    if (n > 0) cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    p += n;
+    return dst;
+  };
+  SweepArgs a = base_args(h);
+  Level2Args l2 = base_l2(h);
+  a.u_z = up(v->u_z, n_cn); a.e_tau = up(v->e_tau, n_cn); a.u_tau = up(v->u_tau, n_cn);
+  a.t3_l = up(v->t3_l, n_csn); a.t3_m = up(v->t3_m, n_csn); a.u_acc = up(v->u_acc, n_csn);
+  a.n_eta = (D == 3) ? up(v->n_eta, n_cn) : nullptr;
+  l2.iw_norm = up(v->iw_norm, C * ntril); l2.iw_chi2 = up(v->iw_chi2, C * D); l2.beta_norm = up(v->beta_norm, C * D * K);
+  l2.injected = 1;
+  CK(h, cudaGetLastError());
+  a.sweep = l2.sweep = (uint32_t)(h->sweeps_done + 1);
+  a.store_zt = 1;
+  l2.n_draws = 1; a.loglik_stride = 1;
+  if (keep) {
+    a.slot = 0; a.draw_index = 0; l2.draw_index = 0;
+    if (level1) { a.draws = h->d_draws[0]; a.chunk_cap = cap; }
+  }
+  if (int r = enqueue_sweep(h, a, l2, MODE_INJECT)) return r;
+  if (int r = check_device_error(h)) return r;
+  if (keep) {
+    if (level1)
+      for (long long c = 0; c < C; ++c)
+        CK(h, cudaMemcpy(level1 + (size_t)c * N * h->ncol, h->d_draws[0] + (size_t)c * cap * N * h->ncol,
+                         (size_t)N * h->ncol * sizeof(double), cudaMemcpyDeviceToHost));
+    if (level2) CK(h, cudaMemcpy(level2, h->d_level2, sizeof(double) * C * h->P, cudaMemcpyDeviceToHost));
+    if (loglik) {
+      std::vector<long long> ll((size_t)C);
+      CK(h, cudaMemcpy(ll.data(), h->d_loglik, sizeof(long long) * C, cudaMemcpyDeviceToHost));
+      for (long long c = 0; c < C; ++c) loglik[c] = (double)ll[c] * h->h_mc.ll_inv;
+    }
+  }
+  h->resident_draws = 0;
+  return CLV_OK;
+}
+
+// ---- forecast ---------------------------------------------------------------------------------
+static int launch_forecast(const clv_forecast_config* cfg, ForecastArgs a, bool inject, cudaStream_t st) {
+  const long long N = cfg->n_customers;
+  int gx = (int)std::min<long long>((N + 255) / 256, 65535);
+  int gy = (int)std::max<long long>(1, std::min<long long>(cfg->n_draws_total, 148ll * 8 * 4 / std::max(1, gx) + 1));
+  gy = std::min(gy, 65535);
+  dim3 grid(gx, gy);
+  if (cfg->ncol == 4) {
+    if (inject) k_forecast<4, true><<<grid, 256, 0, st>>>(a);
+    else k_forecast<4, false><<<grid, 256, 0, st>>>(a);
+  } else {
+    if (inject) k_forecast<5, true><<<grid, 256, 0, st>>>(a);
+    else k_forecast<5, false><<<grid, 256, 0, st>>>(a);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, CLV_ERR_CUDA, "forecast launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+static int check_fc(const clv_forecast_config* cfg) {
+  if (!cfg) return fail(nullptr, CLV_ERR_ARG, "null forecast config");
+  if (cfg->ncol != 4 && cfg->ncol != 5) return fail(nullptr, CLV_ERR_ARG, "ncol must be 4 or 5");
+  if (cfg->n_draws_total < 1 || cfg->n_customers < 1) return fail(nullptr, CLV_ERR_ARG, "empty forecast");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(nullptr, CLV_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, CLV_ERR_ARG, "device out of range");
+  return 0;
+}
+
+static int upload_rk() {
+  static bool done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && done[dev]) return 0;
+  double rk[RK_TABLE + 1];
+  rk[0] = 0.0;
+  for (int k = 1; k <= RK_TABLE; ++k) rk[k] = 1.0 / (double)k;
+  cudaError_t e = cudaMemcpyToSymbol(c_rk, rk, sizeof rk);
+  if (e != cudaSuccess) return fail(nullptr, CLV_ERR_CUDA, "cudaMemcpyToSymbol failed: %s", cudaGetErrorString(e));
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return 0;
+}
+
+int clv_forecast_dev(const clv_forecast_config* cfg, const double* level1_dev, const double* T_cal_dev,
+                     int64_t* x_star_dev, double* spend_dev, void* stream) {
+  if (int r = check_fc(cfg)) return r;
+  CK(nullptr, cudaSetDevice(cfg->device));
+  if (int r = upload_rk()) return r;
+  ForecastArgs a{};
+  a.level1 = level1_dev; a.T_cal = T_cal_dev; a.n_draws = cfg->n_draws_total; a.N = cfg->n_customers;
+  a.T_star = cfg->T_star; a.sigma_s = cfg->sigma_s; a.seed = cfg->seed;
+  a.gid_offset = cfg->gid_offset; a.draw_offset = cfg->draw_offset;
+  a.x_out = (long long*)x_star_dev; a.spend_out = cfg->simulate_spend ? spend_dev : nullptr;
+  return launch_forecast(cfg, a, false, (cudaStream_t)stream);
+}
+
+// Host-buffer forecast: draws are streamed through the device in chunks on two streams (PCIe-bound).
+static int forecast_host(const clv_forecast_config* cfg, const double* level1, const double* T_cal, const double* u,
+                         const double* eps, int64_t n_eps, const int64_t* eps_offset, int64_t* x_star, double* spend,
+                         bool inject) {
+  if (int r = check_fc(cfg)) return r;
+  if (!level1 || !T_cal || !x_star) return fail(nullptr, CLV_ERR_ARG, "clv_forecast: null buffer");
+  if (inject && !u) return fail(nullptr, CLV_ERR_ARG, "clv_forecast_injected: u is required");
+  const bool want_spend = cfg->simulate_spend && cfg->ncol == 5 && spend;
+  if (inject && want_spend && (!eps || !eps_offset)) return fail(nullptr, CLV_ERR_ARG, "clv_forecast_injected: eps/eps_offset required for spend");
+  CK(nullptr, cudaSetDevice(cfg->device));
+  if (int r = upload_rk()) return r;
+  const long long N = cfg->n_customers, nd = cfg->n_draws_total, nc = cfg->ncol;
+  size_t free_b = 0, total_b = 0;
+  CK(nullptr, cudaMemGetInfo(&free_b, &total_b));
+  const long long per_draw = N * (nc * 8 + 8 + (want_spend ? 8 : 0) + (inject ? 16 : 0));
+  long long chunk = std::max<long long>(1, std::min<long long>(nd, (long long)(free_b * 0.35) / std::max<long long>(1, per_draw)));
+  chunk = std::min<long long>(chunk, std::max<long long>(1, (1ll << 28) / std::max<long long>(1, N * nc * 8)));  // ~256 MB pieces pipeline well
+  cudaStream_t st[2];
+  double *d_l1[2] = {nullptr, nullptr}, *d_sp[2] = {nullptr, nullptr}, *d_u[2] = {nullptr, nullptr}, *d_T = nullptr, *d_eps = nullptr;
+  long long *d_x[2] = {nullptr, nullptr}, *d_off[2] = {nullptr, nullptr};
+  int rc = 0;
+  auto cleanup = [&]() {
+    for (int b = 0; b < 2; ++b) {
+      if (d_l1[b]) cudaFree(d_l1[b]);
+      if (d_sp[b]) cudaFree(d_sp[b]);
+      if (d_u[b]) cudaFree(d_u[b]);
+      if (d_x[b]) cudaFree(d_x[b]);
+      if (d_off[b]) cudaFree(d_off[b]);
+      cudaStreamDestroy(st[b]);
+    }
+    if (d_T) cudaFree(d_T);
+    if (d_eps) cudaFree(d_eps);
+  };
+  for (int b = 0; b < 2; ++b) cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking);
+#define CKF(call) do { cudaError_t e3 = (call); if (e3 != cudaSuccess) { rc = fail(nullptr, CLV_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e3)); cleanup(); return rc; } } while (0)
+  CKF(dmalloc(&d_T, (size_t)N));
+  CKF(cudaMemcpy(d_T, T_cal, (size_t)N * 8, cudaMemcpyHostToDevice));
+  for (int b = 0; b < 2; ++b) {
+    CKF(dmalloc(&d_l1[b], (size_t)(chunk * N * nc)));
+    CKF(dmalloc(&d_x[b], (size_t)(chunk * N)));
+    if (want_spend) CKF(dmalloc(&d_sp[b], (size_t)(chunk * N)));
+    if (inject) { CKF(dmalloc(&d_u[b], (size_t)(chunk * N))); if (want_spend) CKF(dmalloc(&d_off[b], (size_t)(chunk * N))); }
+  }
+  if (inject && want_spend) {
+    CKF(dmalloc(&d_eps, (size_t)n_eps));
+    CKF(cudaMemcpy(d_eps, eps, (size_t)n_eps * 8, cudaMemcpyHostToDevice));
+  }
+  int b = 0;
+  for (long long d0 = 0; d0 < nd; d0 += chunk, b ^= 1) {
+    const long long n = std::min(chunk, nd - d0);
+    CKF(cudaMemcpyAsync(d_l1[b], level1 + (size_t)d0 * N * nc, (size_t)(n * N * nc) * 8, cudaMemcpyHostToDevice, st[b]));
+    if (inject) {
+      CKF(cudaMemcpyAsync(d_u[b], u + (size_t)d0 * N, (size_t)(n * N) * 8, cudaMemcpyHostToDevice, st[b]));
+      if (want_spend) CKF(cudaMemcpyAsync(d_off[b], eps_offset + (size_t)d0 * N, (size_t)(n * N) * 8, cudaMemcpyHostToDevice, st[b]));
+    }
+    clv_forecast_config c2 = *cfg;
+    c2.n_draws_total = n;
+    c2.draw_offset = cfg->draw_offset + d0;
+    ForecastArgs a{};
+    a.level1 = d_l1[b]; a.T_cal = d_T; a.n_draws = n; a.N = N; a.T_star = cfg->T_star; a.sigma_s = cfg->sigma_s;
+    a.seed = cfg->seed; a.gid_offset = cfg->gid_offset; a.draw_offset = c2.draw_offset;
+    a.u = d_u[b]; a.eps = d_eps; a.eps_offset = d_off[b];
+    a.x_out = d_x[b]; a.spend_out = want_spend ? d_sp[b] : nullptr;
+    if ((rc = launch_forecast(&c2, a, inject, st[b]))) { cleanup(); return rc; }
+    CKF(cudaMemcpyAsync(x_star + (size_t)d0 * N, d_x[b], (size_t)(n * N) * 8, cudaMemcpyDeviceToHost, st[b]));
+    if (want_spend) CKF(cudaMemcpyAsync(spend + (size_t)d0 * N, d_sp[b], (size_t)(n * N) * 8, cudaMemcpyDeviceToHost, st[b]));
+  }
+  CKF(cudaStreamSynchronize(st[0]));
+  CKF(cudaStreamSynchronize(st[1]));
+#undef CKF
+  cleanup();
+  return CLV_OK;
+}
+
+int clv_forecast(const clv_forecast_config* cfg, const double* level1, const double* T_cal, int64_t* x_star, double* spend) {
+  return forecast_host(cfg, level1, T_cal, nullptr, nullptr, 0, nullptr, x_star, spend, false);
+}
+
+int clv_forecast_injected(const clv_forecast_config* cfg, const double* level1, const double* T_cal, const double* u,
+                          const double* eps, int64_t n_eps, const int64_t* eps_offset, int64_t* x_star, double* spend) {
+  return forecast_host(cfg, level1, T_cal, u, eps, n_eps, eps_offset, x_star, spend, true);
+}
+
+int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t* x_star, double* mean_x_star, double* p_alive) {
+  if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
+  if (h->resident_draws <= 0) return fail(h, CLV_ERR_STATE, "no resident draws: run clv_run with a level1 buffer that fits in one device chunk");
+  CK(h, cudaSetDevice(h->cfg.device));
+  if (int r = upload_rk()) return r;
+  const long long C = h->chains, nd = h->resident_draws, N = h->N;
+  double *d_mx = nullptr, *d_pa = nullptr;
+  long long* d_x = nullptr;
+  CK(h, dmalloc(&d_mx, (size_t)N));
+  CK(h, dmalloc(&d_pa, (size_t)N));
+  if (x_star) CK(h, dmalloc(&d_x, (size_t)(C * nd * N)));
+  ForecastArgs a{};
+  // resident layout [chains][nd][N][ncol] with cap == nd is exactly the chain-major (chains*nd, N, ncol) of bi:530-531
+  a.level1 = h->d_draws[0]; a.T_cal = h->d_T; a.n_draws = C * nd; a.N = N; a.T_star = T_star; a.sigma_s = 0.5;
+  a.seed = seed; a.gid_offset = h->cfg.gid_offset; a.draw_offset = 0; a.x_out = d_x; a.spend_out = nullptr;
+  int gx = (int)std::min<long long>((N + 255) / 256, 65535);
+  if (h->ncol == 4) k_forecast_reduce<4><<<gx, 256, 0, h->stream>>>(a, d_mx, d_pa);
+  else k_forecast_reduce<5><<<gx, 256, 0, h->stream>>>(a, d_mx, d_pa);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && mean_x_star) e = cudaMemcpyAsync(mean_x_star, d_mx, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && p_alive) e = cudaMemcpyAsync(p_alive, d_pa, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && x_star) e = cudaMemcpyAsync(x_star, d_x, (size_t)(C * nd * N) * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_mx); cudaFree(d_pa);
+  if (d_x) cudaFree(d_x);
+  if (e != cudaSuccess) return fail(h, CLV_ERR_CUDA, "clv_forecast_resident failed: %s", cudaGetErrorString(e));
+  return CLV_OK;
+}
+
+// ---- generator --------------------------------------------------------------------------------
+int clv_generate(const clv_generate_config* cfg, const double* beta, const double* gamma, int X_given, int T_cal_given,
+                 int32_t* x, double* t_x, double* T_cal, double* X, int32_t* x_star, double* lambda_true,
+                 double* mu_true, double* tau_true) {
+  if (!cfg || !beta || !gamma || !x || !t_x || !T_cal || !X) return fail(nullptr, CLV_ERR_ARG, "clv_generate: null argument");
+  if (cfg->n_cov < 1 || cfg->n_cov > CLV_MAX_K || cfg->n < 1) return fail(nullptr, CLV_ERR_ARG, "clv_generate: bad n / n_cov");
+  int ndev = 0;
+  cudaError_t e0 = cudaGetDeviceCount(&ndev);
+  if (e0 != cudaSuccess || ndev == 0) return fail(nullptr, CLV_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
+  CK(nullptr, cudaSetDevice(cfg->device));
+  if (int r = upload_rk()) return r;
+  const long long n = cfg->n;
+  const int K = cfg->n_cov;
+  GenerateArgs a{};
+  a.n = n; a.gid_offset = cfg->gid_offset; a.K = K; a.seed = cfg->seed;
+  a.T_cal_lo = cfg->T_cal_lo; a.T_cal_hi = cfg->T_cal_hi; a.T_star = cfg->T_star;
+  std::memcpy(a.beta, beta, sizeof(double) * K * 2);
+  if (!chol_host(gamma, a.Lg, 2)) return fail(nullptr, CLV_ERR_NUMERIC, "gamma is not positive definite");
+  int rc = 0;
+  std::vector<void*> allocs;
+  auto dm = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, std::max<size_t>(bytes, 8)) != cudaSuccess) { rc = -1; return nullptr; } allocs.push_back(p); return p; };
+  a.x = (int*)dm(n * 4); a.t_x = (double*)dm(n * 8); a.T_cal = (double*)dm(n * 8);
+  a.Xc = (double*)dm((size_t)n * 8 * std::max(K - 1, 1));
+  a.x_star = x_star ? (int*)dm(n * 4) : nullptr;
+  a.lam = lambda_true ? (double*)dm(n * 8) : nullptr;
+  a.mu = mu_true ? (double*)dm(n * 8) : nullptr;
+  a.tau = tau_true ? (double*)dm(n * 8) : nullptr;
+  auto cleanup = [&]() { for (void* p : allocs) cudaFree(p); };
+  if (rc) { cleanup(); return fail(nullptr, CLV_ERR_CUDA, "clv_generate: out of device memory"); }
+  a.X_given = X_given; a.T_given = T_cal_given;
+  if (T_cal_given && cudaMemcpy(a.T_cal, T_cal, n * 8, cudaMemcpyHostToDevice) != cudaSuccess) rc = -1;
+  for (int k = 1; k < K && X_given && !rc; ++k)
+    if (cudaMemcpy2D(a.Xc + (size_t)(k - 1) * n, 8, X + k, (size_t)K * 8, 8, (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) rc = -1;
+  if (rc) { cleanup(); return fail(nullptr, CLV_ERR_CUDA, "clv_generate: input upload failed"); }
+  k_generate<<<(int)std::min<long long>((n + 255) / 256, 148 * 32), 256>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(x, a.x, n * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(t_x, a.t_x, n * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(T_cal, a.T_cal, n * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && x_star) e = cudaMemcpy(x_star, a.x_star, n * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && lambda_true) e = cudaMemcpy(lambda_true, a.lam, n * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && mu_true) e = cudaMemcpy(mu_true, a.mu, n * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && tau_true) e = cudaMemcpy(tau_true, a.tau, n * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) {
+    // X row-major n x K with intercept column
+    std::vector<double> ones((size_t)n, 1.0);
+    e = cudaMemcpy2D(X, (size_t)K * 8, ones.data(), 8, 8, (size_t)n, cudaMemcpyHostToHost);
+    for (int k = 1; k < K && e == cudaSuccess; ++k)
+      e = cudaMemcpy2D(X + k, (size_t)K * 8, a.Xc + (size_t)(k - 1) * n, 8, 8, (size_t)n, cudaMemcpyDeviceToHost);
+  }
+  cleanup();
+  if (e != cudaSuccess) return fail(nullptr, CLV_ERR_CUDA, "clv_generate failed: %s", cudaGetErrorString(e));
+  return CLV_OK;
+}
+
+// ---- issue-rate peaks ---------------------------------------------------------------------------
+int clv_measure_issue_peaks(int device, double* out4) {
+  if (!out4) return fail(nullptr, CLV_ERR_ARG, "null argument");
+  int ndev = 0;
+  cudaError_t e0 = cudaGetDeviceCount(&ndev);
+  if (e0 != cudaSuccess || ndev == 0) return fail(nullptr, CLV_ERR_CUDA, "no CUDA device available");
+  CK(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(nullptr, cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  float* d_out = nullptr;
+  CK(nullptr, dmalloc(&d_out, (size_t)blocks * threads));
+  cudaEvent_t e1, e2;
+  cudaEventCreate(&e1); cudaEventCreate(&e2);
+  for (int w = 0; w < 4; ++w) {
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+      cudaEventRecord(e1);
+      if (w == 0) k_peak<0><<<blocks, threads>>>(d_out, iters, 1.0f);
+      else if (w == 1) k_peak<1><<<blocks, threads>>>(d_out, iters, 1.0f);
+      else if (w == 2) k_peak<2><<<blocks, threads>>>(d_out, iters, 1.0f);
+      else k_peak<3><<<blocks, threads>>>(d_out, iters, 1.0f);
+      cudaEventRecord(e2);
+      cudaEventSynchronize(e2);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e1, e2);
+      double ops = (double)blocks * threads * iters * 8.0;
+      if (rep > 0) best = std::max(best, ops / (ms * 1e-3) / 1e9);
+    }
+    out4[w] = best;
+  }
+  cudaEventDestroy(e1); cudaEventDestroy(e2);
+  cudaFree(d_out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, CLV_ERR_CUDA, "peak kernels failed: %s", cudaGetErrorString(e));
+  return CLV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+// clv_forecast.cuh — posterior-predictive kernels: draw_future_transactions (bi:506-546, tri:660-749),
+// the fused per-customer reductions the analysis scripts take over its output (mean x*, P(alive):
+// utils/analysis_bi_helpers.py:75-110), and the synthetic-customer generator (bi:95-187).
+// HBM-bound: one 32/40-byte level-1 row in, one int64 (+ one double) out per (draw, customer) cell.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "clv_rng.cuh"
+
+namespace clv {
+
+constexpr int RK_TABLE = 64;
+__constant__ double c_rk[RK_TABLE + 1];   // c_rk[k] = 1.0 / k
+
+// Poisson draw by sequential CDF inversion from zero; arithmetic fixed to match
+// oracle/abe_oracle.py:poisson_inversion bit for bit.
+__device__ __forceinline__ long long poisson_inversion(double m, double u) {
+  double p = exp(-m), cdf = p;
+  long long k = 0;
+  const double cap = floor(4096.0 + 16.0 * m);
+  while (u > cdf && (double)k < cap) {
+    ++k;
+    double rk = (k <= RK_TABLE) ? c_rk[k] : 1.0 / (double)k;
+    p = (p * m) * rk;
+    cdf += p;
+  }
+  return k;
+}
+
+__device__ __forceinline__ double future_horizon(double T_cal, double tau, double zf, double T_star) {
+  // bi:535-540: alive -> T_star ; churned -> clip(tau - T_cal, 0, T_star)
+  return (zf > 0.5) ? T_star : fmin(fmax(tau - T_cal, 0.0), T_star);
+}
+
+struct ForecastArgs {
+  const double* level1;   // [n_draws][N][NCOL]
+  const double* T_cal;    // [N]
+  long long n_draws, N;
+  double T_star, sigma_s;
+  uint64_t seed;
+  long long gid_offset, draw_offset;
+  const double* u;               // injected uniforms [n_draws][N]
+  const double* eps;             // injected per-transaction normals (flat)
+  const long long* eps_offset;   // [n_draws][N]
+  long long* x_out;              // [n_draws][N] (nullable)
+  double* spend_out;             // [n_draws][N] (nullable)
+};
+
+template <int NCOL, bool INJECT>
+__global__ void __launch_bounds__(256) k_forecast(ForecastArgs a) {
+  const PhiloxKey key = chain_key(a.seed, 0u);
+  const bool spend = (NCOL == 5) && a.spend_out != nullptr;
+  for (long long d = blockIdx.y; d < a.n_draws; d += gridDim.y) {
+    const uint32_t gdraw = (uint32_t)(a.draw_offset + d);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.N;
+         i += (long long)gridDim.x * blockDim.x) {
+      const long long cell = d * a.N + i;
+      const double* row = a.level1 + cell * NCOL;
+      double lam, tau, zf, eta = 0.0;
+      if (NCOL == 4) {
+        double2 r0 = reinterpret_cast<const double2*>(row)[0];
+        double2 r1 = reinterpret_cast<const double2*>(row)[1];
+        lam = r0.x; tau = r1.x; zf = r1.y;
+      } else {
+        lam = row[0]; tau = row[2]; zf = row[3]; eta = row[4];
+      }
+      const double h = future_horizon(a.T_cal[i], tau, zf, a.T_star);
+      const uint32_t gid = (uint32_t)(a.gid_offset + i);
+      double u;
+      if (INJECT) u = a.u[cell];
+      else {
+        uint4 r = philox4x32_10(gid, gdraw, 0u, DOM_FORECAST, key);
+        u = u53(r.x, r.y);
+      }
+      const long long xs = poisson_inversion(lam * h, u);                 // bi:543
+      if (a.x_out) a.x_out[cell] = xs;
+      if (spend) {
+        // tri:730-737: sum of x* log-normal transactions, log-mean = eta column as stored (Q7)
+        double tot = 0.0;
+        for (long long j = 0; j < xs; ++j) {
+          double n;
+          if (INJECT) n = a.eps[a.eps_offset[cell] + j];
+          else {
+            double nc, ns;
+            normal_pair_u53(philox4x32_10(gid, gdraw, 1u + (uint32_t)(j >> 1), DOM_FORECAST, key), &nc, &ns);
+            n = (j & 1) ? ns : nc;
+          }
+          tot += exp(eta + a.sigma_s * n);
+        }
+        a.spend_out[cell] = tot;
+      }
+    }
+  }
+}
+
+// One thread per customer walks all resident draws: mean x*, P(alive) = mean z without materialising x*.
+template <int NCOL>
+__global__ void __launch_bounds__(256) k_forecast_reduce(ForecastArgs a, double* mean_x, double* p_alive) {
+  const PhiloxKey key = chain_key(a.seed, 0u);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.N;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double T = a.T_cal[i];
+    const uint32_t gid = (uint32_t)(a.gid_offset + i);
+    double sx = 0.0, sz = 0.0;
+    for (long long d = 0; d < a.n_draws; ++d) {
+      const double* row = a.level1 + (d * a.N + i) * NCOL;
+      const double lam = row[0], tau = row[2], zf = row[3];
+      const double h = future_horizon(T, tau, zf, a.T_star);
+      uint4 r = philox4x32_10(gid, (uint32_t)(a.draw_offset + d), 0u, DOM_FORECAST, key);
+      const long long xs = poisson_inversion(lam * h, u53(r.x, r.y));
+      if (a.x_out) a.x_out[d * a.N + i] = xs;
+      sx += (double)xs;
+      sz += (zf > 0.5) ? 1.0 : 0.0;
+    }
+    if (mean_x) mean_x[i] = sx / (double)a.n_draws;
+    if (p_alive) p_alive[i] = sz / (double)a.n_draws;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic customers (law of generate_pareto_abe, bi:95-187, without the per-customer event loop)
+// ------------------------------------------------------------------------------------------------
+struct GenerateArgs {
+  long long n, gid_offset;
+  int K;
+  uint64_t seed;
+  double T_cal_lo, T_cal_hi, T_star;
+  double beta[16 * 2];
+  double Lg[4];        // chol(gamma), lower
+  int* x;
+  double* t_x;
+  double* T_cal;
+  double* Xc;          // [(K-1)][n]
+  int X_given, T_given; // covariates / T_cal supplied by the caller instead of drawn
+  int* x_star;
+  double *lam, *mu, *tau;
+};
+
+__global__ void __launch_bounds__(256) k_generate(GenerateArgs a) {
+  const PhiloxKey key = chain_key(a.seed, 0u);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t gid = (uint32_t)(a.gid_offset + i);
+    double m0 = a.beta[0], m1 = a.beta[1];
+    for (int k = 1; k < a.K; ++k) {                         // X = [1, U(-1,1)^(K-1)]    bi:118-122
+      double xk;
+      if (a.X_given) xk = a.Xc[(long long)(k - 1) * a.n + i];
+      else {
+        uint4 r = philox4x32_10(gid, (uint32_t)k, 0u, DOM_GENERATOR, key);
+        xk = 2.0 * u53(r.x, r.y) - 1.0;
+        a.Xc[(long long)(k - 1) * a.n + i] = xk;
+      }
+      m0 = fma(xk, a.beta[k * 2 + 0], m0);
+      m1 = fma(xk, a.beta[k * 2 + 1], m1);
+    }
+    double n0, n1;
+    normal_pair_u53(philox4x32_10(gid, 0u, 1u, DOM_GENERATOR, key), &n0, &n1);
+    const double lam = exp(m0 + a.Lg[0] * n0);                           // theta = exp(X beta + MVN(0, gamma))  bi:133-136
+    const double mu = exp(m1 + a.Lg[2] * n0 + a.Lg[3] * n1);
+    uint4 r2 = philox4x32_10(gid, 0u, 2u, DOM_GENERATOR, key);
+    const double tau = -log(u53(r2.x, r2.y)) / mu;                       // bi:137
+    const double T = a.T_given ? a.T_cal[i] : a.T_cal_lo + (a.T_cal_hi - a.T_cal_lo) * u53(r2.z, r2.w);
+    uint4 r3 = philox4x32_10(gid, 0u, 3u, DOM_GENERATOR, key);
+    uint4 r4 = philox4x32_10(gid, 0u, 4u, DOM_GENERATOR, key);
+    const double Teff = fmin(tau, T);
+    const long long x = poisson_inversion(lam * Teff, u53(r3.x, r3.y));  // events in (0, min(tau, T_cal)]  bi:149-162
+    const double tx = (x > 0) ? Teff * pow(u53(r3.z, r3.w), 1.0 / (double)x) : 0.0;   // last of x uniform event times
+    const double hold = fmax(0.0, fmin(tau, T + a.T_star) - T);
+    const long long xs = poisson_inversion(lam * hold, u53(r4.x, r4.y));  // bi:172-181
+    a.x[i] = (int)x;
+    a.t_x[i] = tx;
+    a.T_cal[i] = T;
+    if (a.x_star) a.x_star[i] = (int)xs;
+    if (a.lam) a.lam[i] = lam;
+    if (a.mu) a.mu[i] = mu;
+    if (a.tau) a.tau[i] = tau;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// issue-rate micro-benchmarks (roofline denominators for an instruction-bound kernel)
+// ------------------------------------------------------------------------------------------------
+template <int WHICH>
+__global__ void __launch_bounds__(256) k_peak(float* out, int iters, float seedf) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (WHICH == 0) {          // FFMA
+    float a0 = seedf + tid, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const float m = 1.0000001f, c = 1e-7f;
+    for (int i = 0; i < iters; ++i) {
+      a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+    out[tid] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  } else if (WHICH == 1) {   // IMAD (32-bit)
+    uint32_t a0 = tid, a1 = tid + 1, a2 = tid + 2, a3 = tid + 3, a4 = tid + 4, a5 = tid + 5, a6 = tid + 6, a7 = tid + 7;
+    const uint32_t m = 0xD2511F53u + (uint32_t)seedf;
+    for (int i = 0; i < iters; ++i) {
+      a0 = a0 * m + a1; a1 = a1 * m + a2; a2 = a2 * m + a3; a3 = a3 * m + a4;
+      a4 = a4 * m + a5; a5 = a5 * m + a6; a6 = a6 * m + a7; a7 = a7 * m + a0;
+    }
+    out[tid] = (float)(a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7);
+  } else if (WHICH == 2) {   // MUFU.EX2
+    float a0 = seedf + 1e-3f * tid, a1 = a0 + .1f, a2 = a0 + .2f, a3 = a0 + .3f, a4 = a0 + .4f, a5 = a0 + .5f, a6 = a0 + .6f, a7 = a0 + .7f;
+    for (int i = 0; i < iters; ++i) {
+      a0 = exp2f(-a0); a1 = exp2f(-a1); a2 = exp2f(-a2); a3 = exp2f(-a3);
+      a4 = exp2f(-a4); a5 = exp2f(-a5); a6 = exp2f(-a6); a7 = exp2f(-a7);
+    }
+    out[tid] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  } else {                   // DFMA
+    double a0 = seedf + tid, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[tid] = (float)(a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7);
+  }
+}
+
+}  // namespace clv

@@ -1,0 +1,107 @@
+// clv_rng.cuh — counter-based random numbers for the sampler.
+//
+// Philox4x32-10 keyed by (seed + global chain index), counter (customer_gid, sweep, slot, domain):
+// a draw depends only on WHICH customer/chain/sweep it belongs to, never on the thread, block,
+// shard or GPU that computes it.  oracle/philox_np.py restates this contract in NumPy; the STRICT
+// transforms below (fp64) are what it reproduces, the FAST ones (fp32 through the SFU: MUFU.LG2 /
+// MUFU.SIN / MUFU.COS / MUFU.RSQ) draw from the same laws.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace clv {
+
+enum : uint32_t { DOM_SAMPLER = 0, DOM_LEVEL2 = 1, DOM_FORECAST = 2, DOM_GENERATOR = 3 };
+
+struct PhiloxKey {
+  uint32_t k0, k1;
+};
+
+__host__ __device__ inline PhiloxKey chain_key(uint64_t seed, uint32_t global_chain) {
+  uint64_t s = seed + (uint64_t)global_chain;
+  return PhiloxKey{(uint32_t)s, (uint32_t)(s >> 32)};
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, PhiloxKey key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  uint32_t k0 = key.k0, k1 = key.k1;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// ---- uniforms ---------------------------------------------------------------------------------
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+  uint64_t m = ((uint64_t)(a >> 5) << 26) + (uint64_t)(b >> 6);
+  return ((double)m + 0.5) * 0x1.0p-53;
+}
+__device__ __forceinline__ double u32d(uint32_t a) { return ((double)a + 0.5) * 0x1.0p-32; }
+__device__ __forceinline__ float u24f(uint32_t a) { return ((float)(a >> 8) + 0.5f) * 0x1.0p-24f; }
+
+// ---- Student t(3) without rejection: N0 / sqrt((N1^2 - 2 ln U3)/3) ---------------------------------
+__device__ __forceinline__ double t3_strict(uint32_t ra, uint32_t rb, uint32_t rc) {
+  double u1 = u32d(ra), u2 = u32d(rb), u3 = u32d(rc);
+  double r = sqrt(-2.0 * log(u1));
+  double ang = 6.283185307179586476925286766559 * u2;
+  double s, c;
+  sincos(ang, &s, &c);
+  double n0 = r * c, n1 = r * s;
+  double chi2 = n1 * n1 + (-2.0 * log(u3));
+  return n0 / sqrt(chi2 / 3.0);
+}
+
+__device__ __forceinline__ float t3_fast(uint32_t ra, uint32_t rb, uint32_t rc) {
+  constexpr float NEG2LN2 = -1.3862943611198906f;  // -2 ln 2
+  float u1 = u24f(ra), u2 = u24f(rb), u3 = u24f(rc);
+  float r2 = NEG2LN2 * __log2f(u1);                 // -2 ln u1
+  float ang = 6.2831853071795865f * u2;
+  float s, c;
+  __sincosf(ang, &s, &c);
+  // n0 = sqrt(r2) c ; n1^2 = r2 s^2 ; t = n0 * rsqrt((n1^2 + e)/3)
+  float chi2 = fmaf(r2 * s, s, NEG2LN2 * __log2f(u3));
+  return c * sqrtf(r2) * rsqrtf(chi2 * 0.33333333333333333f);
+}
+
+// two standard normals from four words (53-bit uniforms, fp64): cos / sin branch
+__device__ __forceinline__ void normal_pair_u53(uint4 r, double* nc, double* ns) {
+  double ua = u53(r.x, r.y), ub = u53(r.z, r.w);
+  double rad = sqrt(-2.0 * log(ua));
+  double s, c;
+  sincos(6.283185307179586476925286766559 * ub, &s, &c);
+  *nc = rad * c;
+  *ns = rad * s;
+}
+
+// ---- level-2 domain (one thread per chain; always fp64) -----------------------------------------
+__device__ inline double level2_normal(PhiloxKey key, uint32_t sweep, uint32_t idx) {
+  double c, s;
+  normal_pair_u53(philox4x32_10(idx, sweep, 0u, DOM_LEVEL2, key), &c, &s);
+  return c;
+}
+
+// chi2(df) = 2 Gamma(df/2, 1), Marsaglia-Tsang (df >= 2)
+__device__ inline double level2_chi2(PhiloxKey key, uint32_t sweep, uint32_t idx, double df) {
+  double a = 0.5 * df;
+  double d = a - 1.0 / 3.0;
+  double c = 1.0 / sqrt(9.0 * d);
+  for (uint32_t attempt = 0; attempt < 4096u; ++attempt) {
+    double x, unused;
+    normal_pair_u53(philox4x32_10(idx, sweep, 2u * attempt, DOM_LEVEL2, key), &x, &unused);
+    uint4 rb = philox4x32_10(idx, sweep, 2u * attempt + 1u, DOM_LEVEL2, key);
+    double u = u53(rb.x, rb.y);
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return 2.0 * d * v;
+  }
+  return 2.0 * d;  // unreachable in practice (acceptance > 0.95 per attempt)
+}
+
+}  // namespace clv

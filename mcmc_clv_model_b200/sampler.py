@@ -1,0 +1,197 @@
+"""Host-side mirror of the reference's chain driver over the C-ABI (include/clv_b200.h).
+
+`Sampler` owns one `clv_sampler` handle: one shard of customers x a group of chains on one GPU.
+It does what `_run_chain` (bi:346-431, tri:465-574) does around the Gibbs blocks -- validation,
+hyper-parameters, initial state, burn-in/thinning bookkeeping, draw storage -- and nothing numerical:
+every draw happens in the CUDA library.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib as L
+from .hostmath import ExactSum, init_statistics
+
+_RNG = {"fast": L.RNG_FAST, "strict": L.RNG_STRICT, "injected": L.RNG_INJECTED}
+_COMPAT = {"reference": L.COMPAT_REFERENCE, "paper": L.COMPAT_PAPER}
+_SWEEP = {"auto": L.SWEEP_AUTO, "stream": L.SWEEP_STREAM, "graph": L.SWEEP_GRAPH, "persistent": L.SWEEP_PERSISTENT}
+
+
+def default_hyper(K: int, D: int):
+    """Diffuse NIW prior of bi:474-479 (D=2) / tri:622-626 (D=3)."""
+    nu0 = (3 + K) if D == 2 else (4 + K)
+    return dict(beta_0=np.zeros((K, D)), A_0=np.eye(K) * 0.01, nu_00=float(nu0), gamma_00=nu0 * np.eye(D))
+
+
+def _pinned_empty(shape):
+    """Page-locked float64 host array (torch is used for the allocation only)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+    except Exception:  # pragma: no cover - allocation plumbing only
+        pass
+    return np.empty(shape, dtype=np.float64)
+
+
+class Sampler:
+    def __init__(self, x, t_x, T_cal, X, log_s=None, *, model_dim=2, chains=1, chain_offset=0, n_mh_steps=20,
+                 seed=0, rng="fast", compat="reference", device=0, n_global=None, gid_offset=0, hyper=None,
+                 esum: Optional[ExactSum] = None, sweep_mode="auto", init_stats=None):
+        self.lib = L.load()
+        self.h = C.c_void_p()
+        x = np.ascontiguousarray(x, dtype=np.int32)
+        t_x = np.ascontiguousarray(t_x, dtype=np.float64)
+        T_cal = np.ascontiguousarray(T_cal, dtype=np.float64)
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim != 2 or X.shape[0] != x.size:
+            raise ValueError("X must be (N, K)")
+        if not np.all(X[:, 0] == 1.0):
+            raise ValueError("column 0 of X must be the intercept (all ones)")
+        N, K = X.shape
+        D = int(model_dim)
+        if D == 3:
+            if log_s is None:
+                raise ValueError("the trivariate model needs log_s")
+            log_s = np.ascontiguousarray(log_s, dtype=np.float64)
+        else:
+            log_s = None
+        self.N, self.K, self.D, self.chains = N, K, D, int(chains)
+        self.ncol = 4 if D == 2 else 5
+        self.P = D * K + D * (D + 1) // 2
+        self.n_global = int(n_global if n_global is not None else N)
+        self.S = int(n_mh_steps)
+        cfg = L.Config(model_dim=D, n_cov=K, n_chains=self.chains, chain_offset=int(chain_offset),
+                       n_mh_steps=self.S, rng_mode=_RNG[rng], compat=_COMPAT[compat], sweep_mode=_SWEEP[sweep_mode],
+                       device=int(device), reserved=0, n_local=N, n_global=self.n_global,
+                       gid_offset=int(gid_offset), seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
+        L.check(self.lib.clv_create(C.byref(self.h), C.byref(cfg)))
+        try:
+            L.check(self.lib.clv_set_data(self.h, x.ctypes.data_as(L.c_int32_p), L.dptr(t_x), L.dptr(T_cal),
+                                          L.dptr(X), L.dptr(log_s)), self.h)
+            hy = hyper or default_hyper(K, D)
+            b0 = np.ascontiguousarray(hy["beta_0"], dtype=np.float64)
+            a0 = np.ascontiguousarray(hy["A_0"], dtype=np.float64)
+            g0 = np.ascontiguousarray(hy["gamma_00"], dtype=np.float64)
+            if b0.shape != (K, D) or a0.shape != (K, K) or g0.shape != (D, D):
+                raise ValueError("hyper-parameter shapes do not match (K, D)")
+            L.check(self.lib.clv_set_hyper(self.h, L.dptr(b0), L.dptr(a0), float(hy["nu_00"]), L.dptr(g0)), self.h)
+            st = init_stats or init_statistics(x, t_x, T_cal, X, log_s, self.n_global, esum)
+            self.init_stats = st
+            xtx = np.ascontiguousarray(st["xtx"], dtype=np.float64)
+            cst = L.InitStats(lam_init=st["lam_init"], mean_mu_init=st["mean_mu_init"], mean_log_s=st["mean_log_s"],
+                              omega2=st["omega2"], max_abs_x=st["max_abs_x"], xtx=L.dptr(xtx))
+            L.check(self.lib.clv_init_state(self.h, C.byref(cst)), self.h)
+        except Exception:
+            self.close()
+            raise
+
+    # ---- lifecycle ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.clv_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- communication -----------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        L.check(L.load().clv_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(unique_id, 128)
+        L.check(self.lib.clv_comm_init(self.h, buf, int(rank), int(world)), self.h)
+
+    # ---- sweeps ------------------------------------------------------------------------------
+    def run(self, burnin, mcmc, thin, store_level1=True, trace=0, progress=None):
+        """burnin + mcmc sweeps; returns dict(level_1 [chains] of (n_draws,N,ncol) | None,
+        level_2 (chains,n_draws,P), loglik_sum (chains,n_draws) = per-draw SUM over local customers)."""
+        n_draws = (int(mcmc) - 1) // int(thin) + 1
+        lvl1 = _pinned_empty((self.chains, n_draws, self.N, self.ncol)) if store_level1 else None
+        lvl2 = np.empty((self.chains, n_draws, self.P))
+        ll = np.empty((self.chains, n_draws))
+        cb = L.PROGRESS_CB(lambda user, step, total: progress(int(step), int(total))) if progress else L.PROGRESS_CB(0)
+        L.check(self.lib.clv_run(self.h, int(burnin), int(mcmc), int(thin), L.dptr(lvl1) if lvl1 is not None else None,
+                                 L.dptr(lvl2), L.dptr(ll), cb, None, int(trace)), self.h)
+        return dict(level_1=lvl1, level_2=lvl2, loglik_sum=ll)
+
+    def advance(self, n_sweeps, sync=True):
+        L.check(self.lib.clv_advance(self.h, int(n_sweeps), 1 if sync else 0), self.h)
+
+    @property
+    def sweeps_done(self):
+        return int(self.lib.clv_sweeps_done(self.h))
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.clv_kernel_launches(self.h))
+
+    def set_timing(self, on=True):
+        L.check(self.lib.clv_set_timing(self.h, 1 if on else 0), self.h)
+
+    def kernel_time_ms(self):
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        L.check(self.lib.clv_kernel_time_ms(self.h, C.byref(a), C.byref(b), C.byref(n)), self.h)
+        return a.value, b.value, n.value
+
+    # ---- state -------------------------------------------------------------------------------
+    def get_state(self, chain=0):
+        N, K, D = self.N, self.K, self.D
+        out = dict(log_lambda=np.empty(N), log_mu=np.empty(N), z=np.empty(N), tau=np.empty(N),
+                   beta=np.empty((K, D)), Sigma=np.empty((D, D)))
+        le = np.empty(N) if D == 3 else None
+        L.check(self.lib.clv_get_state(self.h, int(chain), L.dptr(out["log_lambda"]), L.dptr(out["log_mu"]), L.dptr(le),
+                                       L.dptr(out["z"]), L.dptr(out["tau"]), L.dptr(out["beta"]), L.dptr(out["Sigma"])),
+                self.h)
+        if D == 3:
+            out["log_eta"] = le
+        return out
+
+    def set_state(self, chain=0, log_lambda=None, log_mu=None, log_eta=None, beta=None, Sigma=None):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        arrs = [f(a) for a in (log_lambda, log_mu, log_eta, beta, Sigma)]
+        L.check(self.lib.clv_set_state(self.h, int(chain), *[L.dptr(a) for a in arrs]), self.h)
+
+    def sweep_injected(self, v: dict, keep=True):
+        """One sweep of every chain with caller-supplied variates (arrays chain-major, see clv_injected)."""
+        C_, N, S, D, K = self.chains, self.N, self.S, self.D, self.K
+        shapes = dict(u_z=(C_, N), e_tau=(C_, N), u_tau=(C_, N), t3_l=(C_, S, N), t3_m=(C_, S, N), u_acc=(C_, S, N),
+                      n_eta=(C_, N), iw_norm=(C_, D * (D - 1) // 2), iw_chi2=(C_, D), beta_norm=(C_, D * K))
+        keepalive, inj = [], L.Injected()
+        for name, shp in shapes.items():
+            if name == "n_eta" and D == 2:
+                continue
+            a = np.ascontiguousarray(np.asarray(v[name], dtype=np.float64).reshape(shp))
+            keepalive.append(a)
+            setattr(inj, name, L.dptr(a))
+        lvl1 = np.empty((C_, N, self.ncol)) if keep else None
+        lvl2 = np.empty((C_, self.P)) if keep else None
+        ll = np.empty(C_) if keep else None
+        L.check(self.lib.clv_sweep_injected(self.h, C.byref(inj), 1 if keep else 0, L.dptr(lvl1), L.dptr(lvl2), L.dptr(ll)),
+                self.h)
+        return dict(level_1=lvl1, level_2=lvl2, loglik_sum=ll)
+
+    # ---- resident forecast ---------------------------------------------------------------------
+    def forecast_resident(self, T_star=39.0, seed=0, want_x_star=False, n_draws=None):
+        mx, pa = np.empty(self.N), np.empty(self.N)
+        xs = np.empty((self.chains * n_draws, self.N), dtype=np.int64) if want_x_star else None
+        L.check(self.lib.clv_forecast_resident(self.h, float(T_star), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                               xs.ctypes.data_as(L.c_int64_p) if xs is not None else None,
+                                               L.dptr(mx), L.dptr(pa)), self.h)
+        return dict(mean_x_star=mx, p_alive=pa, x_star=xs)

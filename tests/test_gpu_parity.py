@@ -1,0 +1,146 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the reference's own outputs
+(tests/golden/*.npz) and against the oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): driven by identical injected streams from the same state,
+z and x* bit-exact, continuous updates 1e-6 relative."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from mcmc_clv_model_b200 import Sampler
+from oracle import abe_oracle as ao
+from oracle.streams import PhiloxStreams, ReplayStreams
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6   # continuous updates, injected streams (north_star)
+
+
+def _sweep_arrays(g, t, D):
+    names = ["u_z", "e_tau", "u_tau", "t3_l", "t3_m", "u_acc", "iw_norm", "iw_chi2", "beta_norm"] + (["n_eta"] if D == 3 else [])
+    return {n: g[n][t][None] for n in names}
+
+
+@pytest.mark.parametrize("name", ["inj_bi_k1", "inj_bi_k2", "inj_bi_k4", "inj_tri_k3", "inj_tri_k1", "inj_edge"])
+def test_injected_trajectory_vs_reference(name):
+    """Reference `_run_chain` outputs (golden) vs the CUDA sweep fed the same injected streams."""
+    g = load_golden(name + ".npz")
+    D, S = int(g["D"]), int(g["S"])
+    T = g["u_z"].shape[0]
+    with Sampler(g["x"], g["t_x"], g["T_cal"], g["X"], g.get("log_s"), model_dim=D, chains=1, n_mh_steps=S,
+                 rng="injected") as s:
+        for t in range(T):
+            out = s.sweep_injected(_sweep_arrays(g, t, D), keep=True)
+            l1, ref = out["level_1"][0], g["level_1"][t]
+            np.testing.assert_array_equal(l1[:, 3], ref[:, 3], err_msg=f"z differs at sweep {t}")
+            np.testing.assert_allclose(l1, ref, rtol=RTOL, atol=0, err_msg=f"level_1 sweep {t}")
+            np.testing.assert_allclose(out["level_2"][0], g["level_2"][t], rtol=RTOL, atol=1e-9, err_msg=f"level_2 sweep {t}")
+            np.testing.assert_allclose(out["loglik_sum"][0] / len(g["x"]), g["loglik"][t], rtol=RTOL)
+
+
+def test_injected_two_chains_match_single_chain_runs():
+    """Chains are independent: a 2-chain handle equals two 1-chain handles."""
+    g = load_golden("inj_bi_k2.npz")
+    rng = np.random.default_rng(5)
+    N, S, K, D = len(g["x"]), 20, 2, 2
+    from oracle.streams import random_replay_arrays
+    a = [random_replay_arrays(rng, 2, N, S, D, K, 5 + N) for _ in range(2)]
+    both = {k: np.stack([a[0][k], a[1][k]], axis=1) for k in a[0]}     # (T, chains, ...)
+    with Sampler(g["x"], g["t_x"], g["T_cal"], g["X"], model_dim=2, chains=2, n_mh_steps=S, rng="injected") as s2:
+        outs2 = [s2.sweep_injected({k: v[t] for k, v in both.items()}) for t in range(2)]
+    for c in range(2):
+        with Sampler(g["x"], g["t_x"], g["T_cal"], g["X"], model_dim=2, chains=1, n_mh_steps=S, rng="injected") as s1:
+            for t in range(2):
+                o = s1.sweep_injected({k: v[t][None] for k, v in a[c].items()})
+                np.testing.assert_array_equal(o["level_1"][0], outs2[t]["level_1"][c])
+                np.testing.assert_array_equal(o["level_2"][0], outs2[t]["level_2"][c])
+
+
+@pytest.mark.parametrize("D,cov", [(2, []), (2, ["first_sales_scaled"]), (3, ["gender_F", "age_scaled"])])
+def test_strict_philox_trajectory_vs_oracle(cdnow_abe, D, cov):
+    """The production sweep loop (clv_run, strict-f64 Philox) against the oracle replaying the same
+    counter-based variates: the whole device pipeline (RNG transforms, fixed-point level-2 statistics,
+    Bartlett/IW draw, burn-in/thin bookkeeping) over several sweeps."""
+    d = cdnow_abe
+    n = 700
+    X = np.column_stack([np.ones(n)] + [d[c][:n].astype(float) for c in cov])
+    cbs = ao.Cbs(x=d["x"][:n].astype(np.int64), t_x=d["t_x"][:n], T_cal=d["T_cal"][:n], X=X,
+                 log_s=d["log_s"][:n] if D == 3 else None)
+    seed, burnin, mcmc, thin, S = 1234, 2, 5, 2, 20
+    for chain in (0, 1):
+        ora = ao.run_chain(cbs, ao.default_hyper(cbs.K, D), PhiloxStreams(seed, chain, np.arange(n), S, D, cbs.K),
+                           mcmc=mcmc, burnin=burnin, thin=thin, D=D, n_mh_steps=S)
+        with Sampler(cbs.x, cbs.t_x, cbs.T_cal, X, cbs.log_s, model_dim=D, chains=1, chain_offset=chain,
+                     n_mh_steps=S, seed=seed, rng="strict") as s:
+            out = s.run(burnin, mcmc, thin)
+        np.testing.assert_array_equal(out["level_1"][0][:, :, 3], ora["level_1"][:, :, 3])
+        np.testing.assert_allclose(out["level_1"][0], ora["level_1"], rtol=RTOL)
+        np.testing.assert_allclose(out["level_2"][0], ora["level_2"], rtol=RTOL, atol=1e-9)
+        np.testing.assert_allclose(out["loglik_sum"][0] / n, ora["log_likelihood"], rtol=RTOL)
+
+
+def test_chain_offset_reproduces_chain(cdnow_abe):
+    """`chains=1, seed=seed+ch` reproduces chain ch (the property of bi:486), and runs are deterministic."""
+    d = cdnow_abe
+    n = 500
+    X = np.ones((n, 1))
+    args = (d["x"][:n], d["t_x"][:n], d["T_cal"][:n], X)
+    with Sampler(*args, chains=3, seed=42) as s:
+        a = s.run(3, 4, 1)
+    with Sampler(*args, chains=1, seed=44) as s:
+        b = s.run(3, 4, 1)
+    with Sampler(*args, chains=1, chain_offset=2, seed=42) as s:
+        c = s.run(3, 4, 1)
+    np.testing.assert_array_equal(a["level_2"][2], b["level_2"][0])
+    np.testing.assert_array_equal(a["level_1"][2], b["level_1"][0])
+    np.testing.assert_array_equal(a["level_2"][2], c["level_2"][0])
+
+
+def test_forecast_bivariate_vs_reference():
+    g = load_golden("fc_bi.npz")
+    import ctypes as C
+    from mcmc_clv_model_b200 import _lib as L
+    lib = L.load()
+    l1 = np.ascontiguousarray(g["level_1"])
+    nd, N, nc = l1.shape
+    xs = np.empty((nd, N), dtype=np.int64)
+    cfg = L.ForecastConfig(device=0, ncol=nc, n_draws_total=nd, n_customers=N, T_star=float(g["T_star"]), seed=1)
+    L.check(lib.clv_forecast_injected(C.byref(cfg), L.dptr(l1), L.dptr(np.ascontiguousarray(g["T_cal"])),
+                                      L.dptr(np.ascontiguousarray(g["u"])), None, 0, None,
+                                      xs.ctypes.data_as(L.c_int64_p), None))
+    np.testing.assert_array_equal(xs, g["x_star"])          # x* bit-exact
+
+
+def test_forecast_trivariate_spend_vs_reference():
+    g = load_golden("fc_tri.npz")
+    import ctypes as C
+    from mcmc_clv_model_b200 import _lib as L
+    lib = L.load()
+    l1 = np.ascontiguousarray(g["level_1"])
+    nd, N, nc = l1.shape
+    stride = g["eps"].shape[1]
+    # the reference consumes eps[d][:sum x*] in customer order: offsets = exclusive cumsum of x* within the draw
+    off = (np.cumsum(g["x_star"], axis=1) - g["x_star"]) + (np.arange(nd) * stride)[:, None]
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    eps = np.ascontiguousarray(g["eps"]).ravel()
+    xs = np.empty((nd, N), dtype=np.int64)
+    sp = np.empty((nd, N))
+    cfg = L.ForecastConfig(device=0, ncol=nc, n_draws_total=nd, n_customers=N, T_star=float(g["T_star"]), seed=1,
+                           simulate_spend=1, sigma_s=float(g["sigma_s"]))
+    L.check(lib.clv_forecast_injected(C.byref(cfg), L.dptr(l1), L.dptr(np.ascontiguousarray(g["T_cal"])),
+                                      L.dptr(np.ascontiguousarray(g["u"])), L.dptr(eps), eps.size,
+                                      off.ctypes.data_as(L.c_int64_p), xs.ctypes.data_as(L.c_int64_p), L.dptr(sp)))
+    np.testing.assert_array_equal(xs, g["x_star"])
+    np.testing.assert_allclose(sp, g["spend"], rtol=RTOL)
+
+
+def test_forecast_philox_vs_oracle():
+    """Production forecast (Philox uniforms) == oracle Poisson inversion on the same counter-based uniforms."""
+    from oracle import philox_np as px
+    from mcmc_clv_model_b200.api import _forecast
+    g = load_golden("fc_bi.npz")
+    l1 = g["level_1"]
+    nd, N, _ = l1.shape
+    x, _ = _forecast(g["T_cal"], [l1[:2], l1[2:]], 39.0, 77, False, 0.5)
+    u = np.stack([px.forecast_uniform(77, np.arange(N), d) for d in range(nd)])
+    np.testing.assert_array_equal(x, ao.forecast(g["T_cal"], l1, 39.0, u))
