@@ -123,6 +123,8 @@ int clv_run(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* 
             double* loglik, clv_progress_cb cb, void* user, int64_t trace);
 /* Advance n sweeps without storing draws (burn-in, benchmarks).  Asynchronous unless sync != 0. */
 int clv_advance(clv_sampler* h, int64_t n_sweeps, int sync);
+/* Same, synchronous, bracketed by CUDA events on the handle's stream: *elapsed_ms = device time of the n sweeps. */
+int clv_advance_timed(clv_sampler* h, int64_t n_sweeps, double* elapsed_ms);
 int64_t clv_sweeps_done(const clv_sampler* h);
 /* kernels launched by this handle so far (bench.py's gpu_launches) */
 int64_t clv_kernel_launches(const clv_sampler* h);

@@ -70,6 +70,7 @@ SIGNATURES = {
     "clv_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, c_double_p, c_double_p, c_double_p,
                           PROGRESS_CB, C.c_void_p, C.c_int64]),
     "clv_advance": (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),
+    "clv_advance_timed": (C.c_int, [C.c_void_p, C.c_int64, c_double_p]),
     "clv_sweeps_done": (C.c_int64, [C.c_void_p]),
     "clv_kernel_launches": (C.c_int64, [C.c_void_p]),
     "clv_set_timing": (C.c_int, [C.c_void_p, C.c_int]),

@@ -553,6 +553,28 @@ int clv_advance(clv_sampler* h, int64_t n_sweeps, int sync) {
   return CLV_OK;
 }
 
+int clv_advance_timed(clv_sampler* h, int64_t n_sweeps, double* elapsed_ms) {
+  if (!h || !elapsed_ms) return fail(h, CLV_ERR_ARG, "null argument");
+  if (!h->inited) return fail(h, CLV_ERR_STATE, "clv_advance_timed: call clv_init_state first");
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaEvent_t e0, e1;
+  CK(h, cudaEventCreate(&e0));
+  CK(h, cudaEventCreate(&e1));
+  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, cudaEventRecord(e0, h->stream));
+  int r = clv_advance(h, n_sweeps, 0);
+  if (r == 0) {
+    cudaEventRecord(e1, h->stream);
+    r = check_device_error(h);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *elapsed_ms = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return r;
+}
+
 static int ensure_run_buffers(clv_sampler* h, long long n_draws, bool want_level1, long long* chunk_cap) {
   const long long C = h->chains;
   if (h->loglik_cap < C * n_draws) {

@@ -126,13 +126,19 @@ class Sampler:
         lvl1 = _pinned_empty((self.chains, n_draws, self.N, self.ncol)) if store_level1 else None
         lvl2 = np.empty((self.chains, n_draws, self.P))
         ll = np.empty((self.chains, n_draws))
-        cb = L.PROGRESS_CB(lambda user, step, total: progress(int(step), int(total))) if progress else L.PROGRESS_CB(0)
+        cb = L.PROGRESS_CB(lambda user, step, total: progress(int(step), int(total))) if progress else C.cast(None, L.PROGRESS_CB)
         L.check(self.lib.clv_run(self.h, int(burnin), int(mcmc), int(thin), L.dptr(lvl1) if lvl1 is not None else None,
                                  L.dptr(lvl2), L.dptr(ll), cb, None, int(trace)), self.h)
         return dict(level_1=lvl1, level_2=lvl2, loglik_sum=ll)
 
     def advance(self, n_sweeps, sync=True):
         L.check(self.lib.clv_advance(self.h, int(n_sweeps), 1 if sync else 0), self.h)
+
+    def advance_timed(self, n_sweeps) -> float:
+        """n sweeps, synchronous; returns their device time in ms (CUDA events on the handle's stream)."""
+        ms = C.c_double()
+        L.check(self.lib.clv_advance_timed(self.h, int(n_sweeps), C.byref(ms)), self.h)
+        return ms.value
 
     @property
     def sweeps_done(self):
