@@ -44,40 +44,55 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.samples, self.t0, self.t1 = index, None, [], None, None
 
-    def __enter__(self):
+    def start(self):
+        """Start polling (nvidia-smi needs ~0.3 s to come up: call well before the timed region)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+
+            def pump():
+                for ln in self.proc.stdout:
+                    self.samples.append((time.time(), ln))
+            self.t = threading.Thread(target=pump, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
         return self
 
+    def __enter__(self):            # the timed region
+        self.t0 = time.time()
+        return self
+
     def __exit__(self, *a):
+        self.t1 = time.time()
+
+    def stop(self):
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.1)
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        for ln in self.lines:
+        sm, mx, reasons, power = [], 0.0, set(), []
+        for ts, ln in self.samples:
+            if self.t0 is None or not (self.t0 <= ts <= self.t1 + 0.06):
+                continue
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
                 sm.append(float(f[1]))
                 mx = max(mx, float(f[2]))
+                power.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
 def _pin(a):
@@ -168,8 +183,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from mcmc_clv_model_b200 import Sampler
-    from mcmc_clv_model_b200.distributed import broadcast_unique_id, dist_exact_sum, shard_bounds
-    from mcmc_clv_model_b200.hostmath import init_statistics
+    from mcmc_clv_model_b200.distributed import broadcast_unique_id, shard_bounds
     from mcmc_clv_model_b200.synthetic import C4_BETA, C4_GAMMA, C4_SEED, C4_T_CAL, generate_cbs_arrays
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,27 +216,24 @@ def run_ours(args):
     cols = generate_cbs_arrays(n_loc, C4_BETA, C4_GAMMA, T_cal=C4_T_CAL, T_star=39.0, seed=C4_SEED, gid_offset=lo,
                                device=local, with_truth=False)
     pinned = {k: _pin(cols[k]) for k in ("x", "t_x", "T_cal", "X")}
-    esum = dist_exact_sum() if world > 1 else None
-    t0 = time.perf_counter()
-    stats = init_statistics(cols["x"], cols["t_x"], cols["T_cal"], cols["X"], None, n_tot, esum)
-    t_stats = time.perf_counter() - t0
 
     def make(rng="fast"):
-        s = Sampler(pinned["x"][0], pinned["t_x"][0], pinned["T_cal"][0], pinned["X"][0], model_dim=2, chains=1,
-                    n_mh_steps=S_MH, seed=args.seed, rng=rng, device=local, n_global=n_tot, gid_offset=lo, init_stats=stats)
-        if world > 1:
-            s.comm_init(broadcast_unique_id(Sampler.comm_unique_id), rank, world)
-        return s
+        # CBS columns from pinned host memory -> device; exact init statistics on the device (+ NCCL when sharded)
+        comm = (broadcast_unique_id(Sampler.comm_unique_id), rank, world) if world > 1 else None
+        return Sampler(pinned["x"][0], pinned["t_x"][0], pinned["T_cal"][0], pinned["X"][0], model_dim=2, chains=1,
+                       n_mh_steps=S_MH, seed=args.seed, rng=rng, device=local, n_global=n_tot, gid_offset=lo, comm=comm)
 
     # ---- device-resident throughput ("value") -----------------------------------------------------
+    clk = ClockSampler(local).start()
     s = make()
     s.advance(args.warmup, sync=True)
     s.set_timing(True)
     launches0 = s.kernel_launches
     barrier()
-    with ClockSampler(local) as clk:
+    with clk:
         ms = s.advance_timed(args.steps)
     barrier()
+    clk.stop()
     ms = max_over_ranks(ms)
     launches = s.kernel_launches - launches0
     sweep_ms, l2_ms, n_timed = s.kernel_time_ms()
@@ -268,7 +279,7 @@ def run_ours(args):
     e2e = {"value": n_tot * args.steps / e2e_s, "unit": "customer-updates/s", "h2d_bytes_per_step": h2d / args.steps,
            "d2h_bytes_per_step": d2h / args.steps, "seconds": e2e_s,
            "what": "clv_create + clv_set_data (pinned host CBS -> device) + clv_init_state + clv_run(K sweeps, 1 kept "
-                   "level-1 draw -> pinned host) + clv_destroy; host-side init statistics excluded (%.2f s, once per data set)" % t_stats}
+                   "level-1 draw -> host) + clv_destroy, i.e. everything mcmc_draw_parameters does after the DataFrame is unpacked"}
     assert np.isfinite(chk)
 
     if rank != 0:
@@ -318,8 +329,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--customers", type=int, default=N_C4)
     ap.add_argument("--seed", type=int, default=42)

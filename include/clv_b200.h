@@ -103,8 +103,12 @@ int clv_set_data(clv_sampler* h, const int32_t* x, const double* t_x, const doub
 /* hyper dict of bi:474-479 / tri:622-626: beta0 K x D, A0 K x K, nu0, gamma0 D x D.
  * Row 0 of beta0 is overwritten from the init statistics exactly as bi:373-374 / tri:497-499 do. */
 int clv_set_hyper(clv_sampler* h, const double* beta0, const double* A0, double nu0, const double* gamma0);
-/* Initial lambda, mu, eta, beta, Sigma of bi:367-379 / tri:488-504. */
+/* Initial lambda, mu, eta, beta, Sigma of bi:367-379 / tri:488-504.  stats == NULL: the statistics are computed
+ * on the device as exact integer sums (and all-reduced over the communicator when clv_comm_init was called first),
+ * bit-identical to mcmc_clv_model_b200/hostmath.py for any sharding. */
 int clv_init_state(clv_sampler* h, const clv_init_stats* stats);
+/* The statistics the last clv_init_state(h, NULL) computed; xtx_out (nullable) receives K*K doubles. */
+int clv_get_init_stats(clv_sampler* h, clv_init_stats* out, double* xtx_out);
 /* Customer-sharded mode: join the NCCL communicator used for the per-sweep all-reduce of the
  * level-2 sufficient statistics.  unique_id is the 128-byte ncclUniqueId from clv_comm_unique_id
  * on rank 0, broadcast by the host (torch.distributed). */

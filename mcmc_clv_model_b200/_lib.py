@@ -65,6 +65,7 @@ SIGNATURES = {
     "clv_set_data": (C.c_int, [C.c_void_p, c_int32_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "clv_set_hyper": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_double, c_double_p]),
     "clv_init_state": (C.c_int, [C.c_void_p, C.POINTER(InitStats)]),
+    "clv_get_init_stats": (C.c_int, [C.c_void_p, C.POINTER(InitStats), c_double_p]),
     "clv_comm_unique_id": (C.c_int, [C.c_void_p]),
     "clv_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "clv_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, c_double_p, c_double_p, c_double_p,

@@ -87,6 +87,9 @@ struct clv_sampler {
   int grid_x = 1;
   // comm
   nccl_comm_t comm = nullptr; int world = 1, rank = 0;
+  // statistics computed by clv_init_state(h, NULL)
+  clv_init_stats last_stats{};
+  std::vector<double> last_xtx;
   // timing
   bool timing = false;
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
@@ -159,6 +162,32 @@ int ceil_log2(double v) {
   double p = 1.0;
   while (p < v && e < 1000) { p *= 2.0; ++e; }
   return e;
+}
+
+int fx_bits_host(double max_abs) {              // hostmath.fx_bits
+  if (!(max_abs > 1.0)) return 51;
+  int ex;
+  double f = std::frexp(max_abs, &ex);
+  return 51 - (f == 0.5 ? ex - 1 : ex);
+}
+
+// total * 2^-bits, correctly rounded (hostmath.from_fx)
+double i128_scaled(__int128 t, int bits) {
+  if (t == 0) return 0.0;
+  const bool neg = t < 0;
+  unsigned __int128 a = neg ? (unsigned __int128)(-t) : (unsigned __int128)t;
+  int msb = 127;
+  while (!((a >> msb) & 1)) --msb;
+  double m;
+  int sh = 0;
+  if (msb <= 52) m = (double)(uint64_t)a;
+  else {
+    sh = msb - 52;
+    unsigned __int128 q = a >> sh, rem = a & ((((unsigned __int128)1) << sh) - 1), half = ((unsigned __int128)1) << (sh - 1);
+    if (rem > half || (rem == half && (q & 1))) ++q;
+    m = (double)(uint64_t)q;
+  }
+  return std::ldexp(neg ? -m : m, sh - bits);
 }
 
 SweepArgs base_args(clv_sampler* h) {
@@ -336,6 +365,9 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
     rk[0] = 0.0;
     for (int k = 1; k <= RK_TABLE; ++k) rk[k] = 1.0 / (double)k;
     CKC(cudaMemcpyToSymbol(c_rk, rk, sizeof rk));
+    double et[64];
+    for (int j = 0; j < 64; ++j) et[j] = (double)exp2l((long double)j / 64.0L);
+    CKC(cudaMemcpyToSymbol(c_exptab, et, sizeof et));
   }
   // grid: a few resident waves of 128-thread blocks, grid-stride over customer tiles
   long long ntiles = (h->N + SWEEP_THREADS - 1) / SWEEP_THREADS;
@@ -376,13 +408,21 @@ int clv_set_data(clv_sampler* h, const int32_t* x, const double* t_x, const doub
   CK(h, cudaMemcpyAsync(h->d_tx, t_x, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->d_T, T_cal, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   if (h->D == 3) CK(h, cudaMemcpyAsync(h->d_logs, log_s, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  double* d_rows = nullptr;
   if (h->K > 1) {
-    // row-major N x K (column 0 = intercept) -> SoA covariate columns; strided 2-D copies, one per column
-    for (int k = 1; k < h->K; ++k)
-      CK(h, cudaMemcpy2DAsync(h->d_Xc + (size_t)(k - 1) * N, sizeof(double), X + k, (size_t)h->K * sizeof(double),
-                              sizeof(double), N, cudaMemcpyHostToDevice, h->stream));
+    // row-major N x K (column 0 = intercept): one contiguous copy, then split into SoA columns on the device
+    CK(h, dmalloc(&d_rows, N * (size_t)h->K));
+    cudaError_t e = cudaMemcpyAsync(d_rows, X, N * (size_t)h->K * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+      k_split_columns<<<h->sm_count * 8, 256, 0, h->stream>>>(d_rows, (long long)N, h->K, h->d_Xc);
+      h->launches++;
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { cudaFree(d_rows); return fail(h, CLV_ERR_CUDA, "design-matrix upload failed: %s", cudaGetErrorString(e)); }
   }
-  CK(h, cudaStreamSynchronize(h->stream));
+  cudaError_t es = cudaStreamSynchronize(h->stream);
+  if (d_rows) cudaFree(d_rows);
+  if (es != cudaSuccess) return fail(h, CLV_ERR_CUDA, "clv_set_data failed: %s", cudaGetErrorString(es));
   h->have_data = true;
   h->inited = false;
   return CLV_OK;
@@ -400,10 +440,103 @@ int clv_set_hyper(clv_sampler* h, const double* beta0, const double* A0, double 
   return CLV_OK;
 }
 
+// Exact, shard-independent initialisation statistics on the device (+ NCCL when sharded); see k_init_quantities.
+static int device_init_stats(clv_sampler* h, clv_init_stats* out, std::vector<double>& xtx) {
+  const int K = h->K, D = h->D;
+  const int nqA = 3 + K * (K + 1) / 2;
+  unsigned long long* d_max = nullptr;
+  long long* d_sum = nullptr;
+  CK(h, dmalloc(&d_max, (size_t)NQ_MAX));
+  CK(h, dmalloc(&d_sum, (size_t)NQ_MAX * 2));
+  int rc = 0;
+  InitQArgs a{};
+  a.x = h->d_x; a.t_x = h->d_tx; a.T_cal = h->d_T; a.Xc = h->d_Xc; a.log_s = h->d_logs;
+  a.N = h->N; a.K = K; a.D = D; a.out_max = d_max; a.out_sum = d_sum;
+  const double n = (double)h->cfg.n_global;
+  std::vector<double> tot(NQ_MAX, 0.0);
+  double max_abs_x = 1.0;
+  auto run_phase = [&](int phase, int nq) -> int {
+    std::vector<unsigned long long> hmax(nq);
+    std::vector<long long> hsum(2 * nq);
+    a.phase = phase;
+    a.mode = 0;
+    CK(h, cudaMemsetAsync(d_max, 0, sizeof(unsigned long long) * NQ_MAX, h->stream));
+    CK(h, cudaMemsetAsync(d_sum, 0, sizeof(long long) * NQ_MAX * 2, h->stream));
+    k_init_quantities<<<h->sm_count * 8, 256, 0, h->stream>>>(a);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    if (h->comm) {
+      int r = g_nccl.AllReduce(d_max, d_max, (size_t)nq, 5 /*ncclUint64*/, 2 /*ncclMax*/, h->comm, h->stream);
+      if (r != 0) return fail(h, CLV_ERR_COMM, "ncclAllReduce(max) failed (%d)", r);
+    }
+    CK(h, cudaMemcpyAsync(hmax.data(), d_max, sizeof(unsigned long long) * nq, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    std::vector<int> bits(nq);
+    for (int q = 0; q < nq; ++q) {
+      double m;
+      std::memcpy(&m, &hmax[q], sizeof m);
+      if (!std::isfinite(m)) return fail(h, CLV_ERR_NUMERIC, "non-finite value in an initialisation statistic");
+      bits[q] = fx_bits_host(m);
+      a.scale[q] = std::ldexp(1.0, bits[q]);
+      if (phase == 0 && q >= 3) max_abs_x = std::max(max_abs_x, std::sqrt(m));   // diagonal pairs give max |X_k|^2
+    }
+    a.mode = 1;
+    k_init_quantities<<<h->sm_count * 8, 256, 0, h->stream>>>(a);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    if (h->comm) {
+      int r = g_nccl.AllReduce(d_sum, d_sum, (size_t)nq * 2, NCCL_INT64, NCCL_SUM, h->comm, h->stream);
+      if (r != 0) return fail(h, CLV_ERR_COMM, "ncclAllReduce(sum) failed (%d)", r);
+    }
+    CK(h, cudaMemcpyAsync(hsum.data(), d_sum, sizeof(long long) * nq * 2, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < nq; ++q) {
+      __int128 t = ((__int128)hsum[2 * q + 1] << 32) + (__int128)hsum[2 * q];
+      tot[q] = i128_scaled(t, bits[q]);
+    }
+    return 0;
+  };
+  rc = run_phase(0, nqA);
+  if (!rc) {
+    const double mean_x = tot[0] / n, mean_t = tot[1] / n;
+    out->lam_init = mean_x / mean_t;
+    out->mean_log_s = (D == 3) ? tot[2] / n : 0.0;
+    xtx.assign((size_t)K * K, 0.0);
+    int q = 3;
+    for (int i = 0; i < K; ++i)
+      for (int j = i; j < K; ++j, ++q) xtx[i * K + j] = xtx[j * K + i] = tot[q];
+    out->max_abs_x = max_abs_x;
+    if (!(out->lam_init > 0.0) || !std::isfinite(out->lam_init))
+      rc = fail(h, CLV_ERR_NUMERIC, "lam_init = mean(x)/mean(t) is not positive and finite (no repeat purchases?)");
+  }
+  if (!rc) {
+    a.lam_init = out->lam_init;
+    a.mean_log_s = out->mean_log_s;
+    rc = run_phase(1, 2);
+  }
+  if (!rc) {
+    out->mean_mu_init = tot[0] / n;
+    out->omega2 = (D == 3) ? tot[1] / (n - 1.0) : 1.0;
+    out->xtx = xtx.data();
+  }
+  cudaFree(d_max);
+  cudaFree(d_sum);
+  return rc;
+}
+
 int clv_init_state(clv_sampler* h, const clv_init_stats* st) {
   if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
-  if (!st || !st->xtx) return fail(h, CLV_ERR_ARG, "clv_init_state: stats (with xtx) are required");
   if (!h->have_data || !h->have_hyper) return fail(h, CLV_ERR_STATE, "clv_init_state: call clv_set_data and clv_set_hyper first");
+  clv_init_stats computed{};
+  std::vector<double> xtx_buf;
+  if (!st) {
+    CK(h, cudaSetDevice(h->cfg.device));
+    if (int r = device_init_stats(h, &computed, xtx_buf)) return r;
+    st = &computed;
+    h->last_stats = computed;
+    h->last_xtx = xtx_buf;
+  }
+  if (!st->xtx) return fail(h, CLV_ERR_ARG, "clv_init_state: stats without xtx");
   if (!(st->lam_init > 0.0) || !std::isfinite(st->lam_init) || !(st->mean_mu_init > 0.0))
     return fail(h, CLV_ERR_NUMERIC, "clv_init_state: lam_init / mean_mu_init must be positive and finite");
   CK(h, cudaSetDevice(h->cfg.device));
@@ -452,25 +585,15 @@ int clv_init_state(clv_sampler* h, const clv_init_stats* st) {
   CK(h, cudaMemcpyAsync(h->d_mc, &mc, sizeof mc, cudaMemcpyHostToDevice, h->stream));
   // initial level-1 state (bi:368-370, tri:489-493) and level-2 placeholders (bi:379, tri:504)
   const size_t N = (size_t)h->N;
-  std::vector<double> tx(N), buf(N);
-  CK(h, cudaMemcpyAsync(tx.data(), h->d_tx, N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(h, cudaStreamSynchronize(h->stream));
   std::vector<ChainParams> cps(h->chains);
   for (int c = 0; c < h->chains; ++c) {
     std::memset(&cps[c], 0, sizeof(ChainParams));
     for (int t = 0; t < K * D; ++t) cps[c].beta[t] = B0[t];
     for (int t = 0; t < D * D; ++t) cps[c].Sigma[t] = h->gamma0[t];
   }
-  const double ll0 = std::log(st->lam_init);
-  for (size_t i = 0; i < N; ++i) buf[i] = ll0;
-  for (int c = 0; c < h->chains; ++c)
-    CK(h, cudaMemcpyAsync(h->d_ll + (size_t)c * N, buf.data(), N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaStreamSynchronize(h->stream));
-  for (size_t i = 0; i < N; ++i) buf[i] = std::log(1.0 / (tx[i] + 0.5 / st->lam_init));
-  for (int c = 0; c < h->chains; ++c)
-    CK(h, cudaMemcpyAsync(h->d_lm + (size_t)c * N, buf.data(), N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaStreamSynchronize(h->stream));
-  if (D == 3) CK(h, cudaMemsetAsync(h->d_le, 0, sizeof(double) * N * h->chains, h->stream));   // eta = 1 (tri:493)
+  k_init_state<<<h->sm_count * 8, 256, 0, h->stream>>>(h->d_tx, (long long)N, h->chains, D, st->lam_init, h->d_ll, h->d_lm, h->d_le);
+  h->launches++;
+  CK(h, cudaGetLastError());
   CK(h, cudaMemsetAsync(h->d_z, 0, sizeof(double) * N * h->chains, h->stream));
   CK(h, cudaMemsetAsync(h->d_tau, 0, sizeof(double) * N * h->chains, h->stream));
   CK(h, cudaMemcpyAsync(h->d_params, cps.data(), sizeof(ChainParams) * h->chains, cudaMemcpyHostToDevice, h->stream));
@@ -483,6 +606,15 @@ int clv_init_state(clv_sampler* h, const clv_init_stats* st) {
   CK(h, cudaStreamSynchronize(h->stream));
   h->sweeps_done = 0;
   h->resident_draws = 0;
+  return CLV_OK;
+}
+
+int clv_get_init_stats(clv_sampler* h, clv_init_stats* out, double* xtx_out) {
+  if (!h || !out) return fail(h, CLV_ERR_ARG, "null argument");
+  if (h->last_xtx.empty()) return fail(h, CLV_ERR_STATE, "no device-computed statistics: call clv_init_state(h, NULL) first");
+  *out = h->last_stats;
+  out->xtx = nullptr;
+  if (xtx_out) std::memcpy(xtx_out, h->last_xtx.data(), sizeof(double) * h->K * h->K);
   return CLV_OK;
 }
 

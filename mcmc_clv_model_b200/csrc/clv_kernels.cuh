@@ -81,28 +81,71 @@ struct SweepArgs {
   const double *u_z, *e_tau, *u_tau, *t3_l, *t3_m, *u_acc, *n_eta;
 };
 
+__constant__ double c_exptab[64];   // 2^(j/64), uploaded by clv_create
+
 __device__ __forceinline__ long long to_fx(double v, double scale) { return __double2ll_rn(v * scale); }
 
+// Warp-wide int64 sum with three REDUX.SUM (32-bit) instead of a 64-bit shuffle tree:
+// v = lo + mid 2^26 + hi 2^52 (hi signed), and 32 pieces of 26 bits cannot overflow 32 bits.  All 32 lanes must call.
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  return v;
+  const unsigned lo = (unsigned)v & 0x3ffffffu, mid = (unsigned)(v >> 26) & 0x3ffffffu;
+  const int hi = (int)(v >> 52);
+  const unsigned slo = __reduce_add_sync(0xffffffffu, lo), smid = __reduce_add_sync(0xffffffffu, mid);
+  const int shi = __reduce_add_sync(0xffffffffu, hi);
+  return (long long)slo + ((long long)smid << 26) + (long long)((unsigned long long)(long long)shi << 52);
 }
 
-// Level-1 target, bi:291-310.  Tz = z*T_cal + (1-z)*tau, omz = 1-z.
+// exp(x) for |x| <= 70 (the clip range of bi:323-324), ~1 ulp, branch-free:
+//   n = rint(x 64/ln2), r = x - n ln2/64 (|r| <= 0.0055), exp(x) = 2^(n>>6) * 2^((n&63)/64) * (1 + r + ... + r^5/120)
+// 2^(j/64) comes from a 64-entry shared-memory table; the degree-5 remainder is < 4e-17.
+__device__ __forceinline__ double exp_clip70(double x, const double* __restrict__ tab) {
+  const double t = fma(x, 92.332482616893656877, 6755399441055744.0);   // 64/ln2 ; 1.5 * 2^52 rounds to nearest
+  const int n = __double2loint(t);
+  const double nd = t - 6755399441055744.0;
+  double r = fma(nd, -0x1.62e42fefa0000p-7, x);                           // ln2/64, high part (low 16 bits zero: n*hi exact)
+  r = fma(nd, -0x1.cf79abc9e3b3ap-46, r);                                 // low part
+  double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = p * r;
+  const double T = tab[n & 63];
+  double v = fma(T, p, T);
+  const int hi = __double2hiint(v) + ((n >> 6) << 20);
+  return __hiloint2double(hi, __double2loint(v));
+}
+
+// Level-1 target, bi:291-310.  Tz = z*T_cal + (1-z)*tau, omz = 1-z.  ll, lm in [-70, 70].
 __device__ __forceinline__ double log_post(double ll, double lm, double xd, double omz, double Tz, double m0,
-                                           double m1, double P00, double P01, double P11) {
+                                           double m1, double P00, double P01, double P11, const double* tab) {
   double dl = ll - m0, dm = lm - m1;
-  double lik = xd * ll + omz * lm - (exp(ll) + exp(lm)) * Tz;
+  double lik = xd * ll + omz * lm - (exp_clip70(ll, tab) + exp_clip70(lm, tab)) * Tz;
   double prior = -0.5 * (dl * dl * P00 + 2.0 * dl * dm * P01 + dm * dm * P11);
   double res = lik + prior;
   return (lm > 5.0) ? -CUDART_INF : res;
 }
 
-// MH accept rule of bi:329-330: exp(prop - cur) > u, NaN compares false.
-__device__ __forceinline__ bool mh_accept(double d, double u) {
+// MH accept rule of bi:329-330: exp(prop - cur) > u, NaN compares false.  An fp32 SFU screen in log space
+// (uf = fp32 image of u) settles all but ~1e-5 of the decisions; the tie zone is re-decided with the exact fp64
+// expression, so the outcome always equals `exp(d) > u`.
+template <typename ExactU>
+__device__ __forceinline__ bool mh_accept(double d, float uf, ExactU exact_u) {
   if (d >= 0.0) return true;       // exp(d) >= 1 > u
-  return exp(d) > u;               // NaN -> false; d = -inf -> 0 > u false
+  const float df = (float)d, lu = 0.69314718055994531f * lg2_ftz(uf);
+  const float tol = 1e-5f * (1.0f + fabsf(lu));
+  if (uf > 1e-30f && df > -80.0f) {
+    if (df > lu + tol) return true;
+    if (df < lu - tol) return false;
+  }
+  return exp(d) > exact_u();       // NaN -> false; d = -inf -> 0 > u false
+}
+
+// np.clip(v, -70, 70) of bi:323-324; the comparison runs on the high word so the common case costs two integer ops
+__device__ __noinline__ double clip70_slow(double v) { return fmin(fmax(v, -70.0), 70.0); }
+__device__ __forceinline__ double clip70(double v) {
+  // a real (never if-converted) branch: |v| >= 70 is a once-in-a-run event
+  if (((unsigned)__double2hiint(v) & 0x7fffffffu) >= 0x40518000u) v = clip70_slow(v);
+  return v;
 }
 
 template <int D>
@@ -135,6 +178,7 @@ __device__ __forceinline__ void accumulate_stats(const ModelConst& mc, const dou
 template <int D, int MODE>
 __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(SweepArgs a) {
   __shared__ double s_beta[MAXK * MAXD];
+  __shared__ double s_tab[64];
   __shared__ unsigned long long s_acc[NSTAT_MAX + 1];
   const ModelConst& mc = *a.mc;
   const int chain = blockIdx.y;
@@ -143,6 +187,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(SweepArgs a) {
   const long long N = mc.N;
   const ChainParams& cp = a.params[chain];
   for (int t = tid; t < K * D; t += SWEEP_THREADS) s_beta[t] = cp.beta[t];
+  if (tid < 64) s_tab[tid] = c_exptab[tid];
   for (int t = tid; t < NSTAT_MAX + 1; t += SWEEP_THREADS) s_acc[t] = 0ull;
   __syncthreads();
   const double P00 = cp.P00, P01 = cp.P01, P11 = cp.P11;
@@ -170,7 +215,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(SweepArgs a) {
         if (D == 3) m2 = fma(xk, s_beta[k * D + 2], m2);
       }
       // ---- z (bi:193-200) and tau (bi:203-227) from the current lambda, mu -------------------------
-      const double lam = exp(ll), mu = exp(lm);
+      const double lam = exp_clip70(ll, s_tab), mu = exp_clip70(lm, s_tab);   // |ll|, |lm| <= 70 by construction
       double uz, ut, et;
       if (MODE == MODE_INJECT) {
         uz = a.u_z[cN + i];
@@ -198,14 +243,17 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(SweepArgs a) {
       const double omz = 1.0 - zf;
       const double Tz = alive ? T : tau;          // z*T_cal + (1-z)*tau, bi:298
       // ---- S Metropolis steps (bi:312-335) -------------------------------------------------------
-      double cur = log_post(ll, lm, xd, omz, Tz, m0, m1, P00, P01, P11);
+      double cur = log_post(ll, lm, xd, omz, Tz, m0, m1, P00, P01, P11, s_tab);
       for (int s = 0; s < S; ++s) {
-        double tl, tm, ua;
+        double tl, tm, ua = 0.0;
+        float uaf;
+        uint32_t ur = 0u;
         if (MODE == MODE_INJECT) {
           long long o = ((long long)chain * S + s) * N + i;
           tl = a.t3_l[o];
           tm = a.t3_m[o];
           ua = a.u_acc[o];
+          uaf = (float)ua;
         } else {
           uint4 ra = philox4x32_10(gid, a.sweep, 1u + 2u * s, DOM_SAMPLER, key);
           uint4 rb = philox4x32_10(gid, a.sweep, 2u + 2u * s, DOM_SAMPLER, key);
@@ -216,12 +264,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(SweepArgs a) {
             tl = (double)t3_fast(ra.x, ra.y, ra.z);
             tm = (double)t3_fast(ra.w, rb.x, rb.y);
           }
-          ua = u32d(rb.z);
+          ur = rb.z;
+          uaf = u32f(ur);
         }
-        double pl = fmin(fmax(ll + s_l * tl, -70.0), 70.0);     // bi:318-324
-        double pm = fmin(fmax(lm + s_m * tm, -70.0), 70.0);
-        double prop = log_post(pl, pm, xd, omz, Tz, m0, m1, P00, P01, P11);
-        if (mh_accept(prop - cur, ua)) {
+        const double pl = clip70(ll + s_l * tl);                 // bi:318-324
+        const double pm = clip70(lm + s_m * tm);
+        const double prop = log_post(pl, pm, xd, omz, Tz, m0, m1, P00, P01, P11, s_tab);
+        if (mh_accept(prop - cur, uaf, [&]() { return MODE == MODE_INJECT ? ua : u32d(ur); })) {
           ll = pl;
           lm = pm;
           cur = prop;
@@ -250,7 +299,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(SweepArgs a) {
       }
       // ---- kept draw: lambda, mu, tau, z(, eta)   bi:407-410, tri:544-548 -------------------------
       if (keep) {
-        const double lam_n = exp(ll), mu_n = exp(lm);
+        const double lam_n = exp_clip70(ll, s_tab), mu_n = exp_clip70(lm, s_tab);
         constexpr int NC = (D == 2) ? 4 : 5;
         double* o = a.draws + (((long long)chain * a.chunk_cap + a.slot) * N + i) * NC;
         if (D == 2) {
@@ -306,6 +355,93 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_stats_only(SweepArgs a) {
   const int nstat = mc.K * D + D * (D + 1) / 2;
   for (int t = tid; t < nstat; t += SWEEP_THREADS)
     if (s_acc[t]) atomicAdd(&a.acc[chain * NSTAT_MAX + t], s_acc[t]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// initialisation statistics (bi:367-374, tri:488-499) as exact integer sums: every term is rounded once to
+// fixed point (bits chosen from the global max |term|) and added in int64 (lo 32 bits / hi part separately),
+// so the totals do not depend on thread, block, shard or GPU count.  Mirrors mcmc_clv_model_b200/hostmath.py.
+// ------------------------------------------------------------------------------------------------
+constexpr int NQ_MAX = 3 + MAXK * (MAXK + 1) / 2;
+
+struct InitQArgs {
+  const int* x;
+  const double *t_x, *T_cal, *Xc, *log_s;
+  long long N;
+  int K, D, phase, mode;          // phase 0: x, tden, log_s, X_a X_b ; phase 1: mu_init, (log_s - m)^2.  mode 0: max |v| ; 1: sums
+  double lam_init, mean_log_s;
+  double scale[NQ_MAX];           // 2^bits per quantity (mode 1)
+  unsigned long long* out_max;    // [NQ] bit patterns of max |v|
+  long long* out_sum;             // [NQ][2]: lo (low 32 bits of each term), hi (term >> 32)
+};
+
+__global__ void __launch_bounds__(256) k_init_quantities(InitQArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long nwarp_tiles = (a.N + 31) / 32;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nq = a.phase == 0 ? 3 + a.K * (a.K + 1) / 2 : 2;
+  for (long long wt = wid; wt < nwarp_tiles; wt += nw) {
+    const long long i = wt * 32 + lane;
+    const bool valid = i < a.N;
+    double xv[MAXK];
+    xv[0] = 1.0;
+    double tx = 0, T = 0, ls = 0, xd = 0;
+    if (valid) {
+      xd = (double)a.x[i]; tx = a.t_x[i]; T = a.T_cal[i];
+      if (a.D == 3) ls = a.log_s[i];
+      for (int k = 1; k < a.K; ++k) xv[k] = a.Xc[(long long)(k - 1) * a.N + i];
+    }
+    int pa = 0, pb = 0;
+    for (int q = 0; q < nq; ++q) {
+      double v = 0.0;
+      if (a.phase == 0) {
+        if (q == 0) v = xd;
+        else if (q == 1) v = (tx == 0.0) ? T : tx;                      // bi:368
+        else if (q == 2) v = ls;
+        else { v = xv[pa] * xv[pb]; if (++pb == a.K) { ++pa; pb = pa; } }  // pairs a <= b, row-major
+      } else {
+        if (q == 0) v = 1.0 / (tx + 0.5 / a.lam_init);                    // bi:370
+        else { double d = ls - a.mean_log_s; v = d * d; }                 // tri:494
+      }
+      if (!valid) v = 0.0;
+      if (a.mode == 0) {
+        unsigned long long m = (unsigned long long)__double_as_longlong(fabs(v));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_down_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+        if (lane == 0 && m) atomicMax(&a.out_max[q], m);
+      } else {
+        const long long term = __double2ll_rn(v * a.scale[q]);
+        const long long lo = warp_sum_ll(term & 0xffffffffll), hi = warp_sum_ll(term >> 32);
+        if (lane == 0) {
+          if (lo) atomicAdd((unsigned long long*)&a.out_sum[2 * q], (unsigned long long)lo);
+          if (hi) atomicAdd((unsigned long long*)&a.out_sum[2 * q + 1], (unsigned long long)hi);
+        }
+      }
+    }
+  }
+}
+
+// initial level-1 state: lambda_i = lam_init, mu_i = 1/(t_x + 0.5/lam_init), eta_i = 1   (bi:369-370, tri:493)
+__global__ void __launch_bounds__(256) k_init_state(const double* t_x, long long N, int chains, int D, double lam_init,
+                                                    double* ll, double* lm, double* le) {
+  const double ll0 = log(lam_init);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    const double lm0 = log(1.0 / (t_x[i] + 0.5 / lam_init));
+    for (int c = 0; c < chains; ++c) {
+      ll[(long long)c * N + i] = ll0;
+      lm[(long long)c * N + i] = lm0;
+      if (D == 3) le[(long long)c * N + i] = 0.0;
+    }
+  }
+}
+
+// row-major (N, K) design matrix -> SoA covariate columns [(K-1)][N] (column 0, the intercept, is implicit)
+__global__ void __launch_bounds__(256) k_split_columns(const double* X, long long N, int K, double* Xc) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < N * K; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / K;
+    const int k = (int)(t - i * K);
+    if (k > 0) Xc[(long long)(k - 1) * N + i] = X[t];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

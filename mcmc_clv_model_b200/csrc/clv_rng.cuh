@@ -27,10 +27,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   uint32_t k0 = key.k0, k1 = key.k1;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-    uint32_t n0 = hi1 ^ c1 ^ k0;
-    uint32_t n2 = hi0 ^ c3 ^ k1;
+    // one IMAD.WIDE.U32 per product gives both halves
+    uint32_t lo0, hi0, lo1, hi1;
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo0), "=r"(hi0) : "r"(c0), "r"(M0));
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo1), "=r"(hi1) : "r"(c2), "r"(M1));
+    const uint32_t n0 = hi1 ^ c1 ^ k0;
+    const uint32_t n2 = hi0 ^ c3 ^ k1;
     c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
     k0 += W0; k1 += W1;
   }
@@ -43,7 +45,17 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
   return ((double)m + 0.5) * 0x1.0p-53;
 }
 __device__ __forceinline__ double u32d(uint32_t a) { return ((double)a + 0.5) * 0x1.0p-32; }
-__device__ __forceinline__ float u24f(uint32_t a) { return ((float)(a >> 8) + 0.5f) * 0x1.0p-24f; }
+// fp32 image of u32d (24 significant bits), only used to screen MH decisions
+__device__ __forceinline__ float u32f(uint32_t a) { return fmaf((float)a, 0x1.0p-32f, 0x1.0p-33f); }
+// (k + 0.5) 2^-24, k = top 24 bits: exact in fp32, one FFMA
+__device__ __forceinline__ float u24f(uint32_t a) { return fmaf((float)(a >> 8), 0x1.0p-24f, 0x1.0p-25f); }
+
+// SFU primitives without the denormal / IEEE-rounding fix-up code the default intrinsics carry
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_ftz(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sin_ftz(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float cos_ftz(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // ---- Student t(3) without rejection: N0 / sqrt((N1^2 - 2 ln U3)/3) ---------------------------------
 __device__ __forceinline__ double t3_strict(uint32_t ra, uint32_t rb, uint32_t rc) {
@@ -59,14 +71,14 @@ __device__ __forceinline__ double t3_strict(uint32_t ra, uint32_t rb, uint32_t r
 
 __device__ __forceinline__ float t3_fast(uint32_t ra, uint32_t rb, uint32_t rc) {
   constexpr float NEG2LN2 = -1.3862943611198906f;  // -2 ln 2
-  float u1 = u24f(ra), u2 = u24f(rb), u3 = u24f(rc);
-  float r2 = NEG2LN2 * __log2f(u1);                 // -2 ln u1
-  float ang = 6.2831853071795865f * u2;
-  float s, c;
-  __sincosf(ang, &s, &c);
+  const float u1 = u24f(ra), u3 = u24f(rc);
+  const float r2 = NEG2LN2 * lg2_ftz(u1);           // -2 ln u1
+  // angle 2 pi (k + 0.5) 2^-24 straight from the integer
+  const float ang = fmaf((float)(rb >> 8), 6.2831853071795865f * 0x1.0p-24f, 6.2831853071795865f * 0x1.0p-25f);
+  const float s = sin_ftz(ang), c = cos_ftz(ang);
   // n0 = sqrt(r2) c ; n1^2 = r2 s^2 ; t = n0 * rsqrt((n1^2 + e)/3)
-  float chi2 = fmaf(r2 * s, s, NEG2LN2 * __log2f(u3));
-  return c * sqrtf(r2) * rsqrtf(chi2 * 0.33333333333333333f);
+  const float chi2 = fmaf(r2 * s, s, NEG2LN2 * lg2_ftz(u3));
+  return c * sqrt_ftz(r2) * rsqrt_ftz(chi2 * 0.33333333333333333f);
 }
 
 // two standard normals from four words (53-bit uniforms, fp64): cos / sin branch

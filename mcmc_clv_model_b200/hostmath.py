@@ -18,8 +18,10 @@ _TILE = 1024
 
 def fx_bits(max_abs: float) -> int:
     """Fixed-point fraction bits such that a 1024-term tile of |v| <= max_abs fits in int64."""
-    e = 0 if max_abs <= 1.0 else math.ceil(math.log2(max_abs))
-    return 51 - e
+    if not max_abs > 1.0:
+        return 51
+    mant, ex = math.frexp(max_abs)          # max_abs = mant * 2**ex, mant in [0.5, 1)
+    return 51 - (ex - 1 if mant == 0.5 else ex)   # 51 - ceil(log2(max_abs)), exactly
 
 
 def exact_partial(v: np.ndarray, bits: int) -> int:
@@ -73,7 +75,7 @@ def init_statistics(x, t_x, T_cal, X, log_s, n_global, esum: ExactSum | None = N
         for b in range(a, K):
             xtx[a, b] = xtx[b, a] = esum(X[:, a] * X[:, b])                 # bi:248
     out = dict(lam_init=lam_init, mean_mu_init=mean_mu, mean_log_s=0.0, omega2=1.0,
-               max_abs_x=esum.amax(float(np.max(np.abs(X))) if X.size else 1.0), xtx=xtx)
+               max_abs_x=math.sqrt(max(1.0, esum.amax(float(np.max(X * X)) if X.size else 1.0))), xtx=xtx)
     if log_s is not None:
         log_s = np.asarray(log_s, dtype=np.float64)
         m = esum(log_s) / n                                                 # tri:499

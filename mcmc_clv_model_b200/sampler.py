@@ -40,7 +40,10 @@ def _pinned_empty(shape):
 class Sampler:
     def __init__(self, x, t_x, T_cal, X, log_s=None, *, model_dim=2, chains=1, chain_offset=0, n_mh_steps=20,
                  seed=0, rng="fast", compat="reference", device=0, n_global=None, gid_offset=0, hyper=None,
-                 esum: Optional[ExactSum] = None, sweep_mode="auto", init_stats=None):
+                 esum: Optional[ExactSum] = None, sweep_mode="auto", init_stats=None, comm=None):
+        """init_stats: None -> exact statistics computed on the device (all-reduced over `comm` when sharded);
+        "host" -> hostmath.init_statistics (with `esum` for sharded runs); or an explicit dict.
+        comm: (nccl_unique_id_bytes, rank, world) for customer-sharded runs."""
         self.lib = L.load()
         self.h = C.c_void_p()
         x = np.ascontiguousarray(x, dtype=np.int32)
@@ -79,12 +82,21 @@ class Sampler:
             if b0.shape != (K, D) or a0.shape != (K, K) or g0.shape != (D, D):
                 raise ValueError("hyper-parameter shapes do not match (K, D)")
             L.check(self.lib.clv_set_hyper(self.h, L.dptr(b0), L.dptr(a0), float(hy["nu_00"]), L.dptr(g0)), self.h)
-            st = init_stats or init_statistics(x, t_x, T_cal, X, log_s, self.n_global, esum)
-            self.init_stats = st
-            xtx = np.ascontiguousarray(st["xtx"], dtype=np.float64)
-            cst = L.InitStats(lam_init=st["lam_init"], mean_mu_init=st["mean_mu_init"], mean_log_s=st["mean_log_s"],
-                              omega2=st["omega2"], max_abs_x=st["max_abs_x"], xtx=L.dptr(xtx))
-            L.check(self.lib.clv_init_state(self.h, C.byref(cst)), self.h)
+            if comm is not None:
+                self.comm_init(*comm)
+            if init_stats is None and esum is None:
+                L.check(self.lib.clv_init_state(self.h, None), self.h)
+                cst, xtx = L.InitStats(), np.empty((K, K))
+                L.check(self.lib.clv_get_init_stats(self.h, C.byref(cst), L.dptr(xtx)), self.h)
+                self.init_stats = dict(lam_init=cst.lam_init, mean_mu_init=cst.mean_mu_init, mean_log_s=cst.mean_log_s,
+                                       omega2=cst.omega2, max_abs_x=cst.max_abs_x, xtx=xtx)
+            else:
+                st = init_stats if isinstance(init_stats, dict) else init_statistics(x, t_x, T_cal, X, log_s, self.n_global, esum)
+                self.init_stats = st
+                xtx = np.ascontiguousarray(st["xtx"], dtype=np.float64)
+                cst = L.InitStats(lam_init=st["lam_init"], mean_mu_init=st["mean_mu_init"], mean_log_s=st["mean_log_s"],
+                                  omega2=st["omega2"], max_abs_x=st["max_abs_x"], xtx=L.dptr(xtx))
+                L.check(self.lib.clv_init_state(self.h, C.byref(cst)), self.h)
         except Exception:
             self.close()
             raise
@@ -119,11 +131,14 @@ class Sampler:
         L.check(self.lib.clv_comm_init(self.h, buf, int(rank), int(world)), self.h)
 
     # ---- sweeps ------------------------------------------------------------------------------
-    def run(self, burnin, mcmc, thin, store_level1=True, trace=0, progress=None):
+    def run(self, burnin, mcmc, thin, store_level1=True, trace=0, progress=None, pinned=False):
         """burnin + mcmc sweeps; returns dict(level_1 [chains] of (n_draws,N,ncol) | None,
-        level_2 (chains,n_draws,P), loglik_sum (chains,n_draws) = per-draw SUM over local customers)."""
+        level_2 (chains,n_draws,P), loglik_sum (chains,n_draws) = per-draw SUM over local customers).
+        pinned=True page-locks the level-1 output (worth it only when the draws do not fit one device chunk and
+        are streamed out while the sweeps continue)."""
         n_draws = (int(mcmc) - 1) // int(thin) + 1
-        lvl1 = _pinned_empty((self.chains, n_draws, self.N, self.ncol)) if store_level1 else None
+        shape = (self.chains, n_draws, self.N, self.ncol)
+        lvl1 = (_pinned_empty(shape) if pinned else np.empty(shape)) if store_level1 else None
         lvl2 = np.empty((self.chains, n_draws, self.P))
         ll = np.empty((self.chains, n_draws))
         cb = L.PROGRESS_CB(lambda user, step, total: progress(int(step), int(total))) if progress else C.cast(None, L.PROGRESS_CB)

@@ -144,3 +144,21 @@ def test_forecast_philox_vs_oracle():
     x, _ = _forecast(g["T_cal"], [l1[:2], l1[2:]], 39.0, 77, False, 0.5)
     u = np.stack([px.forecast_uniform(77, np.arange(N), d) for d in range(nd)])
     np.testing.assert_array_equal(x, ao.forecast(g["T_cal"], l1, 39.0, u))
+
+
+@pytest.mark.parametrize("D", [2, 3])
+def test_device_init_statistics_equal_host_exact_sums(cdnow_full, D):
+    """clv_init_state(NULL): the device's exact integer sums == hostmath's, bit for bit."""
+    from mcmc_clv_model_b200.hostmath import init_statistics
+    d = cdnow_full
+    X = np.column_stack([np.ones(d["x"].size), d["first_sales_scaled"], d["gender_F"].astype(float), d["age_scaled"]])
+    log_s = d["log_s"] if D == 3 else None
+    host = init_statistics(d["x"], d["t_x"], d["T_cal"], X, log_s, d["x"].size)
+    with Sampler(d["x"], d["t_x"], d["T_cal"], X, log_s, model_dim=D, chains=1) as s:
+        dev = s.init_stats
+    for k in ("lam_init", "mean_mu_init", "mean_log_s", "omega2", "max_abs_x"):
+        assert dev[k] == host[k], (k, dev[k], host[k])
+    np.testing.assert_array_equal(dev["xtx"], host["xtx"])
+    # and close to the reference's plain NumPy means (bi:368-374)
+    lam = d["x"].mean() / np.mean(np.where(d["t_x"] == 0, d["T_cal"], d["t_x"]))
+    assert abs(dev["lam_init"] / lam - 1) < 1e-13
