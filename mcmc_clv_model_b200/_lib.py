@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclv_b200.so")
+LIB_PATH = os.environ.get("CLV_B200_LIB") or os.path.join(_HERE, "libclv_b200.so")
 
 MAX_K = 16
 RNG_FAST, RNG_STRICT, RNG_INJECTED = 0, 1, 2

@@ -20,6 +20,11 @@ constexpr int MAXK = 16;
 constexpr int MAXD = 3;
 constexpr int NSTAT_MAX = MAXK * MAXD + 6;
 constexpr int SWEEP_THREADS = 128;
+// 8 resident blocks of 128 threads per SM (<= 64 registers): measured 25% faster than the 80-register build,
+// the sweep being latency/issue bound (profiles/r01_kernel_ab.txt)
+#ifndef CLV_MINBLOCKS
+#define CLV_MINBLOCKS 8
+#endif
 
 enum : int { MODE_FAST = 0, MODE_STRICT = 1, MODE_INJECT = 2 };
 
@@ -88,6 +93,11 @@ __device__ __forceinline__ long long to_fx(double v, double scale) { return __do
 // Warp-wide int64 sum with three REDUX.SUM (32-bit) instead of a 64-bit shuffle tree:
 // v = lo + mid 2^26 + hi 2^52 (hi signed), and 32 pieces of 26 bits cannot overflow 32 bits.  All 32 lanes must call.
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
+#ifdef CLV_SHFL_SUM
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+#endif
   const unsigned lo = (unsigned)v & 0x3ffffffu, mid = (unsigned)(v >> 26) & 0x3ffffffu;
   const int hi = (int)(v >> 52);
   const unsigned slo = __reduce_add_sync(0xffffffffu, lo), smid = __reduce_add_sync(0xffffffffu, mid);
@@ -131,9 +141,11 @@ __device__ __forceinline__ double log_post(double ll, double lm, double xd, doub
 template <typename ExactU>
 __device__ __forceinline__ bool mh_accept(double d, float uf, ExactU exact_u) {
   if (d >= 0.0) return true;       // exp(d) >= 1 > u
-  const float df = (float)d, lu = 0.69314718055994531f * lg2_ftz(uf);
-  const float tol = 1e-5f * (1.0f + fabsf(lu));
-  if (uf > 1e-30f && df > -80.0f) {
+  const float df = (float)d;
+  if (uf > 1e-30f) {
+    if (df < -80.0f) return false; // exp(d) < 2e-35 < u (also d = -inf: the lm > 5 cap of bi:309)
+    const float lu = 0.69314718055994531f * lg2_ftz(uf);
+    const float tol = 1e-5f * (1.0f + fabsf(lu));
     if (df > lu + tol) return true;
     if (df < lu - tol) return false;
   }
@@ -176,7 +188,7 @@ __device__ __forceinline__ void accumulate_stats(const ModelConst& mc, const dou
 }
 
 template <int D, int MODE>
-__global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(SweepArgs a) {
+__global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArgs a) {
   __shared__ double s_beta[MAXK * MAXD];
   __shared__ double s_tab[64];
   __shared__ unsigned long long s_acc[NSTAT_MAX + 1];
