@@ -1,0 +1,52 @@
+"""Statistical parity with the reference chains (re-measured from the unmodified reference):
+posterior means of beta, Gamma, E[lambda], P(alive) within 3 Monte-Carlo standard errors (north_star)."""
+import numpy as np
+import pytest
+
+from mcmc_clv_model_b200 import Sampler
+from mcmc_clv_model_b200.diagnostics import summarize
+
+pytestmark = [pytest.mark.gpu, pytest.mark.slow]
+
+# reference pooled means and MCSE(mean) over 4 x 4000 kept draws
+REF_M1 = dict(mean=[-3.528, -3.624, 1.362, 0.226, 3.077], mcse=[0.010, 0.021, 0.013, 0.024, 0.147],
+              mean_lambda=0.0584, mean_z=0.4316, loglik=-5.4937,
+              e_lambda5=[0.0457, 0.0353, 0.0770, 0.0362, 0.0346], p_alive5=[0.872, 0.259, 0.185, 0.252, 0.292])
+REF_M2 = dict(mean=[-3.564, 0.207, -3.723, 0.059, 1.386, 0.295, 2.951],
+              mcse=[0.011, 0.003, 0.026, 0.009, 0.016, 0.033, 0.133], mean_lambda=0.0587, mean_z=0.4497, loglik=-5.4769)
+
+
+def _run(d, cov, rng, chains=16, seed=42):
+    X = np.column_stack([np.ones(d["x"].size)] + [d[c].astype(float) for c in cov])
+    with Sampler(d["x"], d["t_x"], d["T_cal"], X, model_dim=2, chains=chains, n_mh_steps=20, seed=seed, rng=rng) as s:
+        out = s.run(10000, 4000, 1, store_level1=False)
+        tail = s.run(0, 400, 4, store_level1=True)            # 100 level-1 draws per chain for customer-level checks
+    return out, tail
+
+
+def _check(out, tail, ref, n):
+    summ = summarize(out["level_2"])
+    for j, (m, se) in enumerate(zip(ref["mean"], ref["mcse"])):
+        ours, se_ours = summ[j]["mean"], summ[j]["mcse_mean"]
+        tol = 3.0 * np.hypot(se, se_ours)
+        assert abs(ours - m) < tol, f"level_2 column {j}: ours {ours:.4f} vs reference {m:.4f} (3 MCSE = {tol:.4f})"
+        assert summ[j]["rhat"] < 1.2
+    l1 = np.concatenate(list(tail["level_1"]), axis=0)
+    assert abs(l1[:, :, 0].mean() - ref["mean_lambda"]) < 0.004
+    assert abs(l1[:, :, 3].mean() - ref["mean_z"]) < 0.03
+    ll = (out["loglik_sum"] / n).mean()
+    assert abs(ll - ref["loglik"]) < 0.05
+    return l1
+
+
+@pytest.mark.parametrize("rng", ["fast", "strict"])
+def test_c1_posterior_matches_reference(cdnow_abe, rng):
+    out, tail = _run(cdnow_abe, [], rng)
+    l1 = _check(out, tail, REF_M1, cdnow_abe["x"].size)
+    np.testing.assert_allclose(l1[:, :5, 0].mean(axis=0), REF_M1["e_lambda5"], rtol=0.15)
+    np.testing.assert_allclose(l1[:, :5, 3].mean(axis=0), REF_M1["p_alive5"], atol=0.06)
+
+
+def test_m2_posterior_matches_reference_including_beta_quirk(cdnow_abe):
+    out, tail = _run(cdnow_abe, ["first_sales_scaled"], "fast")
+    _check(out, tail, REF_M2, cdnow_abe["x"].size)
