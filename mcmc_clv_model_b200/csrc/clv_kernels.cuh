@@ -313,12 +313,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArg
       if (keep) {
         const double lam_n = exp_clip70(ll, s_tab), mu_n = exp_clip70(lm, s_tab);
         constexpr int NC = (D == 2) ? 4 : 5;
-        double* o = a.draws + (((long long)chain * a.chunk_cap + a.slot) * N + i) * NC;
-        if (D == 2) {
-          reinterpret_cast<double2*>(o)[0] = make_double2(lam_n, mu_n);
-          reinterpret_cast<double2*>(o)[1] = make_double2(tau, zf);
-        } else {
-          o[0] = lam_n; o[1] = mu_n; o[2] = tau; o[3] = zf; o[4] = exp(le);
+        if (a.draws) {           // level-1 storage is optional (clv_run with level1 == NULL)
+          double* o = a.draws + (((long long)chain * a.chunk_cap + a.slot) * N + i) * NC;
+          if (D == 2) {
+            reinterpret_cast<double2*>(o)[0] = make_double2(lam_n, mu_n);
+            reinterpret_cast<double2*>(o)[1] = make_double2(tau, zf);
+          } else {
+            o[0] = lam_n; o[1] = mu_n; o[2] = tau; o[3] = zf; o[4] = exp(le);
+          }
         }
         lik = xd * ll + omz * lm - (lam_n + mu_n) * Tz;         // bi:423-427
         lik = fmin(fmax(lik, -1048576.0), 1048576.0);
