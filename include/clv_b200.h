@@ -111,7 +111,8 @@ int clv_init_state(clv_sampler* h, const clv_init_stats* stats);
 int clv_get_init_stats(clv_sampler* h, clv_init_stats* out, double* xtx_out);
 /* Customer-sharded mode: join the NCCL communicator used for the per-sweep all-reduce of the
  * level-2 sufficient statistics.  unique_id is the 128-byte ncclUniqueId from clv_comm_unique_id
- * on rank 0, broadcast by the host (torch.distributed). */
+ * on rank 0, broadcast by the host (torch.distributed).  The communicator is created once per
+ * (device, rank, world) and reused by later handles of the same process (unique_id is then ignored). */
 int clv_comm_unique_id(void* out128);
 int clv_comm_init(clv_sampler* h, const void* unique_id128, int rank, int world);
 

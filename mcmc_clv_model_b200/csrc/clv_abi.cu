@@ -50,6 +50,10 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 constexpr int NCCL_INT64 = 4, NCCL_SUM = 0;
+// communicators are created once per (device, rank, world) and shared by every later handle of the process:
+// ncclCommInitRank costs seconds, a sampler call should not pay it twice
+struct CachedComm { int device, rank, world; nccl_comm_t comm; };
+std::vector<CachedComm> g_comms;
 
 }  // namespace
 
@@ -82,6 +86,11 @@ struct clv_sampler {
   long long resident_draws = 0;
   // injected staging
   double* d_inj = nullptr; long long inj_cap = 0;
+  // persistent mode
+  unsigned long long* d_acc3 = nullptr;
+  unsigned int* d_barrier = nullptr;
+  int persist_grid_x = 0;          // 0: cooperative launch not possible for this problem
+  bool persist_fits = false;       // every tile has its own co-resident block (small problems: AUTO picks persistent)
   // bookkeeping
   long long sweeps_done = 0, launches = 0;
   int grid_x = 1;
@@ -373,6 +382,22 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   long long ntiles = (h->N + SWEEP_THREADS - 1) / SWEEP_THREADS;
   long long want = ((long long)h->sm_count * 32 + h->chains - 1) / h->chains;
   h->grid_x = (int)std::max<long long>(1, std::min(ntiles, want));
+  // persistent cooperative mode: all blocks must be co-resident
+  CKC(dmalloc(&h->d_acc3, 3 * C * NSTAT_MAX));
+  CKC(dmalloc(&h->d_barrier, 2));
+  CKC(cudaMemset(h->d_barrier, 0, 2 * sizeof(unsigned int)));
+  {
+    int coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
+    cudaError_t eo = (h->D == 2)
+        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<2, MODE_FAST>, SWEEP_THREADS, 0)
+        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<3, MODE_FAST>, SWEEP_THREADS, 0);
+    long long maxb = (eo == cudaSuccess && coop) ? (long long)per_sm * h->sm_count : 0;
+    if (maxb >= h->chains) {
+      h->persist_grid_x = (int)std::min<long long>(ntiles, maxb / h->chains);
+      h->persist_fits = (long long)h->persist_grid_x == ntiles;
+    }
+  }
 #undef CKC
   *out = h;
   return CLV_OK;
@@ -383,7 +408,8 @@ void clv_destroy(clv_sampler* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  if (h->d_acc3) cudaFree(h->d_acc3);
+  if (h->d_barrier) cudaFree(h->d_barrier);
   void* ptrs[] = {h->d_mc, h->d_params, h->d_x, h->d_tx, h->d_T, h->d_Xc, h->d_logs, h->d_ll, h->d_lm, h->d_le,
                   h->d_z, h->d_tau, h->d_acc, h->d_err, h->d_loglik, h->d_level2, h->d_draws[0], h->d_draws[1], h->d_inj};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -636,11 +662,14 @@ int clv_comm_init(clv_sampler* h, const void* unique_id128, int rank, int world)
   std::string err;
   if (!g_nccl.load(err)) return fail(h, CLV_ERR_COMM, "%s", err.c_str());
   CK(h, cudaSetDevice(h->cfg.device));
+  h->world = world; h->rank = rank;
+  for (auto& c : g_comms)
+    if (c.device == h->cfg.device && c.rank == rank && c.world == world) { h->comm = c.comm; return CLV_OK; }
   NcclUid id;
   std::memcpy(&id, unique_id128, sizeof id);
   int r = g_nccl.CommInitRank(&h->comm, world, id, rank);
   if (r != 0) return fail(h, CLV_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
-  h->world = world; h->rank = rank;
+  g_comms.push_back({h->cfg.device, rank, world, h->comm});
   return CLV_OK;
 }
 
@@ -669,17 +698,109 @@ int clv_kernel_time_ms(clv_sampler* h, double* sweep_ms, double* l2_ms, int64_t*
   return CLV_OK;
 }
 
+
+namespace {
+
+bool want_persistent(const clv_sampler* h) {
+  if (h->comm || h->timing || h->persist_grid_x <= 0 || h->cfg.rng_mode == CLV_RNG_INJECTED) return false;
+  if (h->cfg.sweep_mode == CLV_SWEEP_PERSISTENT) return true;
+  return h->cfg.sweep_mode == CLV_SWEEP_AUTO && h->persist_fits;
+}
+
+struct RunCtx {                 // draw bookkeeping of the current clv_run (zeros for clv_advance)
+  long long burnin = 0, thin = 1, n_draws = 1, chunk_base = 0, cap = 1, step0 = 1;
+  double* draws = nullptr;
+  bool keep_any = false;
+};
+
+// n sweeps fused in one cooperative launch (grid barrier per sweep).
+int launch_persistent(clv_sampler* h, const RunCtx& rc, long long n, bool store_zt_last) {
+  const size_t slot_bytes = sizeof(unsigned long long) * h->chains * NSTAT_MAX;
+  const uint32_t first = (uint32_t)(h->sweeps_done + 1), last = (uint32_t)(h->sweeps_done + n);
+  CK(h, cudaMemsetAsync(h->d_acc3, 0, 3 * slot_bytes, h->stream));
+  if (h->D == 2)   // statistics of the current state feed the first level-2 draw (bi:393)
+    CK(h, cudaMemcpyAsync(h->d_acc3 + (size_t)((first + 2u) % 3u) * h->chains * NSTAT_MAX, h->d_acc, slot_bytes,
+                          cudaMemcpyDeviceToDevice, h->stream));
+  PersistArgs pa{};
+  pa.sw = base_args(h);
+  pa.sw.loglik_stride = rc.n_draws;
+  pa.sw.draws = rc.draws;
+  pa.sw.chunk_cap = rc.cap;
+  pa.params = h->d_params;
+  pa.acc3 = h->d_acc3;
+  pa.level2_draws = h->d_level2;
+  pa.n_draws = rc.n_draws;
+  pa.first_sweep = first;
+  pa.n_sweeps = (uint32_t)n;
+  pa.run_step0 = rc.step0;
+  pa.burnin = rc.keep_any ? rc.burnin : (1ll << 62);
+  pa.thin = rc.thin;
+  pa.chunk_base = rc.chunk_base;
+  pa.store_zt_last = store_zt_last ? 1 : 0;
+  pa.error_flag = h->d_err;
+  pa.barrier = h->d_barrier;
+  dim3 grid(h->persist_grid_x, h->chains), block(SWEEP_THREADS);
+  void* args[] = {&pa};
+  const void* fn;
+  const bool strict = h->cfg.rng_mode == CLV_RNG_PHILOX_STRICT;
+  if (h->D == 2) fn = strict ? (const void*)k_persistent<2, MODE_STRICT> : (const void*)k_persistent<2, MODE_FAST>;
+  else fn = strict ? (const void*)k_persistent<3, MODE_STRICT> : (const void*)k_persistent<3, MODE_FAST>;
+  CK(h, cudaLaunchCooperativeKernel(fn, grid, block, args, 0, h->stream));
+  h->launches++;
+  if (h->D == 2)
+    CK(h, cudaMemcpyAsync(h->d_acc, h->d_acc3 + (size_t)(last % 3u) * h->chains * NSTAT_MAX, slot_bytes,
+                          cudaMemcpyDeviceToDevice, h->stream));
+  else
+    CK(h, cudaMemsetAsync(h->d_acc, 0, slot_bytes, h->stream));
+  h->sweeps_done += n;
+  return 0;
+}
+
+// Sweeps [rc.step0, rc.step0 + n) of the current run, stream mode: two kernels per sweep.
+int run_stream_segment(clv_sampler* h, const RunCtx& rc, long long n, bool store_zt_last) {
+  for (long long it = 0; it < n; ++it) {
+    const long long step = rc.step0 + it;
+    SweepArgs a = base_args(h);
+    Level2Args l2 = base_l2(h);
+    a.sweep = l2.sweep = (uint32_t)(h->sweeps_done + 1);
+    l2.n_draws = rc.n_draws;
+    a.loglik_stride = rc.n_draws;
+    const bool kept = rc.keep_any && step > rc.burnin && (step - 1 - rc.burnin) % rc.thin == 0;      // bi:402
+    if (kept) {
+      const long long draw = (step - 1 - rc.burnin) / rc.thin;
+      a.draw_index = l2.draw_index = draw;
+      a.slot = 0;
+      if (rc.draws) {
+        a.draws = rc.draws;
+        a.chunk_cap = rc.cap;
+        a.slot = draw - rc.chunk_base;
+      }
+    }
+    if (store_zt_last && it + 1 == n) a.store_zt = 1;
+    if (int r = enqueue_sweep(h, a, l2, h->cfg.rng_mode)) return r;
+    if (h->timing && (it & 1023) == 1023) { CK(h, cudaStreamSynchronize(h->stream)); collect_timing(h); }
+  }
+  return 0;
+}
+
+int run_segment(clv_sampler* h, const RunCtx& rc, long long n, bool store_zt_last) {
+  if (n <= 0) return 0;
+  return want_persistent(h) ? launch_persistent(h, rc, n, store_zt_last) : run_stream_segment(h, rc, n, store_zt_last);
+}
+
+}  // namespace
+
 int clv_advance(clv_sampler* h, int64_t n_sweeps, int sync) {
   if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
   if (!h->inited) return fail(h, CLV_ERR_STATE, "clv_advance: call clv_init_state first");
   if (h->cfg.rng_mode == CLV_RNG_INJECTED) return fail(h, CLV_ERR_ARG, "handle is in injected-RNG mode; use clv_sweep_injected");
   CK(h, cudaSetDevice(h->cfg.device));
-  for (int64_t s = 0; s < n_sweeps; ++s) {
-    SweepArgs a = base_args(h);
-    Level2Args l2 = base_l2(h);
-    a.sweep = l2.sweep = (uint32_t)(h->sweeps_done + 1);
-    if (int r = enqueue_sweep(h, a, l2, h->cfg.rng_mode)) return r;
-    if (h->timing && (s & 1023) == 1023) { CK(h, cudaStreamSynchronize(h->stream)); collect_timing(h); }
+  RunCtx rc;
+  // cooperative launches are bounded so that a runaway kernel cannot outlive the watchdog of a shared box
+  for (int64_t done = 0; done < n_sweeps;) {
+    const long long n = std::min<long long>(n_sweeps - done, 20000);
+    if (int r = run_segment(h, rc, n, false)) return r;
+    done += n;
   }
   if (sync) return check_device_error(h);
   return CLV_OK;
@@ -777,44 +898,39 @@ int clv_run(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* 
     used[buf] = true;
     return 0;
   };
-  for (long long step = 1; step <= total; ++step) {
-    SweepArgs a = base_args(h);
-    Level2Args l2 = base_l2(h);
-    a.sweep = l2.sweep = (uint32_t)(h->sweeps_done + 1);
-    l2.n_draws = n_draws;
-    a.loglik_stride = n_draws;
-    const bool kept = step > burnin && (step - 1 - burnin) % thin == 0;      // bi:402
-    if (kept) {
-      const long long draw = (step - 1 - burnin) / thin;
-      a.draw_index = l2.draw_index = draw;
-      a.slot = 0;
-      if (level1) {
-        a.draws = h->d_draws[buf];
-        a.chunk_cap = cap;
-        a.slot = draw - chunk_base;
-      }
-      a.store_zt = 0;
+  // The run is cut into segments that end where the host has to act: a full draw chunk (flush), a progress
+  // callback, or the end.  A segment is one cooperative launch (persistent mode) or 2 launches per sweep.
+  long long step = 1;
+  while (step <= total) {
+    long long seg_end = total;
+    if (level1) {
+      const long long last_draw = std::min(n_draws - 1, chunk_base + cap - 1);
+      seg_end = std::min(seg_end, burnin + 1 + last_draw * thin);
+      if (last_draw == n_draws - 1) seg_end = total;         // trailing non-kept sweeps ride with the last chunk
     }
-    if (step == total) a.store_zt = 1;
-    if (int r = enqueue_sweep(h, a, l2, h->cfg.rng_mode)) return r;
-    if (kept && level1) {
-      const long long draw = (step - 1 - burnin) / thin;
-      const long long filled = draw - chunk_base + 1;
-      if (filled == cap || draw == n_draws - 1) {
+    if (trace > 0) seg_end = std::min(seg_end, ((step + trace - 1) / trace) * trace);
+    seg_end = std::min(seg_end, step + 19999);
+    RunCtx rc;
+    rc.burnin = burnin; rc.thin = thin; rc.n_draws = n_draws; rc.chunk_base = chunk_base; rc.cap = level1 ? cap : 1;
+    rc.step0 = step; rc.draws = level1 ? h->d_draws[buf] : nullptr; rc.keep_any = true;
+    if (int r = run_segment(h, rc, seg_end - step + 1, seg_end == total)) return r;
+    step = seg_end + 1;
+    if (level1) {
+      // draws kept so far: those with burnin + 1 + d*thin <= seg_end
+      const long long kept_upto = seg_end > burnin ? std::min(n_draws, (seg_end - burnin - 1) / thin + 1) : 0;
+      const long long filled = kept_upto - chunk_base;
+      if (filled > 0 && (filled == cap || kept_upto == n_draws)) {
         if (int r = flush(filled)) return r;
         chunk_base += filled;
-        if (draw != n_draws - 1) {
+        if (kept_upto != n_draws) {
           buf ^= 1;
           if (used[buf]) CK(h, cudaStreamWaitEvent(h->stream, h->ev_copy_done[buf], 0));
         }
       }
     }
-    if (trace > 0 && step % trace == 0) {                                      // bi:384-385
+    if (trace > 0 && seg_end % trace == 0) {                                   // bi:384-385
       if (int r = check_device_error(h)) return r;
-      if (cb) cb(user, step, total);
-    } else if (h->timing && (step & 1023) == 0) {
-      CK(h, cudaStreamSynchronize(h->stream));
-      collect_timing(h);
+      if (cb) cb(user, seg_end, total);
     }
   }
   if (int r = check_device_error(h)) return r;

@@ -187,6 +187,155 @@ __device__ __forceinline__ void accumulate_stats(const ModelConst& mc, const dou
     }
 }
 
+// Per-sweep scalars (kernel arguments in stream mode, computed on the device in persistent mode).
+struct SweepStep {
+  uint32_t sweep;        // 1-based sweep number (Philox counter)
+  int keep;              // this sweep is a kept draw
+  int store_zt;          // write z / tau state arrays
+  long long slot;        // slot inside the draw chunk
+  long long chunk_cap;
+  double* draws;         // nullable
+};
+
+// One tile of 128 customers of one chain through one Gibbs sweep (blocks a1-a3, a5 of SURVEY 8a) plus its share of
+// the level-2 statistics.  cp / s_beta / s_tab / s_acc live in shared memory.
+template <int D, int MODE>
+__device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst& mc, const ChainParams& cp,
+                                           const double* s_beta, const double* s_tab, unsigned long long* s_acc,
+                                           const SweepStep& sw, int chain, long long tile, PhiloxKey key) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int K = mc.K, S = mc.S;
+  const long long N = mc.N;
+  const long long cN = (long long)chain * N;
+  const double P00 = cp.P00, P01 = cp.P01, P11 = cp.P11;
+  const double s_l = cp.Sigma[0], s_m = cp.Sigma[D + 1];   // proposal scales are variances (bi:316-317, Q2)
+  const bool keep = sw.keep != 0;
+  const long long i = tile * SWEEP_THREADS + tid;
+  const bool valid = i < N;
+  double yc0 = 0.0, yc1 = 0.0, yc2 = 0.0, lik = 0.0;
+  if (valid) {
+    const uint32_t gid = (uint32_t)(mc.gid_offset + i);
+    const double xd = (double)a.x[i];
+    const double tx = a.t_x[i], T = a.T_cal[i];
+    double ll = a.ll[cN + i], lm = a.lm[cN + i];
+    // prior means (X beta)[i, :]   bi:284
+    double m0 = s_beta[0], m1 = s_beta[1], m2 = (D == 3) ? s_beta[2] : 0.0;
+    for (int k = 1; k < K; ++k) {
+      double xk = a.Xc[(long long)(k - 1) * N + i];
+      m0 = fma(xk, s_beta[k * D + 0], m0);
+      m1 = fma(xk, s_beta[k * D + 1], m1);
+      if (D == 3) m2 = fma(xk, s_beta[k * D + 2], m2);
+    }
+    // ---- z (bi:193-200) and tau (bi:203-227) from the current lambda, mu -------------------------
+    const double lam = exp_clip70(ll, s_tab), mu = exp_clip70(lm, s_tab);   // |ll|, |lm| <= 70 by construction
+    double uz, ut, et;
+    if (MODE == MODE_INJECT) {
+      uz = a.u_z[cN + i];
+      ut = a.u_tau[cN + i];
+      et = a.e_tau[cN + i];
+    } else {
+      uint4 r = philox4x32_10(gid, sw.sweep, 0u, DOM_SAMPLER, key);
+      uz = u53(r.x, r.y);
+      ut = u53(r.z, r.w);
+      et = 0.0;
+    }
+    const double ml = mu + lam;
+    const double e = exp(-(ml * (T - tx)));
+    const double pa = (ml * e) / (ml * e + mu * (1.0 - e));
+    const bool alive = uz < pa;
+    double tau;
+    if (alive) {
+      if (MODE != MODE_INJECT) et = -log(ut);
+      tau = T + (1.0 / mu) * et;
+    } else {
+      double mtx = fmin(700.0, ml * tx), mT = fmin(700.0, ml * T);
+      tau = -log((1.0 - ut) * exp(-mtx) + ut * exp(-mT)) / ml;
+    }
+    const double zf = alive ? 1.0 : 0.0;
+    const double omz = 1.0 - zf;
+    const double Tz = alive ? T : tau;          // z*T_cal + (1-z)*tau, bi:298
+    // ---- S Metropolis steps (bi:312-335) -------------------------------------------------------
+    double cur = log_post(ll, lm, xd, omz, Tz, m0, m1, P00, P01, P11, s_tab);
+    for (int s = 0; s < S; ++s) {
+      double tl, tm, ua = 0.0;
+      float uaf;
+      uint32_t ur = 0u;
+      if (MODE == MODE_INJECT) {
+        long long o = ((long long)chain * S + s) * N + i;
+        tl = a.t3_l[o];
+        tm = a.t3_m[o];
+        ua = a.u_acc[o];
+        uaf = (float)ua;
+      } else {
+        uint4 ra = philox4x32_10(gid, sw.sweep, 1u + 2u * s, DOM_SAMPLER, key);
+        uint4 rb = philox4x32_10(gid, sw.sweep, 2u + 2u * s, DOM_SAMPLER, key);
+        if (MODE == MODE_STRICT) {
+          tl = t3_strict(ra.x, ra.y, ra.z);
+          tm = t3_strict(ra.w, rb.x, rb.y);
+        } else {
+          tl = (double)t3_fast(ra.x, ra.y, ra.z);
+          tm = (double)t3_fast(ra.w, rb.x, rb.y);
+        }
+        ur = rb.z;
+        uaf = u32f(ur);
+      }
+      const double pl = clip70(ll + s_l * tl);                 // bi:318-324
+      const double pm = clip70(lm + s_m * tm);
+      const double prop = log_post(pl, pm, xd, omz, Tz, m0, m1, P00, P01, P11, s_tab);
+      if (mh_accept(prop - cur, uaf, [&]() { return MODE == MODE_INJECT ? ua : u32d(ur); })) {
+        ll = pl;
+        lm = pm;
+        cur = prop;
+      }
+    }
+    a.ll[cN + i] = ll;
+    a.lm[cN + i] = lm;
+    // ---- eta (tri:306-333, 524-526) ------------------------------------------------------------
+    double le = 0.0;
+    if (D == 3) {
+      double n;
+      if (MODE == MODE_INJECT) {
+        n = a.n_eta[cN + i];
+      } else {
+        double ns;
+        normal_pair_u53(philox4x32_10(gid, sw.sweep, 1u + 2u * (uint32_t)S, DOM_SAMPLER, key), &n, &ns);
+      }
+      const double prior_var = cp.Sigma[8];
+      double post_mean = cp.eta_post_var * (a.log_s[i] / mc.omega2 + m2 / prior_var);
+      le = post_mean + cp.eta_sd * n;
+      a.le[cN + i] = le;
+    }
+    if (sw.store_zt) {
+      a.z[cN + i] = zf;
+      a.tau[cN + i] = tau;
+    }
+    // ---- kept draw: lambda, mu, tau, z(, eta)   bi:407-410, tri:544-548 -------------------------
+    if (keep) {
+      const double lam_n = exp_clip70(ll, s_tab), mu_n = exp_clip70(lm, s_tab);
+      constexpr int NC = (D == 2) ? 4 : 5;
+      if (sw.draws) {           // level-1 storage is optional (clv_run with level1 == NULL)
+        double* o = sw.draws + (((long long)chain * sw.chunk_cap + sw.slot) * N + i) * NC;
+        if (D == 2) {
+          reinterpret_cast<double2*>(o)[0] = make_double2(lam_n, mu_n);
+          reinterpret_cast<double2*>(o)[1] = make_double2(tau, zf);
+        } else {
+          o[0] = lam_n; o[1] = mu_n; o[2] = tau; o[3] = zf; o[4] = exp(le);
+        }
+      }
+      lik = xd * ll + omz * lm - (lam_n + mu_n) * Tz;         // bi:423-427
+      lik = fmin(fmax(lik, -1048576.0), 1048576.0);
+    }
+    yc0 = ll - mc.center[0];
+    yc1 = lm - mc.center[1];
+    if (D == 3) yc2 = le - mc.center[2];
+  }
+  accumulate_stats<D>(mc, a.Xc, N, i, valid, yc0, yc1, yc2, s_acc, lane);
+  if (keep) {
+    long long v = warp_sum_ll(valid ? to_fx(lik, mc.ll_scale) : 0ll);
+    if (lane == 0) atomicAdd(&s_acc[NSTAT_MAX], (unsigned long long)v);
+  }
+}
+
 template <int D, int MODE>
 __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArgs a) {
   __shared__ double s_beta[MAXK * MAXD];
@@ -194,152 +343,25 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArg
   __shared__ unsigned long long s_acc[NSTAT_MAX + 1];
   const ModelConst& mc = *a.mc;
   const int chain = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int K = mc.K, S = mc.S;
-  const long long N = mc.N;
+  const int tid = threadIdx.x;
+  const int K = mc.K;
   const ChainParams& cp = a.params[chain];
   for (int t = tid; t < K * D; t += SWEEP_THREADS) s_beta[t] = cp.beta[t];
   if (tid < 64) s_tab[tid] = c_exptab[tid];
   for (int t = tid; t < NSTAT_MAX + 1; t += SWEEP_THREADS) s_acc[t] = 0ull;
   __syncthreads();
-  const double P00 = cp.P00, P01 = cp.P01, P11 = cp.P11;
-  const double s_l = cp.Sigma[0], s_m = cp.Sigma[D + 1];   // proposal scales are variances (bi:316-317, Q2)
   const PhiloxKey key = chain_key(a.seed, a.chain_offset + (uint32_t)chain);
-  const bool keep = a.slot >= 0;
-  const long long ntiles = (N + SWEEP_THREADS - 1) / SWEEP_THREADS;
-  const long long cN = (long long)chain * N;
-
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long i = tile * SWEEP_THREADS + tid;
-    const bool valid = i < N;
-    double yc0 = 0.0, yc1 = 0.0, yc2 = 0.0, lik = 0.0;
-    if (valid) {
-      const uint32_t gid = (uint32_t)(mc.gid_offset + i);
-      const double xd = (double)a.x[i];
-      const double tx = a.t_x[i], T = a.T_cal[i];
-      double ll = a.ll[cN + i], lm = a.lm[cN + i];
-      // prior means (X beta)[i, :]   bi:284
-      double m0 = s_beta[0], m1 = s_beta[1], m2 = (D == 3) ? s_beta[2] : 0.0;
-      for (int k = 1; k < K; ++k) {
-        double xk = a.Xc[(long long)(k - 1) * N + i];
-        m0 = fma(xk, s_beta[k * D + 0], m0);
-        m1 = fma(xk, s_beta[k * D + 1], m1);
-        if (D == 3) m2 = fma(xk, s_beta[k * D + 2], m2);
-      }
-      // ---- z (bi:193-200) and tau (bi:203-227) from the current lambda, mu -------------------------
-      const double lam = exp_clip70(ll, s_tab), mu = exp_clip70(lm, s_tab);   // |ll|, |lm| <= 70 by construction
-      double uz, ut, et;
-      if (MODE == MODE_INJECT) {
-        uz = a.u_z[cN + i];
-        ut = a.u_tau[cN + i];
-        et = a.e_tau[cN + i];
-      } else {
-        uint4 r = philox4x32_10(gid, a.sweep, 0u, DOM_SAMPLER, key);
-        uz = u53(r.x, r.y);
-        ut = u53(r.z, r.w);
-        et = 0.0;
-      }
-      const double ml = mu + lam;
-      const double e = exp(-(ml * (T - tx)));
-      const double pa = (ml * e) / (ml * e + mu * (1.0 - e));
-      const bool alive = uz < pa;
-      double tau;
-      if (alive) {
-        if (MODE != MODE_INJECT) et = -log(ut);
-        tau = T + (1.0 / mu) * et;
-      } else {
-        double mtx = fmin(700.0, ml * tx), mT = fmin(700.0, ml * T);
-        tau = -log((1.0 - ut) * exp(-mtx) + ut * exp(-mT)) / ml;
-      }
-      const double zf = alive ? 1.0 : 0.0;
-      const double omz = 1.0 - zf;
-      const double Tz = alive ? T : tau;          // z*T_cal + (1-z)*tau, bi:298
-      // ---- S Metropolis steps (bi:312-335) -------------------------------------------------------
-      double cur = log_post(ll, lm, xd, omz, Tz, m0, m1, P00, P01, P11, s_tab);
-      for (int s = 0; s < S; ++s) {
-        double tl, tm, ua = 0.0;
-        float uaf;
-        uint32_t ur = 0u;
-        if (MODE == MODE_INJECT) {
-          long long o = ((long long)chain * S + s) * N + i;
-          tl = a.t3_l[o];
-          tm = a.t3_m[o];
-          ua = a.u_acc[o];
-          uaf = (float)ua;
-        } else {
-          uint4 ra = philox4x32_10(gid, a.sweep, 1u + 2u * s, DOM_SAMPLER, key);
-          uint4 rb = philox4x32_10(gid, a.sweep, 2u + 2u * s, DOM_SAMPLER, key);
-          if (MODE == MODE_STRICT) {
-            tl = t3_strict(ra.x, ra.y, ra.z);
-            tm = t3_strict(ra.w, rb.x, rb.y);
-          } else {
-            tl = (double)t3_fast(ra.x, ra.y, ra.z);
-            tm = (double)t3_fast(ra.w, rb.x, rb.y);
-          }
-          ur = rb.z;
-          uaf = u32f(ur);
-        }
-        const double pl = clip70(ll + s_l * tl);                 // bi:318-324
-        const double pm = clip70(lm + s_m * tm);
-        const double prop = log_post(pl, pm, xd, omz, Tz, m0, m1, P00, P01, P11, s_tab);
-        if (mh_accept(prop - cur, uaf, [&]() { return MODE == MODE_INJECT ? ua : u32d(ur); })) {
-          ll = pl;
-          lm = pm;
-          cur = prop;
-        }
-      }
-      a.ll[cN + i] = ll;
-      a.lm[cN + i] = lm;
-      // ---- eta (tri:306-333, 524-526) ------------------------------------------------------------
-      double le = 0.0;
-      if (D == 3) {
-        double n;
-        if (MODE == MODE_INJECT) {
-          n = a.n_eta[cN + i];
-        } else {
-          double ns;
-          normal_pair_u53(philox4x32_10(gid, a.sweep, 1u + 2u * (uint32_t)S, DOM_SAMPLER, key), &n, &ns);
-        }
-        const double prior_var = cp.Sigma[8];
-        double post_mean = cp.eta_post_var * (a.log_s[i] / mc.omega2 + m2 / prior_var);
-        le = post_mean + cp.eta_sd * n;
-        a.le[cN + i] = le;
-      }
-      if (a.store_zt) {
-        a.z[cN + i] = zf;
-        a.tau[cN + i] = tau;
-      }
-      // ---- kept draw: lambda, mu, tau, z(, eta)   bi:407-410, tri:544-548 -------------------------
-      if (keep) {
-        const double lam_n = exp_clip70(ll, s_tab), mu_n = exp_clip70(lm, s_tab);
-        constexpr int NC = (D == 2) ? 4 : 5;
-        if (a.draws) {           // level-1 storage is optional (clv_run with level1 == NULL)
-          double* o = a.draws + (((long long)chain * a.chunk_cap + a.slot) * N + i) * NC;
-          if (D == 2) {
-            reinterpret_cast<double2*>(o)[0] = make_double2(lam_n, mu_n);
-            reinterpret_cast<double2*>(o)[1] = make_double2(tau, zf);
-          } else {
-            o[0] = lam_n; o[1] = mu_n; o[2] = tau; o[3] = zf; o[4] = exp(le);
-          }
-        }
-        lik = xd * ll + omz * lm - (lam_n + mu_n) * Tz;         // bi:423-427
-        lik = fmin(fmax(lik, -1048576.0), 1048576.0);
-      }
-      yc0 = ll - mc.center[0];
-      yc1 = lm - mc.center[1];
-      if (D == 3) yc2 = le - mc.center[2];
-    }
-    accumulate_stats<D>(mc, a.Xc, N, i, valid, yc0, yc1, yc2, s_acc, lane);
-    if (keep) {
-      long long v = warp_sum_ll(valid ? to_fx(lik, mc.ll_scale) : 0ll);
-      if (lane == 0) atomicAdd(&s_acc[NSTAT_MAX], (unsigned long long)v);
-    }
-  }
+  SweepStep sw;
+  sw.sweep = a.sweep; sw.keep = a.slot >= 0; sw.store_zt = a.store_zt; sw.slot = a.slot; sw.chunk_cap = a.chunk_cap;
+  sw.draws = a.draws;
+  const long long ntiles = (mc.N + SWEEP_THREADS - 1) / SWEEP_THREADS;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    sweep_tile<D, MODE>(a, mc, cp, s_beta, s_tab, s_acc, sw, chain, tile, key);
   __syncthreads();
   const int nstat = K * D + D * (D + 1) / 2;
   for (int t = tid; t < nstat; t += SWEEP_THREADS)
     if (s_acc[t]) atomicAdd(&a.acc[chain * NSTAT_MAX + t], s_acc[t]);
-  if (keep && tid == 0)
+  if (sw.keep && tid == 0)
     atomicAdd(reinterpret_cast<unsigned long long*>(&a.loglik_acc[chain * a.loglik_stride + a.draw_index]),
               s_acc[NSTAT_MAX]);
 }
@@ -529,137 +551,266 @@ struct Level2Args {
   int* error_flag;
 };
 
-// Conjugate multivariate regression draw (bi:233-262, tri:340-380) from the reduced statistics.
+// Shared-memory scratch of one level-2 draw (one warp).
+struct Level2Scratch {
+  double st[NSTAT_MAX];            // reduced statistics: X'Yc [k*D+d], then triu(Yc'Yc)
+  double trn[3], chi[3], zb[MAXD * MAXK];
+  double R[MAXK * MAXD], Bc[MAXK * MAXD], W[MAXD * MAXK], Ef[MAXD * MAXK];
+  double Sn[MAXD * MAXD], CA[MAXD * MAXD];
+  int ok;
+};
+
+// Conjugate multivariate regression draw (bi:233-262, tri:340-380) from the reduced statistics, by ONE WARP:
+// the variates and every small matrix product are spread over the lanes; the D x D factorisations run on lane 0.
 // Works in centred responses y - c (c = prior intercept row), which leaves E and beta - B0 unchanged.
+// sc.st must be filled (and visible to the warp) on entry; cp (shared or global memory) receives beta, Sigma, P.
+template <int D>
+__device__ __forceinline__ void level2_draw(const ModelConst& mc, Level2Scratch& sc, ChainParams& cp, PhiloxKey key,
+                                            uint32_t sweep, int injected, const double* iw_norm, const double* iw_chi2,
+                                            const double* beta_norm, int lane) {
+  const int K = mc.K;
+  constexpr int ntril = D * (D - 1) / 2;
+  const int nb = D * K;
+  // variates (fp64 Philox transforms are long dependent chains: one per lane)
+  for (int t = lane; t < ntril + D + nb; t += 32) {
+    if (t < ntril) sc.trn[t] = injected ? iw_norm[t] : level2_normal(key, sweep, (uint32_t)t);
+    else if (t < ntril + D) {
+      const int i = t - ntril;
+      sc.chi[i] = injected ? iw_chi2[i] : level2_chi2(key, sweep, 16u + i, mc.nu_n - D + 1 + i);   // chi2(nu_n - D + 1 + i)
+    } else {
+      const int j = t - ntril - D;
+      sc.zb[j] = injected ? beta_norm[j] : level2_normal(key, sweep, 32u + (uint32_t)j);
+    }
+  }
+  // R = X'Yc + A0 B0c                                           bi:250
+  for (int t = lane; t < nb; t += 32) sc.R[t] = sc.st[t] + mc.A0B0c[t];
+  __syncwarp();
+  // Bc = V R ; W = chol(V) z (per response)
+  for (int t = lane; t < nb; t += 32) {
+    const int k = t / D, d = t - k * D;
+    double s = 0.0;
+    for (int m = 0; m < K; ++m) s += mc.V[k * K + m] * sc.R[m * D + d];
+    sc.Bc[t] = s;
+  }
+  for (int t = lane; t < nb; t += 32) {
+    const int d = t / K, k = t - d * K;
+    double s = 0.0;
+    for (int m = 0; m <= k; ++m) s += mc.LV[k * K + m] * sc.zb[d * K + m];
+    sc.W[t] = s;
+  }
+  __syncwarp();
+  // S_n = S0 + E'E + C'A0C = Q0 + Yc'Yc - Bc' R                bi:253-255
+  if (lane < D * D) {
+    const int d = lane / D, e = lane - d * D;
+    const int lo = d < e ? d : e, hi = d < e ? e : d;
+    const int t = nb + lo * D - lo * (lo - 1) / 2 + (hi - lo);   // index of (lo, hi) in the row-major upper triangle
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < K; ++k) {
+      s1 += sc.Bc[k * D + d] * sc.R[k * D + e];
+      s2 += sc.Bc[k * D + e] * sc.R[k * D + d];
+    }
+    sc.Sn[lane] = sc.st[t] + mc.Q0[lane] - 0.5 * (s1 + s2);        // symmetrised
+  }
+  __syncwarp();
+  if (lane == 0) {
+    double C[D * D], A[D * D];
+    bool ok = chol_lower<D>(sc.Sn, C);
+    // Sigma ~ IW(nu_n, S_n): scipy's Bartlett construction (bi:258)
+    for (int t = 0; t < D * D; ++t) A[t] = 0.0;
+    int t = 0;
+    for (int i = 1; i < D; ++i)
+      for (int j = 0; j < i; ++j) A[i * D + j] = sc.trn[t++];
+    for (int i = 0; i < D; ++i) A[i * D + i] = sqrt(sc.chi[i]);
+    // CA = C A^-1 (lower triangular)  =>  Sigma = CA CA'
+    for (int r = 0; r < D; ++r)
+      for (int j = D - 1; j >= 0; --j) {
+        double s = C[r * D + j];
+        for (int m = j + 1; m < D; ++m) s -= sc.CA[r * D + m] * A[m * D + j];
+        sc.CA[r * D + j] = s / A[j * D + j];
+      }
+    for (int d = 0; d < D; ++d)
+      for (int e = 0; e < D; ++e) {
+        double s = 0.0;
+        for (int m = 0; m < D; ++m) s += sc.CA[d * D + m] * sc.CA[e * D + m];
+        cp.Sigma[d * D + e] = s;
+        if (!isfinite(s)) ok = false;
+      }
+    derive_params<D>(cp, mc.omega2);
+    cp.status = ok ? 0 : 1;
+    sc.ok = ok ? 1 : 0;
+  }
+  __syncwarp();
+  // beta | Sigma: noise = kron(chol Sigma, chol V) z, ordered d*K+k           bi:261
+  for (int t = lane; t < nb; t += 32) {
+    const int d = t / K, k = t - d * K;
+    double s = 0.0;
+    for (int m = 0; m <= d; ++m) s += sc.CA[d * D + m] * sc.W[m * K + k];
+    sc.Ef[t] = s;
+  }
+  __syncwarp();
+  for (int j = lane; j < nb; j += 32) {
+    const int k = j / D, d = j - k * D;
+    const double bh = sc.Bc[j] + (k == 0 ? mc.center[d] : 0.0);    // B_hat = Bc + e0 c'
+    const double nz = (mc.compat == 0) ? sc.Ef[j] : sc.Ef[d * K + k];  // Q1: reference adds kron-ordered noise to ravel()
+    cp.beta[j] = bh + nz;
+  }
+  __syncwarp();
+}
+
+// level_2 row: beta.T.ravel() then the upper triangle of Sigma (bi:411-412, tri:549-554)
+template <int D>
+__device__ __forceinline__ void write_level2_row(const ModelConst& mc, const ChainParams& cp, double* o, int lane) {
+  const int K = mc.K;
+  for (int t = lane; t < D * K; t += 32) {
+    const int d = t / K, k = t - d * K;
+    o[t] = cp.beta[k * D + d];
+  }
+  if (lane == 0) {
+    int t = D * K;
+    for (int d = 0; d < D; ++d)
+      for (int e = d; e < D; ++e) o[t++] = cp.Sigma[d * D + e];
+  }
+}
+
 template <int D>
 __global__ void __launch_bounds__(32) k_level2(Level2Args a) {
-  __shared__ double st[NSTAT_MAX];
+  __shared__ Level2Scratch sc;
   const ModelConst& mc = *a.mc;
   const int chain = blockIdx.x, lane = threadIdx.x;
   const int K = mc.K;
   const int nstat = K * D + D * (D + 1) / 2;
   for (int t = lane; t < nstat; t += 32) {
     unsigned long long* p = &a.acc[chain * NSTAT_MAX + t];
-    st[t] = (double)(long long)(*p) * mc.fx_inv;
+    sc.st[t] = (double)(long long)(*p) * mc.fx_inv;
     *p = 0ull;
   }
-  // variates: every lane draws its share (fp64 Philox transforms are long dependent chains)
-  __shared__ double s_trn[3], s_chi[3], s_zb[MAXD * MAXK];
-  const PhiloxKey key = chain_key(a.seed, a.chain_offset + (uint32_t)chain);
-  {
-    const int ntril = D * (D - 1) / 2, nb = D * K;
-    for (int t = lane; t < ntril + D + nb; t += 32) {
-      if (t < ntril) {
-        s_trn[t] = a.injected ? a.iw_norm[chain * ntril + t] : level2_normal(key, a.sweep, (uint32_t)t);
-      } else if (t < ntril + D) {
-        int i = t - ntril;
-        s_chi[i] = a.injected ? a.iw_chi2[chain * D + i] : level2_chi2(key, a.sweep, 16u + i, mc.nu_n - D + 1 + i);
-      } else {
-        int j = t - ntril - D;
-        s_zb[j] = a.injected ? a.beta_norm[chain * nb + j] : level2_normal(key, a.sweep, 32u + (uint32_t)j);
-      }
-    }
-  }
   __syncwarp();
-  if (lane != 0) return;
   ChainParams& cp = a.params[chain];
+  const PhiloxKey key = chain_key(a.seed, a.chain_offset + (uint32_t)chain);
+  constexpr int ntril = D * (D - 1) / 2;
+  level2_draw<D>(mc, sc, cp, key, a.sweep, a.injected, a.injected ? a.iw_norm + chain * ntril : nullptr,
+                 a.injected ? a.iw_chi2 + chain * D : nullptr, a.injected ? a.beta_norm + chain * D * K : nullptr, lane);
+  if (lane == 0 && !sc.ok) *a.error_flag = 1;
+  if (a.draw_index >= 0)
+    write_level2_row<D>(mc, cp, a.level2_draws + ((long long)chain * a.n_draws + a.draw_index) * (D * K + D * (D + 1) / 2), lane);
+}
 
-  // R = X'Yc + A0 B0c ; Bc = V R                               bi:250
-  double R[MAXK * MAXD], Bc[MAXK * MAXD];
-  for (int t = 0; t < K * D; ++t) R[t] = st[t] + mc.A0B0c[t];
-  for (int k = 0; k < K; ++k)
-    for (int d = 0; d < D; ++d) {
-      double s = 0.0;
-      for (int m = 0; m < K; ++m) s += mc.V[k * K + m] * R[m * D + d];
-      Bc[k * D + d] = s;
+// ------------------------------------------------------------------------------------------------
+// persistent cooperative kernel: whole sweeps fused, one grid-wide barrier per sweep
+// ------------------------------------------------------------------------------------------------
+struct PersistArgs {
+  SweepArgs sw;                 // data, state, draw chunk (sw.draws, sw.chunk_cap), loglik_acc / loglik_stride
+  ChainParams* params;          // [chains] (read at entry, written back at exit)
+  unsigned long long* acc3;     // [3][chains][NSTAT_MAX] rotating accumulators; acc3[first_sweep % 3 ... ] see below
+  double* level2_draws;
+  long long n_draws;            // draws of the run (stride of level2_draws / loglik_acc)
+  uint32_t first_sweep;         // 1-based number of the first sweep of this launch
+  uint32_t n_sweeps;
+  long long run_step0;          // step index (1-based, within the run) of the first sweep of this launch
+  long long burnin, thin;       // keep iff step > burnin && (step-1-burnin) % thin == 0   (bi:402)
+  long long chunk_base;         // first draw index held by the chunk
+  int store_zt_last;
+  int* error_flag;
+  unsigned int* barrier;        // [2] grid barrier: arrival counter, generation
+};
+
+// Sense-reversing grid barrier on two global words (all blocks are co-resident: cooperative launch).
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned int* gen = bar + 1;
+    const unsigned int my = *gen;
+    __threadfence();
+    if (atomicAdd(bar, 1u) == nblocks - 1u) {
+      *bar = 0u;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*gen == my) { }
     }
-  // S_n = S0 + E'E + C'A0C = Q0 + Yc'Yc - Bc' R                bi:253-255
-  double Sn[D * D];
-  {
-    int t = K * D;
-    for (int d = 0; d < D; ++d)
-      for (int e = d; e < D; ++e) {
-        Sn[d * D + e] = st[t];
-        Sn[e * D + d] = st[t];
-        ++t;
-      }
+    __threadfence();
   }
-  for (int d = 0; d < D; ++d)
-    for (int e = 0; e < D; ++e) {
-      double s = 0.0;
-      for (int k = 0; k < K; ++k) s += Bc[k * D + d] * R[k * D + e];
-      Sn[d * D + e] += mc.Q0[d * D + e] - s;
-    }
-  for (int d = 0; d < D; ++d)
-    for (int e = d + 1; e < D; ++e) {
-      double m = 0.5 * (Sn[d * D + e] + Sn[e * D + d]);
-      Sn[d * D + e] = m;
-      Sn[e * D + d] = m;
-    }
-  double C[D * D];
-  bool ok = chol_lower<D>(Sn, C);
-  // Sigma ~ IW(nu_n, S_n): scipy's Bartlett construction (bi:258)
-  double A[D * D];
-  for (int t = 0; t < D * D; ++t) A[t] = 0.0;
+  __syncthreads();
+}
+
+// Accumulator rotation: sweep s ADDS its statistics to slot s%3, the level-2 draw that follows (bivariate: at the start
+// of sweep s+1; trivariate: at the end of sweep s) READS slot s%3, and slot (s+1)%3 is ZEROED during sweep s, one full
+// barrier after its last reader and one before its next writer.
+template <int D, int MODE>
+__global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(PersistArgs pa) {
+  __shared__ double s_beta[MAXK * MAXD];
+  __shared__ double s_tab[64];
+  __shared__ unsigned long long s_acc[NSTAT_MAX + 1];
+  __shared__ ChainParams s_cp;
+  __shared__ Level2Scratch sc;
+  const SweepArgs& a = pa.sw;
+  const ModelConst& mc = *a.mc;
+  const int chain = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int K = mc.K;
+  const int nstat = K * D + D * (D + 1) / 2;
+  const unsigned int nblocks = gridDim.x * gridDim.y;
+  const long long ntiles = (mc.N + SWEEP_THREADS - 1) / SWEEP_THREADS;
+  const PhiloxKey key = chain_key(a.seed, a.chain_offset + (uint32_t)chain);
+  const long long csz = (long long)gridDim.y * NSTAT_MAX;
+  if (tid < 64) s_tab[tid] = c_exptab[tid];
   {
-    int t = 0;
-    for (int i = 1; i < D; ++i)
-      for (int j = 0; j < i; ++j) {
-        A[i * D + j] = s_trn[t];
-        ++t;
-      }
-    for (int i = 0; i < D; ++i) {
-      A[i * D + i] = sqrt(s_chi[i]);                              // chi2(nu_n - D + 1 + i)
+    const double* src = reinterpret_cast<const double*>(&pa.params[chain]);
+    double* dst = reinterpret_cast<double*>(&s_cp);
+    for (int t = tid; t < (int)(sizeof(ChainParams) / sizeof(double)); t += SWEEP_THREADS) dst[t] = src[t];
+  }
+  __syncthreads();
+
+  auto level2_phase = [&](uint32_t sweep, long long draw_index, unsigned long long* slot_read) {
+    // every block of the chain draws the same (beta, Sigma) from the same totals and the same Philox key
+    if (tid < 32) {
+      for (int t = lane; t < nstat; t += 32)
+        sc.st[t] = (double)(long long)__ldcg(&slot_read[chain * NSTAT_MAX + t]) * mc.fx_inv;
+      __syncwarp();
+      level2_draw<D>(mc, sc, s_cp, key, sweep, 0, nullptr, nullptr, nullptr, lane);
+      if (lane == 0 && !sc.ok) *pa.error_flag = 1;
+      if (blockIdx.x == 0 && draw_index >= 0)
+        write_level2_row<D>(mc, s_cp, pa.level2_draws + ((long long)chain * pa.n_draws + draw_index) * (D * K + D * (D + 1) / 2), lane);
+    }
+    __syncthreads();
+  };
+
+  for (uint32_t it = 0; it < pa.n_sweeps; ++it) {
+    const uint32_t sweep = pa.first_sweep + it;
+    const long long step = pa.run_step0 + it;
+    const bool kept = step > pa.burnin && (step - 1 - pa.burnin) % pa.thin == 0;
+    const long long draw = kept ? (step - 1 - pa.burnin) / pa.thin : -1;
+    unsigned long long* slot_prev = pa.acc3 + (long long)((sweep + 2u) % 3u) * csz;   // (sweep-1) % 3
+    unsigned long long* slot_cur = pa.acc3 + (long long)(sweep % 3u) * csz;
+    unsigned long long* slot_next = pa.acc3 + (long long)((sweep + 1u) % 3u) * csz;
+    if (D == 2) {
+      grid_barrier(pa.barrier, nblocks);         // statistics of sweep-1 (or the initial state) are complete
+      level2_phase(sweep, draw, slot_prev);      // bi:393
+    }
+    if (blockIdx.x == 0)
+      for (int t = tid; t < nstat; t += SWEEP_THREADS) slot_next[chain * NSTAT_MAX + t] = 0ull;
+    for (int t = tid; t < K * D; t += SWEEP_THREADS) s_beta[t] = s_cp.beta[t];
+    for (int t = tid; t < NSTAT_MAX + 1; t += SWEEP_THREADS) s_acc[t] = 0ull;
+    __syncthreads();
+    SweepStep sw;
+    sw.sweep = sweep; sw.keep = kept; sw.store_zt = (pa.store_zt_last && it + 1 == pa.n_sweeps);
+    sw.slot = kept ? draw - pa.chunk_base : 0; sw.chunk_cap = a.chunk_cap; sw.draws = a.draws;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      sweep_tile<D, MODE>(a, mc, s_cp, s_beta, s_tab, s_acc, sw, chain, tile, key);
+    __syncthreads();
+    for (int t = tid; t < nstat; t += SWEEP_THREADS)
+      if (s_acc[t]) atomicAdd(&slot_cur[chain * NSTAT_MAX + t], s_acc[t]);
+    if (kept && tid == 0)
+      atomicAdd(reinterpret_cast<unsigned long long*>(&a.loglik_acc[chain * a.loglik_stride + draw]), s_acc[NSTAT_MAX]);
+    if (D == 3) {
+      grid_barrier(pa.barrier, nblocks);         // tri:529-536: level-2 closes the sweep
+      level2_phase(sweep, draw, slot_cur);
     }
   }
-  // CA = C A^-1 (lower triangular)  =>  Sigma = CA CA'
-  double CA[D * D];
-  for (int r = 0; r < D; ++r)
-    for (int j = D - 1; j >= 0; --j) {
-      double s = C[r * D + j];
-      for (int m = j + 1; m < D; ++m) s -= CA[r * D + m] * A[m * D + j];
-      CA[r * D + j] = s / A[j * D + j];
-    }
-  for (int d = 0; d < D; ++d)
-    for (int e = 0; e < D; ++e) {
-      double s = 0.0;
-      for (int m = 0; m < D; ++m) s += CA[d * D + m] * CA[e * D + m];
-      cp.Sigma[d * D + e] = s;
-      if (!isfinite(s)) ok = false;
-    }
-  // beta | Sigma: noise = kron(chol Sigma, chol V) z, z ordered d*K+k           bi:261
-  double W[MAXD * MAXK];
-  for (int d = 0; d < D; ++d)
-    for (int k = 0; k < K; ++k) {
-      double s = 0.0;
-      for (int m = 0; m <= k; ++m) s += mc.LV[k * K + m] * s_zb[d * K + m];
-      W[d * K + k] = s;
-    }
-  double Ef[MAXD * MAXK];  // noise in kron(Sigma, V) order d*K+k
-  for (int d = 0; d < D; ++d)
-    for (int k = 0; k < K; ++k) {
-      double s = 0.0;
-      for (int m = 0; m <= d; ++m) s += CA[d * D + m] * W[m * K + k];
-      Ef[d * K + k] = s;
-    }
-  for (int k = 0; k < K; ++k)
-    for (int d = 0; d < D; ++d) {
-      double bh = Bc[k * D + d] + (k == 0 ? mc.center[d] : 0.0);   // B_hat = Bc + e0 c'
-      int j = k * D + d;
-      double nz = (mc.compat == 0) ? Ef[j] : Ef[d * K + k];        // Q1: reference adds kron-ordered noise to ravel()
-      cp.beta[j] = bh + nz;
-    }
-  derive_params<D>(cp, mc.omega2);
-  cp.status = ok ? 0 : 1;
-  if (!ok) *a.error_flag = 1;
-  if (a.draw_index >= 0) {
-    const int P = D * K + D * (D + 1) / 2;
-    double* o = a.level2_draws + ((long long)chain * a.n_draws + a.draw_index) * P;
-    for (int d = 0; d < D; ++d)
-      for (int k = 0; k < K; ++k) o[d * K + k] = cp.beta[k * D + d];   // beta.T.ravel()   bi:411
-    int t = D * K;
-    for (int d = 0; d < D; ++d)
-      for (int e = d; e < D; ++e) o[t++] = cp.Sigma[d * D + e];        // bi:412, tri:550-554
+  if (blockIdx.x == 0) {
+    __syncthreads();
+    double* dst = reinterpret_cast<double*>(&pa.params[chain]);
+    const double* src = reinterpret_cast<const double*>(&s_cp);
+    for (int t = tid; t < (int)(sizeof(ChainParams) / sizeof(double)); t += SWEEP_THREADS) dst[t] = src[t];
   }
 }
 
