@@ -245,12 +245,14 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": which, "kernel": "k_sweep<2,FAST>", "kernel_ms": k_ms,
                 "kernel_share_of_step": sweep_ms / (ms if world == 1 else max(sweep_ms + l2_ms, 1e-9)),
-                "algorithmic_bytes_per_customer_update": BYTES_PER_UPDATE,
+                "algorithmic_bytes_per_customer_update": BYTES_PER_UPDATE, "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * n_loc,
                 "note": "the sweep is instruction-issue bound (Philox INT32 + FP64 target + MUFU), not HBM bound; see issue_roofline"}
     prof = os.path.join(ROOT, "profiles", "r01_sweep_metrics.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            # ncu --set full capture of this kernel (profiles/r01_sweep_ncu_summary.md), scaled to this launch's customers
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_customer") * n_loc
+            roofline["traffic_source"] = "profiles/r01_sweep_metrics.json (dram bytes per customer x customers per launch)"
         except Exception:
             pass
     s.close()
