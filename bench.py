@@ -312,6 +312,26 @@ def run_ours(args):
                "min_ess_geyer": me_g, "ess_per_sec": me_g / wall,
                "reference_numpy_1core": {"wall_s": 653.6, "min_ess_geyer": 60, "ess_per_sec": 0.09, "source": "BASELINE.md §2"}}
 
+    # ---- forecast (C5-shaped): x*, P(alive) over customers x posterior draws, draws resident in HBM ----------------
+    forecast = None
+    if world == 1 and not args.no_forecast:
+        nf, nd = args.forecast_customers, args.forecast_draws
+        fc = generate_cbs_arrays(nf, C4_BETA, C4_GAMMA, T_cal=C4_T_CAL, T_star=39.0, seed=C4_SEED + 1, device=local, with_truth=True)
+        with Sampler(fc["x"], fc["t_x"], fc["T_cal"], fc["X"], model_dim=2, chains=1, n_mh_steps=S_MH, seed=7, device=local) as sf:
+            sf.set_state(0, log_lambda=np.log(fc["lambda_true"]), log_mu=np.log(fc["mu_true"]), beta=C4_BETA, Sigma=C4_GAMMA)
+            sf.run_resident(20, nd, 1)
+            sf.forecast_resident(T_star=39.0, seed=42)                         # warm-up
+            best = min(sf.forecast_resident(T_star=39.0, seed=42)["kernel_ms"] for _ in range(3))
+            fr = sf.forecast_resident(T_star=39.0, seed=42)
+        cells = nf * nd
+        gbs = cells * 32 / (best * 1e-3) / 1e9                                  # one 32-byte level-1 row per cell
+        forecast = {"config": f"{nf} synthetic customers x {nd} posterior draws (kept by the sampler, resident in HBM), T_star=39",
+                    "cells_per_sec": cells / (best * 1e-3), "kernel_ms": best, "kernel": "k_forecast_reduce<4>",
+                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                 "algorithmic_bytes_per_cell": 32},
+                    "mean_x_star": float(fr["mean_x_star"].mean()), "mean_p_alive": float(fr["p_alive"].mean()),
+                    "holdout_mean_x_star_generated": float(fc["x_star"].mean())}
+
     line = {"metric": METRIC, "value": value, "unit": "customer-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -322,7 +342,7 @@ def run_ours(args):
                              % (n_loc * 68 / 1e6, ">" if n_loc * 68 > 126e6 else "<"),
                        "customer_mh_steps_per_sec": value * S_MH},
             "gpu_launches": int(launches), "clocks": clk.summary(), "e2e": e2e, "roofline": roofline,
-            "issue_roofline": issue, "cpu_baseline": cpu, "ess": ess}
+            "issue_roofline": issue, "cpu_baseline": cpu, "ess": ess, "forecast": forecast}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -338,6 +358,9 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
+    ap.add_argument("--no-forecast", action="store_true")
+    ap.add_argument("--forecast-customers", type=int, default=1_000_000)
+    ap.add_argument("--forecast-draws", type=int, default=500)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

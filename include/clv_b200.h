@@ -126,6 +126,11 @@ int clv_comm_init(clv_sampler* h, const void* unique_id128, int rank, int world)
  * cb (nullable) is called every `trace` sweeps (bi:384-385).  May be called repeatedly; sweeps continue. */
 int clv_run(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* level1, double* level2,
             double* loglik, clv_progress_cb cb, void* user, int64_t trace);
+/* Same as clv_run, but the level-1 draws stay on the device (they must fit its draw buffer): the input of
+ * clv_forecast_resident and of zero-copy consumers (clv_resident_draws -> [chains][n_draws][n_local][4|5]). */
+int clv_run_resident(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* level2, double* loglik,
+                     clv_progress_cb cb, void* user, int64_t trace);
+int clv_resident_draws(clv_sampler* h, const double** level1_dev, int64_t* n_draws);
 /* Advance n sweeps without storing draws (burn-in, benchmarks).  Asynchronous unless sync != 0. */
 int clv_advance(clv_sampler* h, int64_t n_sweeps, int sync);
 /* Same, synchronous, bracketed by CUDA events on the handle's stream: *elapsed_ms = device time of the n sweeps. */
@@ -185,7 +190,7 @@ int clv_forecast_injected(const clv_forecast_config* cfg, const double* level1, 
 /* Forecast straight from the draws still resident on the device after the last clv_run (no PCIe):
  * x_star host int64 [chains*n_draws][n_local] (nullable), p_alive/mean_x host [n_local] (nullable). */
 int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t* x_star, double* mean_x_star,
-                          double* p_alive);
+                          double* p_alive, double* kernel_ms /* nullable: CUDA-event time of the kernel */);
 
 /* ---- synthetic customers, generate_pareto_abe (bi:95-187) ---------------------------------- */
 /* Device-side generator of the CBS law (x, t_x, x_star | lambda, mu, tau) for n customers with design

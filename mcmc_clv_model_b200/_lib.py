@@ -70,6 +70,9 @@ SIGNATURES = {
     "clv_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "clv_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, c_double_p, c_double_p, c_double_p,
                           PROGRESS_CB, C.c_void_p, C.c_int64]),
+    "clv_run_resident": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, c_double_p, c_double_p,
+                                   PROGRESS_CB, C.c_void_p, C.c_int64]),
+    "clv_resident_draws": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), c_int64_p]),
     "clv_advance": (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),
     "clv_advance_timed": (C.c_int, [C.c_void_p, C.c_int64, c_double_p]),
     "clv_sweeps_done": (C.c_int64, [C.c_void_p]),
@@ -83,7 +86,7 @@ SIGNATURES = {
     "clv_forecast_dev": (C.c_int, [C.POINTER(ForecastConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "clv_forecast_injected": (C.c_int, [C.POINTER(ForecastConfig), c_double_p, c_double_p, c_double_p, c_double_p,
                                         C.c_int64, c_int64_p, c_int64_p, c_double_p]),
-    "clv_forecast_resident": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, c_int64_p, c_double_p, c_double_p]),
+    "clv_forecast_resident": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, c_int64_p, c_double_p, c_double_p, c_double_p]),
     "clv_generate": (C.c_int, [C.POINTER(GenerateConfig), c_double_p, c_double_p, C.c_int, C.c_int, c_int32_p, c_double_p, c_double_p,
                                c_double_p, c_int32_p, c_double_p, c_double_p, c_double_p]),
     "clv_measure_issue_peaks": (C.c_int, [C.c_int, c_double_p]),

@@ -871,8 +871,8 @@ static int ensure_run_buffers(clv_sampler* h, long long n_draws, bool want_level
   return 0;
 }
 
-int clv_run(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* level1, double* level2,
-            double* loglik, clv_progress_cb cb, void* user, int64_t trace) {
+static int run_impl(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* level1, bool resident_only,
+                    double* level2, double* loglik, clv_progress_cb cb, void* user, int64_t trace) {
   if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
   if (!h->inited) return fail(h, CLV_ERR_STATE, "clv_run: call clv_init_state first");
   if (h->cfg.rng_mode == CLV_RNG_INJECTED) return fail(h, CLV_ERR_ARG, "handle is in injected-RNG mode; use clv_sweep_injected");
@@ -882,7 +882,10 @@ int clv_run(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* 
   const long long n_draws = (mcmc - 1) / thin + 1;      // bi:360
   const long long C = h->chains, N = h->N, nc = h->ncol;
   long long cap = 0;
-  if (int r = ensure_run_buffers(h, n_draws, level1 != nullptr, &cap)) return r;
+  const bool store = level1 != nullptr || resident_only;
+  if (int r = ensure_run_buffers(h, n_draws, store, &cap)) return r;
+  if (resident_only && cap < n_draws)
+    return fail(h, CLV_ERR_ARG, "clv_run_resident: %lld draws do not fit the device draw buffer (%lld fit)", n_draws, cap);
   const long long total = burnin + mcmc;
   int buf = 0;
   long long chunk_base = 0;
@@ -903,7 +906,7 @@ int clv_run(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* 
   long long step = 1;
   while (step <= total) {
     long long seg_end = total;
-    if (level1) {
+    if (store) {
       const long long last_draw = std::min(n_draws - 1, chunk_base + cap - 1);
       seg_end = std::min(seg_end, burnin + 1 + last_draw * thin);
       if (last_draw == n_draws - 1) seg_end = total;         // trailing non-kept sweeps ride with the last chunk
@@ -911,8 +914,8 @@ int clv_run(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* 
     if (trace > 0) seg_end = std::min(seg_end, ((step + trace - 1) / trace) * trace);
     seg_end = std::min(seg_end, step + 19999);
     RunCtx rc;
-    rc.burnin = burnin; rc.thin = thin; rc.n_draws = n_draws; rc.chunk_base = chunk_base; rc.cap = level1 ? cap : 1;
-    rc.step0 = step; rc.draws = level1 ? h->d_draws[buf] : nullptr; rc.keep_any = true;
+    rc.burnin = burnin; rc.thin = thin; rc.n_draws = n_draws; rc.chunk_base = chunk_base; rc.cap = store ? cap : 1;
+    rc.step0 = step; rc.draws = store ? h->d_draws[buf] : nullptr; rc.keep_any = true;
     if (int r = run_segment(h, rc, seg_end - step + 1, seg_end == total)) return r;
     step = seg_end + 1;
     if (level1) {
@@ -941,7 +944,24 @@ int clv_run(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* 
   CK(h, cudaStreamSynchronize(h->copy_stream));
   if (loglik)
     for (size_t t = 0; t < ll.size(); ++t) loglik[t] = (double)ll[t] * h->h_mc.ll_inv;
-  h->resident_draws = (level1 && cap >= n_draws) ? n_draws : 0;
+  h->resident_draws = (store && cap >= n_draws) ? n_draws : 0;
+  return CLV_OK;
+}
+
+int clv_run(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* level1, double* level2,
+            double* loglik, clv_progress_cb cb, void* user, int64_t trace) {
+  return run_impl(h, burnin, mcmc, thin, level1, false, level2, loglik, cb, user, trace);
+}
+
+int clv_run_resident(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* level2, double* loglik,
+                     clv_progress_cb cb, void* user, int64_t trace) {
+  return run_impl(h, burnin, mcmc, thin, nullptr, true, level2, loglik, cb, user, trace);
+}
+
+int clv_resident_draws(clv_sampler* h, const double** level1_dev, int64_t* n_draws) {
+  if (!h || !level1_dev || !n_draws) return fail(h, CLV_ERR_ARG, "null argument");
+  *level1_dev = h->resident_draws > 0 ? h->d_draws[0] : nullptr;
+  *n_draws = h->resident_draws;
   return CLV_OK;
 }
 
@@ -1194,7 +1214,8 @@ int clv_forecast_injected(const clv_forecast_config* cfg, const double* level1, 
   return forecast_host(cfg, level1, T_cal, u, eps, n_eps, eps_offset, x_star, spend, true);
 }
 
-int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t* x_star, double* mean_x_star, double* p_alive) {
+int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t* x_star, double* mean_x_star, double* p_alive,
+                          double* kernel_ms) {
   if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
   if (h->resident_draws <= 0) return fail(h, CLV_ERR_STATE, "no resident draws: run clv_run with a level1 buffer that fits in one device chunk");
   CK(h, cudaSetDevice(h->cfg.device));
@@ -1210,10 +1231,17 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
   a.level1 = h->d_draws[0]; a.T_cal = h->d_T; a.n_draws = C * nd; a.N = N; a.T_star = T_star; a.sigma_s = 0.5;
   a.seed = seed; a.gid_offset = h->cfg.gid_offset; a.draw_offset = 0; a.x_out = d_x; a.spend_out = nullptr;
   int gx = (int)std::min<long long>((N + 255) / 256, 65535);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, h->stream);
   if (h->ncol == 4) k_forecast_reduce<4><<<gx, 256, 0, h->stream>>>(a, d_mx, d_pa);
   else k_forecast_reduce<5><<<gx, 256, 0, h->stream>>>(a, d_mx, d_pa);
+  cudaEventRecord(e1, h->stream);
   h->launches++;
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+  if (e == cudaSuccess && kernel_ms) { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); *kernel_ms = ms; }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (e == cudaSuccess && mean_x_star) e = cudaMemcpyAsync(mean_x_star, d_mx, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess && p_alive) e = cudaMemcpyAsync(p_alive, d_pa, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess && x_star) e = cudaMemcpyAsync(x_star, d_x, (size_t)(C * nd * N) * 8, cudaMemcpyDeviceToHost, h->stream);

@@ -146,6 +146,17 @@ class Sampler:
                                  L.dptr(lvl2), L.dptr(ll), cb, None, int(trace)), self.h)
         return dict(level_1=lvl1, level_2=lvl2, loglik_sum=ll)
 
+    def run_resident(self, burnin, mcmc, thin, trace=0, progress=None):
+        """Like run(), but the level-1 draws stay in HBM (for forecast_resident / zero-copy consumers)."""
+        n_draws = (int(mcmc) - 1) // int(thin) + 1
+        lvl2 = np.empty((self.chains, n_draws, self.P))
+        ll = np.empty((self.chains, n_draws))
+        cb = L.PROGRESS_CB(lambda user, step, total: progress(int(step), int(total))) if progress else C.cast(None, L.PROGRESS_CB)
+        L.check(self.lib.clv_run_resident(self.h, int(burnin), int(mcmc), int(thin), L.dptr(lvl2), L.dptr(ll), cb, None,
+                                          int(trace)), self.h)
+        self._resident = n_draws
+        return dict(level_1=None, level_2=lvl2, loglik_sum=ll)
+
     def advance(self, n_sweeps, sync=True):
         L.check(self.lib.clv_advance(self.h, int(n_sweeps), 1 if sync else 0), self.h)
 
@@ -209,10 +220,14 @@ class Sampler:
         return dict(level_1=lvl1, level_2=lvl2, loglik_sum=ll)
 
     # ---- resident forecast ---------------------------------------------------------------------
-    def forecast_resident(self, T_star=39.0, seed=0, want_x_star=False, n_draws=None):
-        mx, pa = np.empty(self.N), np.empty(self.N)
-        xs = np.empty((self.chains * n_draws, self.N), dtype=np.int64) if want_x_star else None
+    def forecast_resident(self, T_star=39.0, seed=0, want_x_star=False):
+        """x* / P(alive) from the draws still in HBM after run()/run_resident(): per-customer mean x* and mean z,
+        optionally the full (chains*n_draws, N) x* matrix."""
+        ptr, nd = C.c_void_p(), C.c_int64()
+        L.check(self.lib.clv_resident_draws(self.h, C.byref(ptr), C.byref(nd)), self.h)
+        mx, pa, ms = np.empty(self.N), np.empty(self.N), C.c_double()
+        xs = np.empty((self.chains * nd.value, self.N), dtype=np.int64) if want_x_star else None
         L.check(self.lib.clv_forecast_resident(self.h, float(T_star), int(seed) & 0xFFFFFFFFFFFFFFFF,
                                                xs.ctypes.data_as(L.c_int64_p) if xs is not None else None,
-                                               L.dptr(mx), L.dptr(pa)), self.h)
-        return dict(mean_x_star=mx, p_alive=pa, x_star=xs)
+                                               L.dptr(mx), L.dptr(pa), C.byref(ms)), self.h)
+        return dict(mean_x_star=mx, p_alive=pa, x_star=xs, kernel_ms=ms.value, n_draws_total=self.chains * nd.value)

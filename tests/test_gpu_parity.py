@@ -197,3 +197,77 @@ def test_persistent_kernel_equals_stream_mode(cdnow_abe, D):
                 np.testing.assert_array_equal(a[k], outs["stream"][0][k], err_msg=f"chunked {mode} {k}")
     finally:
         del os.environ["CLV_DRAW_BUFFER_BYTES"]
+
+
+def test_resident_forecast_equals_host_path(cdnow_abe):
+    """Forecast straight from the draws left in HBM == forecast of the same draws through the host API
+    (same Philox counters: global customer id, chain-major draw index), and its fused reductions are exact."""
+    from mcmc_clv_model_b200.api import _forecast
+    d = cdnow_abe
+    n = 1500
+    with Sampler(d["x"][:n], d["t_x"][:n], d["T_cal"][:n], np.ones((n, 1)), chains=2, seed=3) as s:
+        out = s.run(20, 6, 2)
+        fr = s.forecast_resident(T_star=39.0, seed=11, want_x_star=True)
+        s.run_resident(0, 6, 2)
+        fr2 = s.forecast_resident(T_star=39.0, seed=11, want_x_star=True)
+    x, _ = _forecast(d["T_cal"][:n], list(out["level_1"]), 39.0, 11, False, 0.5)
+    np.testing.assert_array_equal(fr["x_star"], x)
+    np.testing.assert_allclose(fr["mean_x_star"], x.mean(axis=0), rtol=1e-13)
+    np.testing.assert_allclose(fr["p_alive"], np.concatenate(list(out["level_1"]))[:, :, 3].mean(axis=0), rtol=1e-13)
+    assert fr2["x_star"].shape == x.shape and fr2["n_draws_total"] == 6
+
+
+def test_generator_law_matches_numpy_restatement():
+    """Device generator (K5) vs the same law drawn with NumPy: moments of x, t_x, x_star, alive."""
+    from mcmc_clv_model_b200.synthetic import C4_BETA, C4_GAMMA, generate_cbs_arrays
+    n = 400_000
+    g = generate_cbs_arrays(n, C4_BETA, C4_GAMMA, T_cal=(27.0, 38.857), T_star=39.0, seed=123)
+    r = np.random.default_rng(1)
+    X = np.column_stack([np.ones(n), r.uniform(-1, 1, (n, 4))])
+    th = np.exp(X @ C4_BETA + r.multivariate_normal(np.zeros(2), C4_GAMMA, n))
+    tau = r.exponential(1 / th[:, 1])
+    T = r.uniform(27.0, 38.857, n)
+    Te = np.minimum(tau, T)
+    x = r.poisson(th[:, 0] * Te)
+    tx = np.where(x > 0, Te * r.random(n) ** (1 / np.maximum(x, 1)), 0.0)
+    xs = r.poisson(th[:, 0] * np.maximum(0, np.minimum(tau, T + 39.0) - T))
+    assert np.all(g["X"][:, 0] == 1) and np.all(np.abs(g["X"][:, 1:]) <= 1)
+    assert np.all((g["t_x"] >= 0) & (g["t_x"] <= g["T_cal"])) and np.all((g["x"] == 0) == (g["t_x"] == 0))
+    for ours, ref, tol in [(g["x"].mean(), x.mean(), 0.03), ((g["x"] == 0).mean(), (x == 0).mean(), 0.005),
+                           (g["t_x"].mean(), tx.mean(), 0.08), (g["x_star"].mean(), xs.mean(), 0.05),
+                           ((g["tau_true"] > g["T_cal"]).mean(), (tau > T).mean(), 0.005),
+                           (np.log(g["lambda_true"]).mean(), np.log(th[:, 0]).mean(), 0.01),
+                           (np.log(g["mu_true"]).std(), np.log(th[:, 1]).std(), 0.01)]:
+        assert abs(ours - ref) < tol, (ours, ref)
+    # the x | lambda, tau, T law exactly: E[x] = lambda * min(tau, T)
+    m = g["lambda_true"] * np.minimum(g["tau_true"], g["T_cal"])
+    sel = m < 50
+    assert abs((g["x"][sel] - m[sel]).mean()) < 4 * np.sqrt(m[sel].mean() / sel.sum())
+
+
+def test_api_layout_and_shims(cdnow_abe):
+    """The drop-in modules return the reference's dict layout (bi:503-504, tri:653-657) and forecast shapes."""
+    import pandas as pd
+    import pickle
+    from src.models.bivariate.mcmc import draw_future_transactions, mcmc_draw_parameters
+    from src.models.trivariate.mcmc import draw_future_transactions as dft3, mcmc_draw_parameters_rfm_m
+    d = cdnow_abe
+    n = 300
+    cbs = pd.DataFrame({k: d[k][:n] for k in ("x", "t_x", "T_cal", "first_sales_scaled", "log_s", "gender_F", "age_scaled")})
+    before = cbs.copy()
+    draws = mcmc_draw_parameters(cbs, covariates=["first_sales_scaled"], mcmc=21, burnin=10, thin=5, chains=3, seed=1, trace=0)
+    pd.testing.assert_frame_equal(cbs, before)                       # caller's frame is never mutated (bi:467)
+    assert set(draws) == {"level_1", "level_2", "log_likelihood"} and len(draws["level_1"]) == 3
+    assert draws["level_1"][0].shape == (5, n, 4) and draws["level_2"][0].shape == (5, 2 * 2 + 3)
+    assert draws["level_1"][0].flags.c_contiguous and draws["level_1"][0].dtype == np.float64
+    assert isinstance(draws["log_likelihood"], np.floating) and np.array(draws["level_2"]).shape == (3, 5, 7)
+    assert set(np.unique(draws["level_1"][1][:, :, 3])) <= {0.0, 1.0}
+    draws2 = pickle.loads(pickle.dumps(draws))
+    xs = draw_future_transactions(cbs, draws2, T_star=39.0, seed=4)
+    assert xs.shape == (15, n) and xs.dtype == np.int64 and xs.min() >= 0
+    t3 = mcmc_draw_parameters_rfm_m(cbs, covariates=["gender_F", "age_scaled"], mcmc=4, burnin=6, thin=1, chains=2, seed=2, trace=0)
+    assert t3["level_1"][0].shape == (4, n, 5) and t3["level_2"][0].shape == (4, 3 * 3 + 6) and isinstance(t3["log_likelihood"], float)
+    t3["level_1"] = [np.concatenate([a[..., :4], np.log(a[..., 4:])], axis=-1) for a in t3["level_1"]]   # keep exp(eta) finite
+    x3, sp = dft3(cbs, t3, T_star=39.0, simulate_spend=True, sigma_s=0.5, seed=9)
+    assert x3.shape == sp.shape == (8, n) and np.all((sp > 0) == (x3 > 0))
+    assert dft3(cbs, t3, simulate_spend=False, seed=9).shape == (8, n)
