@@ -1077,8 +1077,9 @@ int clv_sweep_injected(clv_sampler* h, const clv_injected* v, int keep, double* 
 // ---- forecast ---------------------------------------------------------------------------------
 static int launch_forecast(const clv_forecast_config* cfg, ForecastArgs a, bool inject, cudaStream_t st) {
   const long long N = cfg->n_customers;
+  const long long npairs = ((a.draw_offset + a.n_draws - 1) >> 1) - (a.draw_offset >> 1) + 1;
   int gx = (int)std::min<long long>((N + 255) / 256, 65535);
-  int gy = (int)std::max<long long>(1, std::min<long long>(cfg->n_draws_total, 148ll * 8 * 4 / std::max(1, gx) + 1));
+  int gy = (int)std::max<long long>(1, std::min<long long>(npairs, 148ll * 8 * 4 / std::max(1, gx) + 1));
   gy = std::min(gy, 65535);
   dim3 grid(gx, gy);
   if (cfg->ncol == 4) {
@@ -1231,11 +1232,17 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
   a.level1 = h->d_draws[0]; a.T_cal = h->d_T; a.n_draws = C * nd; a.N = N; a.T_star = T_star; a.sigma_s = 0.5;
   a.seed = seed; a.gid_offset = h->cfg.gid_offset; a.draw_offset = 0; a.x_out = d_x; a.spend_out = nullptr;
   int gx = (int)std::min<long long>((N + 255) / 256, 65535);
+  // enough (customer, draw-range) threads to fill the GPU ~8 times over
+  const long long npairs = (C * nd + 1) / 2;
+  int gy = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(npairs, 64), (long long)h->sm_count * 8 * 8 / std::max(1, gx)));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, h->stream);
-  if (h->ncol == 4) k_forecast_reduce<4><<<gx, 256, 0, h->stream>>>(a, d_mx, d_pa);
-  else k_forecast_reduce<5><<<gx, 256, 0, h->stream>>>(a, d_mx, d_pa);
+  if (gy > 1) { cudaMemsetAsync(d_mx, 0, sizeof(double) * N, h->stream); cudaMemsetAsync(d_pa, 0, sizeof(double) * N, h->stream); }
+  if (h->ncol == 4) k_forecast_reduce<4><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa);
+  else k_forecast_reduce<5><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa);
+  k_scale<<<h->sm_count * 4, 256, 0, h->stream>>>(d_mx, d_pa, N, 1.0 / (double)(C * nd));
+  h->launches++;
   cudaEventRecord(e1, h->stream);
   h->launches++;
   cudaError_t e = cudaGetLastError();

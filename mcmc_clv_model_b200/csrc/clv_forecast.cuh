@@ -14,7 +14,7 @@ __constant__ double c_rk[RK_TABLE + 1];   // c_rk[k] = 1.0 / k
 
 // Poisson draw by sequential CDF inversion from zero; arithmetic fixed to match
 // oracle/abe_oracle.py:poisson_inversion bit for bit.
-__device__ __forceinline__ long long poisson_inversion(double m, double u) {
+__device__ __noinline__ long long poisson_inversion(double m, double u) {
   double p = exp(-m), cdf = p;
   long long k = 0;
   const double cap = floor(4096.0 + 16.0 * m);
@@ -25,6 +25,25 @@ __device__ __forceinline__ long long poisson_inversion(double m, double u) {
     cdf += p;
   }
   return k;
+}
+
+// The same map u -> k, screened in fp32: the chop-down runs on the FP32/SFU pipes; the result is accepted only when u
+// is further than a guard band (>> the fp32 error of the running CDF) from both neighbouring CDF values, otherwise the
+// fp64 reference loop decides.  Hence the returned k ALWAYS equals poisson_inversion(m, u).
+__device__ __forceinline__ long long poisson_inversion_screened(double m, double u) {
+  if (m >= 0.0 && m < 60.0) {
+    const float mf = (float)m, uf = (float)u;
+    float p = __expf(-mf), cdf = p, prev = -1.0f, kf = 0.0f;
+    while (uf > cdf && kf < 1024.0f) {
+      kf += 1.0f;
+      prev = cdf;
+      p = __fdividef(p * mf, kf);
+      cdf += p;
+    }
+    const float tol = 2e-6f * (8.0f + mf);
+    if (uf < cdf - tol && uf > prev + tol && kf < 1024.0f) return (long long)kf;
+  }
+  return poisson_inversion(m, u);
 }
 
 __device__ __forceinline__ double future_horizon(double T_cal, double tau, double zf, double T_star) {
@@ -46,74 +65,115 @@ struct ForecastArgs {
   double* spend_out;             // [n_draws][N] (nullable)
 };
 
+// Forecast uniforms: one Philox block serves the two draws 2g, 2g+1 of a customer (global draw index, chain-major):
+// counter (gid, g, 0, DOM_FORECAST), words (x,y) for the even draw and (z,w) for the odd one.
+__device__ __forceinline__ double forecast_u(uint4 r, long long gdraw) {
+  return (gdraw & 1) ? u53(r.z, r.w) : u53(r.x, r.y);
+}
+
+template <int NCOL>
+__device__ __forceinline__ void load_row(const double* row, double& lam, double& tau, double& zf, double& eta) {
+  if (NCOL == 4) {
+    const double2 r0 = __ldcs(reinterpret_cast<const double2*>(row));       // streamed once: evict-first
+    const double2 r1 = __ldcs(reinterpret_cast<const double2*>(row) + 1);
+    lam = r0.x; tau = r1.x; zf = r1.y; eta = 0.0;
+  } else {
+    lam = __ldcs(row); tau = __ldcs(row + 2); zf = __ldcs(row + 3); eta = __ldcs(row + 4);
+  }
+}
+
+// One thread per (customer, pair of draws): x* (and spend) for every cell.
 template <int NCOL, bool INJECT>
 __global__ void __launch_bounds__(256) k_forecast(ForecastArgs a) {
   const PhiloxKey key = chain_key(a.seed, 0u);
   const bool spend = (NCOL == 5) && a.spend_out != nullptr;
-  for (long long d = blockIdx.y; d < a.n_draws; d += gridDim.y) {
-    const uint32_t gdraw = (uint32_t)(a.draw_offset + d);
+  const long long gp0 = a.draw_offset >> 1, gp1 = (a.draw_offset + a.n_draws - 1) >> 1;   // global pair range
+  for (long long gp = gp0 + blockIdx.y; gp <= gp1; gp += gridDim.y) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.N;
          i += (long long)gridDim.x * blockDim.x) {
-      const long long cell = d * a.N + i;
-      const double* row = a.level1 + cell * NCOL;
-      double lam, tau, zf, eta = 0.0;
-      if (NCOL == 4) {
-        double2 r0 = reinterpret_cast<const double2*>(row)[0];
-        double2 r1 = reinterpret_cast<const double2*>(row)[1];
-        lam = r0.x; tau = r1.x; zf = r1.y;
-      } else {
-        lam = row[0]; tau = row[2]; zf = row[3]; eta = row[4];
-      }
-      const double h = future_horizon(a.T_cal[i], tau, zf, a.T_star);
       const uint32_t gid = (uint32_t)(a.gid_offset + i);
-      double u;
-      if (INJECT) u = a.u[cell];
-      else {
-        uint4 r = philox4x32_10(gid, gdraw, 0u, DOM_FORECAST, key);
-        u = u53(r.x, r.y);
-      }
-      const long long xs = poisson_inversion(lam * h, u);                 // bi:543
-      if (a.x_out) a.x_out[cell] = xs;
-      if (spend) {
-        // tri:730-737: sum of x* log-normal transactions, log-mean = eta column as stored (Q7)
-        double tot = 0.0;
-        for (long long j = 0; j < xs; ++j) {
-          double n;
-          if (INJECT) n = a.eps[a.eps_offset[cell] + j];
-          else {
-            double nc, ns;
-            normal_pair_u53(philox4x32_10(gid, gdraw, 1u + (uint32_t)(j >> 1), DOM_FORECAST, key), &nc, &ns);
-            n = (j & 1) ? ns : nc;
+      const double T = a.T_cal[i];
+      uint4 r = make_uint4(0, 0, 0, 0);
+      if (!INJECT) r = philox4x32_10(gid, (uint32_t)gp, 0u, DOM_FORECAST, key);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long gdraw = 2 * gp + h, d = gdraw - a.draw_offset;
+        if (d < 0 || d >= a.n_draws) continue;
+        const long long cell = d * a.N + i;
+        double lam, tau, zf, eta;
+        load_row<NCOL>(a.level1 + cell * NCOL, lam, tau, zf, eta);
+        const double hz = future_horizon(T, tau, zf, a.T_star);
+        const long long xs = poisson_inversion_screened(lam * hz, INJECT ? a.u[cell] : forecast_u(r, gdraw));   // bi:543
+        if (a.x_out) __stcs(&a.x_out[cell], xs);
+        if (spend) {
+          // tri:730-737: sum of x* log-normal transactions, log-mean = eta column as stored (Q7)
+          double tot = 0.0;
+          for (long long j = 0; j < xs; ++j) {
+            double n;
+            if (INJECT) n = a.eps[a.eps_offset[cell] + j];
+            else {
+              double nc, ns;
+              normal_pair_u53(philox4x32_10(gid, (uint32_t)gdraw, 1u + (uint32_t)(j >> 1), DOM_FORECAST, key), &nc, &ns);
+              n = (j & 1) ? ns : nc;
+            }
+            tot += exp(eta + a.sigma_s * n);
           }
-          tot += exp(eta + a.sigma_s * n);
+          a.spend_out[cell] = tot;
         }
-        a.spend_out[cell] = tot;
       }
     }
   }
 }
 
-// One thread per customer walks all resident draws: mean x*, P(alive) = mean z without materialising x*.
+// Fused reductions over the draws still resident in HBM: per customer sum of x* and of z (P(alive) = mean z,
+// analysis_bi_helpers.py:98), x* optionally materialised.  blockIdx.y splits the draw pairs; partial sums are exact
+// (integers in fp64) so the atomicAdd order does not matter.
 template <int NCOL>
-__global__ void __launch_bounds__(256) k_forecast_reduce(ForecastArgs a, double* mean_x, double* p_alive) {
+__global__ void __launch_bounds__(256) k_forecast_reduce(ForecastArgs a, double* sum_x, double* sum_z) {
   const PhiloxKey key = chain_key(a.seed, 0u);
+  const long long gp0 = a.draw_offset >> 1, gp1 = (a.draw_offset + a.n_draws - 1) >> 1;
+  const long long npairs = gp1 - gp0 + 1;
+  const long long per = (npairs + gridDim.y - 1) / gridDim.y;
+  const long long pa = gp0 + (long long)blockIdx.y * per, pb = min(gp1 + 1, pa + per);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.N;
        i += (long long)gridDim.x * blockDim.x) {
     const double T = a.T_cal[i];
     const uint32_t gid = (uint32_t)(a.gid_offset + i);
     double sx = 0.0, sz = 0.0;
-    for (long long d = 0; d < a.n_draws; ++d) {
-      const double* row = a.level1 + (d * a.N + i) * NCOL;
-      const double lam = row[0], tau = row[2], zf = row[3];
-      const double h = future_horizon(T, tau, zf, a.T_star);
-      uint4 r = philox4x32_10(gid, (uint32_t)(a.draw_offset + d), 0u, DOM_FORECAST, key);
-      const long long xs = poisson_inversion(lam * h, u53(r.x, r.y));
-      if (a.x_out) a.x_out[d * a.N + i] = xs;
-      sx += (double)xs;
-      sz += (zf > 0.5) ? 1.0 : 0.0;
+    for (long long gp = pa; gp < pb; ++gp) {
+      const long long d0 = 2 * gp - a.draw_offset, d1 = d0 + 1;
+      const bool v0 = d0 >= 0 && d0 < a.n_draws, v1 = d1 >= 0 && d1 < a.n_draws;
+      double lam0 = 0, tau0 = 0, z0 = 0, e0, lam1 = 0, tau1 = 0, z1 = 0, e1;
+      if (v0) load_row<NCOL>(a.level1 + (d0 * a.N + i) * NCOL, lam0, tau0, z0, e0);   // both rows in flight
+      if (v1) load_row<NCOL>(a.level1 + (d1 * a.N + i) * NCOL, lam1, tau1, z1, e1);
+      const uint4 r = philox4x32_10(gid, (uint32_t)gp, 0u, DOM_FORECAST, key);
+      if (v0) {
+        const long long xs = poisson_inversion_screened(lam0 * future_horizon(T, tau0, z0, a.T_star), u53(r.x, r.y));
+        if (a.x_out) __stcs(&a.x_out[d0 * a.N + i], xs);
+        sx += (double)xs;
+        sz += (z0 > 0.5) ? 1.0 : 0.0;
+      }
+      if (v1) {
+        const long long xs = poisson_inversion_screened(lam1 * future_horizon(T, tau1, z1, a.T_star), u53(r.z, r.w));
+        if (a.x_out) __stcs(&a.x_out[d1 * a.N + i], xs);
+        sx += (double)xs;
+        sz += (z1 > 0.5) ? 1.0 : 0.0;
+      }
     }
-    if (mean_x) mean_x[i] = sx / (double)a.n_draws;
-    if (p_alive) p_alive[i] = sz / (double)a.n_draws;
+    if (gridDim.y == 1) {
+      sum_x[i] = sx;
+      sum_z[i] = sz;
+    } else {
+      atomicAdd(&sum_x[i], sx);
+      atomicAdd(&sum_z[i], sz);
+    }
+  }
+}
+
+__global__ void k_scale(double* a, double* b, long long n, double f) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    a[i] *= f;
+    b[i] *= f;
   }
 }
 

@@ -163,9 +163,10 @@ def level2_variates(seed, chain, sweep, D, K, nu_n):
 # forecast domain
 # ---------------------------------------------------------------------------
 def forecast_uniform(seed, gids, draw):
+    """One block serves the two draws 2g, 2g+1 (global, chain-major draw index): words (0,1) / (2,3)."""
     k0, k1 = chain_key(seed, 0)
-    r = philox4x32_10(np.asarray(gids, dtype=np.uint64), draw, 0, DOM_FORECAST, k0, k1)
-    return u53(r[0], r[1])
+    r = philox4x32_10(np.asarray(gids, dtype=np.uint64), draw >> 1, 0, DOM_FORECAST, k0, k1)
+    return u53(r[2], r[3]) if draw & 1 else u53(r[0], r[1])
 
 
 def forecast_spend_normal(seed, gid, draw, j):

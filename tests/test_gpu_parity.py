@@ -271,3 +271,35 @@ def test_api_layout_and_shims(cdnow_abe):
     x3, sp = dft3(cbs, t3, T_star=39.0, simulate_spend=True, sigma_s=0.5, seed=9)
     assert x3.shape == sp.shape == (8, n) and np.all((sp > 0) == (x3 > 0))
     assert dft3(cbs, t3, simulate_spend=False, seed=9).shape == (8, n)
+
+
+def test_screened_poisson_inversion_is_exact_on_adversarial_uniforms():
+    """The fp32-screened inversion must return exactly the fp64 CDF-inversion result, also when u sits on / next to a
+    CDF boundary (where the screen has to hand over to the fp64 loop) and for means beyond the fp32 range."""
+    import ctypes as C
+    from mcmc_clv_model_b200 import _lib as L
+    rng = np.random.default_rng(11)
+    means = np.concatenate([[0.0, 1e-12, 1e-3, 0.5, 1.0, 9.99, 10.0, 59.999, 60.0, 61.0, 150.0, 700.0, 900.0],
+                            rng.uniform(0, 70, 400), rng.lognormal(0.0, 1.5, 400)])
+    us, ms = [], []
+    for m in means:
+        k = np.arange(0, int(m + 12 * np.sqrt(m + 1) + 12))
+        from scipy.stats import poisson
+        cdf = poisson.cdf(k, m)
+        picks = cdf[rng.integers(0, len(cdf), 24)]
+        cand = np.concatenate([picks, np.nextafter(picks, 0), np.nextafter(picks, 1), picks * (1 - 1e-7), picks * (1 + 1e-7),
+                               picks - 3e-6, picks + 3e-6, rng.random(24)])
+        cand = np.clip(cand, 1e-300, 1 - 1e-16)
+        us.append(cand)
+        ms.append(np.full(cand.size, m))
+    u = np.concatenate(us)
+    m = np.concatenate(ms)
+    N = u.size
+    l1 = np.zeros((1, N, 4))
+    l1[0, :, 0] = m / 39.0
+    l1[0, :, 3] = 1.0                                   # alive: horizon = T_star = 39
+    xs = np.empty((1, N), dtype=np.int64)
+    cfg = L.ForecastConfig(device=0, ncol=4, n_draws_total=1, n_customers=N, T_star=39.0, seed=1)
+    L.check(L.load().clv_forecast_injected(C.byref(cfg), L.dptr(l1), L.dptr(np.full(N, 30.0)), L.dptr(np.ascontiguousarray(u[None])),
+                                           None, 0, None, xs.ctypes.data_as(L.c_int64_p), None))
+    np.testing.assert_array_equal(xs[0], ao.poisson_inversion(l1[0, :, 0] * 39.0, u))
