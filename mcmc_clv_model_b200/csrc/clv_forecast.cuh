@@ -21,30 +21,60 @@ __device__ __noinline__ long long poisson_inversion(double m, double u) {
   while (u > cdf && (double)k < cap) {
     ++k;
     double rk = (k <= RK_TABLE) ? c_rk[k] : 1.0 / (double)k;
-    p = (p * m) * rk;
-    cdf += p;
+    p = __dmul_rn(__dmul_rn(p, m), rk);   // no FMA contraction: the oracle rounds after every operation
+    cdf = __dadd_rn(cdf, p);
   }
   return k;
 }
 
-// The same map u -> k, screened in fp32: the chop-down runs on the FP32/SFU pipes; the result is accepted only when u
-// is further than a guard band (>> the fp32 error of the running CDF) from both neighbouring CDF values, otherwise the
-// fp64 reference loop decides.  Hence the returned k ALWAYS equals poisson_inversion(m, u).
-__device__ __forceinline__ long long poisson_inversion_screened(double m, double u) {
-  if (m >= 0.0 && m < 60.0) {
-    const float mf = (float)m, uf = (float)u;
-    float p = __expf(-mf), cdf = p, prev = -1.0f, kf = 0.0f;
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// The same map u -> k, screened in fp32: the chop-down runs on the FP32/SFU pipes from fp32 images (mf, uf) of the mean
+// and the uniform; the result is accepted only when uf is further than a guard band (>> the fp32 error of the running
+// CDF, of mf and of uf) from both neighbouring CDF values, otherwise the fp64 reference loop decides on the exact
+// (m, u) -- which are only computed then.  Hence the returned k ALWAYS equals poisson_inversion(m, u).
+template <typename ExactMU>
+__device__ __forceinline__ long long poisson_inversion_screened(float mf, float uf, ExactMU exact) {
+  if (mf >= 0.0f && mf < 60.0f) {
+    float p = ex2_ftz(-1.4426950408889634f * mf), cdf = p, prev = -1.0f, kf = 0.0f;
     while (uf > cdf && kf < 1024.0f) {
       kf += 1.0f;
       prev = cdf;
-      p = __fdividef(p * mf, kf);
+      p = (p * mf) * rcp_ftz(kf);
       cdf += p;
     }
     const float tol = 2e-6f * (8.0f + mf);
     if (uf < cdf - tol && uf > prev + tol && kf < 1024.0f) return (long long)kf;
   }
+  double m, u;
+  exact(m, u);
   return poisson_inversion(m, u);
 }
+
+// Large means (production path only): Hoermann's transformed rejection "PTRS" (the algorithm NumPy uses for lam >= 10),
+// exact, ~1.2 attempts whatever the mean -- a customer with lambda * T_star in the hundreds must not cost hundreds of
+// dependent fp64 iterations per draw.  Attempt t takes its two uniforms from Philox block (gid, draw, 64 + t).
+__device__ __noinline__ long long poisson_ptrs(double lam, uint32_t gid, uint32_t gdraw, PhiloxKey key) {
+  const double slam = sqrt(lam), loglam = log(lam);
+  const double b = 0.931 + 2.53 * slam;
+  const double a = -0.059 + 0.02483 * b;
+  const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
+  const double vr = 0.9277 - 3.6224 / (b - 2.0);
+  for (uint32_t t = 0; t < 4096u; ++t) {
+    const uint4 r = philox4x32_10(gid, gdraw, 64u + t, DOM_FORECAST, key);
+    const double U = u53(r.x, r.y) - 0.5, V = u53(r.z, r.w);
+    const double us = 0.5 - fabs(U);
+    const double kd = floor((2.0 * a / us + b) * U + lam + 0.43);
+    if (us >= 0.07 && V <= vr) return kd < 9.2e18 ? (long long)kd : 0x7fffffffffffffffll;
+    if (kd < 0.0 || (us < 0.013 && V > us)) continue;
+    if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lam + kd * loglam - lgamma(kd + 1.0))
+      return kd < 9.2e18 ? (long long)kd : 0x7fffffffffffffffll;
+  }
+  return (long long)lam;
+}
+
+constexpr double PTRS_MIN_MEAN = 60.0;   // == the fp32 range limit of the screened inversion
 
 __device__ __forceinline__ double future_horizon(double T_cal, double tau, double zf, double T_star) {
   // bi:535-540: alive -> T_star ; churned -> clip(tau - T_cal, 0, T_star)
@@ -82,11 +112,30 @@ __device__ __forceinline__ void load_row(const double* row, double& lam, double&
   }
 }
 
+// x* of one (draw, customer) cell (bi:535-543).  The fp32 images feed the screen; the exact fp64 mean
+// lambda * clip(tau - T_cal, 0, T_star) and the 53-bit uniform are built only if the screen hands over.
+__device__ __forceinline__ long long forecast_cell(double lam, double tau, double zf, double T, double T_star, float T_star_f,
+                                                   uint32_t ua, uint32_t ub, uint32_t gid, uint32_t gdraw, PhiloxKey key) {
+  const bool alive = zf > 0.5;
+  const float hf = alive ? T_star_f : fminf(fmaxf((float)(tau - T), 0.0f), T_star_f);
+  const float mf = (float)lam * hf;
+  if (mf >= 59.0f) {                  // near or beyond the switch: decide on the exact mean
+    const double m = lam * future_horizon(T, tau, zf, T_star);
+    if (m >= PTRS_MIN_MEAN) return poisson_ptrs(m, gid, gdraw, key);
+  }
+  const float uf = u24f(ua);          // |uf - u53(ua, ub)| <= 2^-24
+  return poisson_inversion_screened(mf, uf, [&](double& m, double& u) {
+    m = lam * future_horizon(T, tau, zf, T_star);
+    u = u53(ua, ub);
+  });
+}
+
 // One thread per (customer, pair of draws): x* (and spend) for every cell.
 template <int NCOL, bool INJECT>
 __global__ void __launch_bounds__(256) k_forecast(ForecastArgs a) {
   const PhiloxKey key = chain_key(a.seed, 0u);
   const bool spend = (NCOL == 5) && a.spend_out != nullptr;
+  const float T_star_f = (float)a.T_star;
   const long long gp0 = a.draw_offset >> 1, gp1 = (a.draw_offset + a.n_draws - 1) >> 1;   // global pair range
   for (long long gp = gp0 + blockIdx.y; gp <= gp1; gp += gridDim.y) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.N;
@@ -102,8 +151,18 @@ __global__ void __launch_bounds__(256) k_forecast(ForecastArgs a) {
         const long long cell = d * a.N + i;
         double lam, tau, zf, eta;
         load_row<NCOL>(a.level1 + cell * NCOL, lam, tau, zf, eta);
-        const double hz = future_horizon(T, tau, zf, a.T_star);
-        const long long xs = poisson_inversion_screened(lam * hz, INJECT ? a.u[cell] : forecast_u(r, gdraw));   // bi:543
+        long long xs;                                                         // bi:543
+        if (INJECT) {
+          const double u = a.u[cell];
+          const bool alive = zf > 0.5;
+          const float hf = alive ? T_star_f : fminf(fmaxf((float)(tau - T), 0.0f), T_star_f);
+          xs = poisson_inversion_screened((float)lam * hf, (float)u, [&](double& m, double& uu) {
+            m = lam * future_horizon(T, tau, zf, a.T_star);
+            uu = u;
+          });
+        } else {
+          xs = forecast_cell(lam, tau, zf, T, a.T_star, T_star_f, h ? r.z : r.x, h ? r.w : r.y, gid, (uint32_t)gdraw, key);
+        }
         if (a.x_out) __stcs(&a.x_out[cell], xs);
         if (spend) {
           // tri:730-737: sum of x* log-normal transactions, log-mean = eta column as stored (Q7)
@@ -125,47 +184,49 @@ __global__ void __launch_bounds__(256) k_forecast(ForecastArgs a) {
   }
 }
 
-// Fused reductions over the draws still resident in HBM: per customer sum of x* and of z (P(alive) = mean z,
-// analysis_bi_helpers.py:98), x* optionally materialised.  blockIdx.y splits the draw pairs; partial sums are exact
-// (integers in fp64) so the atomicAdd order does not matter.
+// Fused reductions over the draws still resident in HBM (draw_offset == 0): per customer sum of x* and of z
+// (P(alive) = mean z, analysis_bi_helpers.py:98), x* optionally materialised.  blockIdx.y splits the draw pairs;
+// partial sums are integers, so the atomicAdd order does not matter.
 template <int NCOL>
 __global__ void __launch_bounds__(256) k_forecast_reduce(ForecastArgs a, double* sum_x, double* sum_z) {
   const PhiloxKey key = chain_key(a.seed, 0u);
-  const long long gp0 = a.draw_offset >> 1, gp1 = (a.draw_offset + a.n_draws - 1) >> 1;
-  const long long npairs = gp1 - gp0 + 1;
+  const float T_star_f = (float)a.T_star;
+  const long long npairs = (a.n_draws + 1) >> 1;
   const long long per = (npairs + gridDim.y - 1) / gridDim.y;
-  const long long pa = gp0 + (long long)blockIdx.y * per, pb = min(gp1 + 1, pa + per);
+  const long long pa = (long long)blockIdx.y * per, pb = min(npairs, pa + per);
+  const long long stride = a.N * NCOL;                 // doubles between consecutive draws of one customer
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.N;
        i += (long long)gridDim.x * blockDim.x) {
     const double T = a.T_cal[i];
     const uint32_t gid = (uint32_t)(a.gid_offset + i);
-    double sx = 0.0, sz = 0.0;
-    for (long long gp = pa; gp < pb; ++gp) {
-      const long long d0 = 2 * gp - a.draw_offset, d1 = d0 + 1;
-      const bool v0 = d0 >= 0 && d0 < a.n_draws, v1 = d1 >= 0 && d1 < a.n_draws;
-      double lam0 = 0, tau0 = 0, z0 = 0, e0, lam1 = 0, tau1 = 0, z1 = 0, e1;
-      if (v0) load_row<NCOL>(a.level1 + (d0 * a.N + i) * NCOL, lam0, tau0, z0, e0);   // both rows in flight
-      if (v1) load_row<NCOL>(a.level1 + (d1 * a.N + i) * NCOL, lam1, tau1, z1, e1);
+    long long sx = 0;
+    int sz = 0;
+    const double* row = a.level1 + (2 * pa * a.N + i) * NCOL;
+    long long* xo = a.x_out ? a.x_out + 2 * pa * a.N + i : nullptr;
+    for (long long gp = pa; gp < pb; ++gp, row += 2 * stride) {
+      const bool v1 = 2 * gp + 1 < a.n_draws;          // only the very last pair can be half empty
+      double lam0, tau0, z0, e0, lam1 = 0.0, tau1 = 0.0, z1 = 0.0, e1;
+      load_row<NCOL>(row, lam0, tau0, z0, e0);          // both rows in flight before the arithmetic starts
+      if (v1) load_row<NCOL>(row + stride, lam1, tau1, z1, e1);
       const uint4 r = philox4x32_10(gid, (uint32_t)gp, 0u, DOM_FORECAST, key);
-      if (v0) {
-        const long long xs = poisson_inversion_screened(lam0 * future_horizon(T, tau0, z0, a.T_star), u53(r.x, r.y));
-        if (a.x_out) __stcs(&a.x_out[d0 * a.N + i], xs);
-        sx += (double)xs;
-        sz += (z0 > 0.5) ? 1.0 : 0.0;
-      }
+      const long long x0 = forecast_cell(lam0, tau0, z0, T, a.T_star, T_star_f, r.x, r.y, gid, (uint32_t)(2 * gp), key);
+      sx += x0;
+      sz += (z0 > 0.5) ? 1 : 0;
+      if (xo) { __stcs(xo, x0); }
       if (v1) {
-        const long long xs = poisson_inversion_screened(lam1 * future_horizon(T, tau1, z1, a.T_star), u53(r.z, r.w));
-        if (a.x_out) __stcs(&a.x_out[d1 * a.N + i], xs);
-        sx += (double)xs;
-        sz += (z1 > 0.5) ? 1.0 : 0.0;
+        const long long x1 = forecast_cell(lam1, tau1, z1, T, a.T_star, T_star_f, r.z, r.w, gid, (uint32_t)(2 * gp + 1), key);
+        sx += x1;
+        sz += (z1 > 0.5) ? 1 : 0;
+        if (xo) __stcs(xo + a.N, x1);
       }
+      if (xo) xo += 2 * a.N;
     }
     if (gridDim.y == 1) {
-      sum_x[i] = sx;
-      sum_z[i] = sz;
+      sum_x[i] = (double)sx;
+      sum_z[i] = (double)sz;
     } else {
-      atomicAdd(&sum_x[i], sx);
-      atomicAdd(&sum_z[i], sz);
+      atomicAdd(&sum_x[i], (double)sx);
+      atomicAdd(&sum_z[i], (double)sz);
     }
   }
 }

@@ -169,6 +169,36 @@ def forecast_uniform(seed, gids, draw):
     return u53(r[2], r[3]) if draw & 1 else u53(r[0], r[1])
 
 
+PTRS_MIN_MEAN = 60.0
+
+
+def forecast_poisson_ptrs(seed, gid, draw, lam):
+    """Device contract for means >= PTRS_MIN_MEAN: Hoermann's PTRS (the algorithm NumPy's Generator.poisson uses for
+    lam >= 10; numpy/random/src/distributions/distributions.c, third-party, not in the reference tree); attempt t draws
+    its two uniforms from Philox block (gid, draw, 64 + t, DOM_FORECAST)."""
+    from math import lgamma, log, sqrt, floor, fabs
+    k0, k1 = chain_key(seed, 0)
+    slam, loglam = sqrt(lam), log(lam)
+    b = 0.931 + 2.53 * slam
+    a = -0.059 + 0.02483 * b
+    invalpha = 1.1239 + 1.1328 / (b - 3.4)
+    vr = 0.9277 - 3.6224 / (b - 2.0)
+    t = 0
+    while True:
+        r = philox4x32_10(np.asarray([gid], dtype=np.uint64), draw, 64 + t, DOM_FORECAST, k0, k1)
+        t += 1
+        U = float(u53(r[0], r[1])[0]) - 0.5
+        V = float(u53(r[2], r[3])[0])
+        us = 0.5 - fabs(U)
+        kd = floor((2.0 * a / us + b) * U + lam + 0.43)
+        if us >= 0.07 and V <= vr:
+            return int(kd)
+        if kd < 0 or (us < 0.013 and V > us):
+            continue
+        if log(V) + log(invalpha) - log(a / (us * us) + b) <= -lam + kd * loglam - lgamma(kd + 1.0):
+            return int(kd)
+
+
 def forecast_spend_normal(seed, gid, draw, j):
     """j-th per-transaction normal of cell (draw, gid)."""
     k0, k1 = chain_key(seed, 0)
