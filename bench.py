@@ -349,6 +349,12 @@ def run_ours(args):
 
 
 def main():
+    # Libraries (NCCL's version banner, torchrun hints) may write to fd 1: park it on stderr and keep the real
+    # stdout for the single JSON line.
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -49,10 +49,10 @@ typedef enum {
 } clv_compat;
 
 typedef enum {
-  CLV_SWEEP_AUTO = 0,
-  CLV_SWEEP_STREAM = 1,    /* two kernels per sweep on a stream */
-  CLV_SWEEP_GRAPH = 2,     /* two kernels per sweep, replayed from a CUDA graph */
-  CLV_SWEEP_PERSISTENT = 3 /* one cooperative kernel, grid sync per sweep (single shard only) */
+  CLV_SWEEP_AUTO = 0,      /* persistent when every 128-customer tile gets its own co-resident block, else stream */
+  CLV_SWEEP_STREAM = 1,    /* two kernels per sweep on a stream (k_sweep, k_level2) */
+  CLV_SWEEP_RESERVED = 2,  /* treated as CLV_SWEEP_STREAM */
+  CLV_SWEEP_PERSISTENT = 3 /* one cooperative kernel, grid barrier per sweep (single shard only) */
 } clv_sweep_mode;
 
 typedef struct clv_sampler clv_sampler;

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("CLV_B200_LIB") or os.path.join(_HERE, "libclv_b200.so
 MAX_K = 16
 RNG_FAST, RNG_STRICT, RNG_INJECTED = 0, 1, 2
 COMPAT_REFERENCE, COMPAT_PAPER = 0, 1
-SWEEP_AUTO, SWEEP_STREAM, SWEEP_GRAPH, SWEEP_PERSISTENT = 0, 1, 2, 3
+SWEEP_AUTO, SWEEP_STREAM, SWEEP_PERSISTENT = 0, 1, 3
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

@@ -17,7 +17,7 @@ from .hostmath import ExactSum, init_statistics
 
 _RNG = {"fast": L.RNG_FAST, "strict": L.RNG_STRICT, "injected": L.RNG_INJECTED}
 _COMPAT = {"reference": L.COMPAT_REFERENCE, "paper": L.COMPAT_PAPER}
-_SWEEP = {"auto": L.SWEEP_AUTO, "stream": L.SWEEP_STREAM, "graph": L.SWEEP_GRAPH, "persistent": L.SWEEP_PERSISTENT}
+_SWEEP = {"auto": L.SWEEP_AUTO, "stream": L.SWEEP_STREAM, "persistent": L.SWEEP_PERSISTENT}
 
 
 def default_hyper(K: int, D: int):
