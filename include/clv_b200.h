@@ -192,6 +192,19 @@ int clv_forecast_injected(const clv_forecast_config* cfg, const double* level1, 
 int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t* x_star, double* mean_x_star,
                           double* p_alive, double* kernel_ms /* nullable: CUDA-event time of the kernel */);
 
+/* ---- analysis reductions on the resident draws (SURVEY 8f "next" rows) ---------------------- */
+#define CLV_SUMMARY_COLS 10
+/* Per-customer posterior summaries over all resident draws of all chains (post_mean_lambdas/mus and compute_table4,
+ * src/models/utils/analysis_bi_helpers.py:15-27, 75-110): out [n_local][CLV_SUMMARY_COLS] =
+ * mean lambda, 2.5 % and 97.5 % of lambda | mean of min(mu, mu_cap), 2.5 % and 97.5 % of mu (raw) | mean z = P(alive) |
+ * mean tau | mean mu (raw) | mean eta (0 for D=2).  Percentiles are np.percentile's (linear). */
+int clv_posterior_summary(clv_sampler* h, double mu_cap, double* out);
+/* Weekly tracking simulation (Figure 2; bivariate/analysis_abe.py:446-464): for each resident draw and each time
+ * times[w], the sum over customers of Poisson(lambda_i) while birth_week_i < t <= birth_week_i + tau_i; returns the mean
+ * over draws inc_mean[n_weeks] (the caller takes the cumulative sum, analysis_abe.py:460). */
+int clv_weekly_tracking(clv_sampler* h, const double* birth_week, const double* times, int n_weeks, uint64_t seed,
+                        double* inc_mean);
+
 /* ---- synthetic customers, generate_pareto_abe (bi:95-187) ---------------------------------- */
 /* Device-side generator of the CBS law (x, t_x, x_star | lambda, mu, tau) for n customers with design
  * matrix X = [1, U(-1,1)^(K-1)] (bi:118-122) and theta = exp(X beta + MVN(0, gamma)) (bi:133-136).

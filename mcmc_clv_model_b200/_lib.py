@@ -87,6 +87,8 @@ SIGNATURES = {
     "clv_forecast_injected": (C.c_int, [C.POINTER(ForecastConfig), c_double_p, c_double_p, c_double_p, c_double_p,
                                         C.c_int64, c_int64_p, c_int64_p, c_double_p]),
     "clv_forecast_resident": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, c_int64_p, c_double_p, c_double_p, c_double_p]),
+    "clv_posterior_summary": (C.c_int, [C.c_void_p, C.c_double, c_double_p]),
+    "clv_weekly_tracking": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int, C.c_uint64, c_double_p]),
     "clv_generate": (C.c_int, [C.POINTER(GenerateConfig), c_double_p, c_double_p, C.c_int, C.c_int, c_int32_p, c_double_p, c_double_p,
                                c_double_p, c_int32_p, c_double_p, c_double_p, c_double_p]),
     "clv_measure_issue_peaks": (C.c_int, [C.c_int, c_double_p]),

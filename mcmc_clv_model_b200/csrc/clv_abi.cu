@@ -995,6 +995,11 @@ int clv_set_state(clv_sampler* h, int chain, const double* ll, const double* lm,
   CK(h, cudaSetDevice(h->cfg.device));
   CK(h, cudaStreamSynchronize(h->stream));
   const size_t N = (size_t)h->N, o = (size_t)chain * N;
+  // the sweep kernel's exp is exact on the clip range of bi:323-324 and well defined up to +-700: reject anything else
+  for (const double* v : {ll, lm})
+    if (v)
+      for (size_t i = 0; i < N; ++i)
+        if (!(std::fabs(v[i]) <= 700.0)) return fail(h, CLV_ERR_ARG, "clv_set_state: log lambda / log mu must be finite and within +-700");
   if (ll) CK(h, cudaMemcpy(h->d_ll + o, ll, N * sizeof(double), cudaMemcpyHostToDevice));
   if (lm) CK(h, cudaMemcpy(h->d_lm + o, lm, N * sizeof(double), cudaMemcpyHostToDevice));
   if (le && h->D == 3) CK(h, cudaMemcpy(h->d_le + o, le, N * sizeof(double), cudaMemcpyHostToDevice));
@@ -1256,6 +1261,70 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
   cudaFree(d_mx); cudaFree(d_pa);
   if (d_x) cudaFree(d_x);
   if (e != cudaSuccess) return fail(h, CLV_ERR_CUDA, "clv_forecast_resident failed: %s", cudaGetErrorString(e));
+  return CLV_OK;
+}
+
+// ---- "next" rows on the resident draws -----------------------------------------------------------
+int clv_posterior_summary(clv_sampler* h, double mu_cap, double* out) {
+  if (!h || !out) return fail(h, CLV_ERR_ARG, "null argument");
+  if (h->resident_draws <= 0) return fail(h, CLV_ERR_STATE, "no resident draws: call clv_run (single device chunk) or clv_run_resident first");
+  CK(h, cudaSetDevice(h->cfg.device));
+  const long long n_tot = (long long)h->chains * h->resident_draws, N = h->N;
+  int n_pad = 1;
+  while (n_pad < n_tot) n_pad <<= 1;
+  const size_t smem = (size_t)n_pad * sizeof(double);
+  if (smem > 220 * 1024) return fail(h, CLV_ERR_ARG, "clv_posterior_summary: %lld draws per customer exceed the in-shared-memory sort (max 28160)", n_tot);
+  double* d_out = nullptr;
+  CK(h, dmalloc(&d_out, (size_t)N * SUMMARY_COLS));
+  cudaError_t e;
+  const int grid = (int)std::min<long long>(N, (long long)h->sm_count * 16);
+  if (h->ncol == 4) {
+    e = cudaFuncSetAttribute(k_posterior_summary<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) k_posterior_summary<4><<<grid, 256, smem, h->stream>>>(h->d_draws[0], n_tot, N, n_pad, mu_cap, d_out);
+  } else {
+    e = cudaFuncSetAttribute(k_posterior_summary<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) k_posterior_summary<5><<<grid, 256, smem, h->stream>>>(h->d_draws[0], n_tot, N, n_pad, mu_cap, d_out);
+  }
+  h->launches++;
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(double) * N * SUMMARY_COLS, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(h, CLV_ERR_CUDA, "clv_posterior_summary failed: %s", cudaGetErrorString(e));
+  return CLV_OK;
+}
+
+int clv_weekly_tracking(clv_sampler* h, const double* birth_week, const double* times, int n_weeks, uint64_t seed,
+                        double* inc_mean) {
+  if (!h || !birth_week || !times || !inc_mean) return fail(h, CLV_ERR_ARG, "null argument");
+  if (n_weeks < 1 || n_weeks > 4096) return fail(h, CLV_ERR_ARG, "n_weeks must be in [1, 4096]");
+  if (h->resident_draws <= 0) return fail(h, CLV_ERR_STATE, "no resident draws: call clv_run (single device chunk) or clv_run_resident first");
+  CK(h, cudaSetDevice(h->cfg.device));
+  if (int r = upload_rk()) return r;
+  const long long n_tot = (long long)h->chains * h->resident_draws, N = h->N;
+  double *d_birth = nullptr, *d_times = nullptr;
+  unsigned long long* d_tot = nullptr;
+  CK(h, dmalloc(&d_birth, (size_t)N));
+  CK(h, dmalloc(&d_times, (size_t)n_weeks));
+  CK(h, dmalloc(&d_tot, (size_t)n_weeks));
+  cudaError_t e = cudaMemcpyAsync(d_birth, birth_week, sizeof(double) * N, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_times, times, sizeof(double) * n_weeks, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long) * n_weeks, h->stream);
+  if (e == cudaSuccess) {
+    const int gx = (int)std::min<long long>((N + 255) / 256, 65535);
+    const int gy = (int)std::max<long long>(1, std::min<long long>(n_tot, (long long)h->sm_count * 8 * 4 / std::max(1, gx) + 1));
+    const size_t smem = sizeof(unsigned long long) * n_weeks;
+    if (h->ncol == 4) k_weekly_tracking<4><<<dim3(gx, gy), 256, smem, h->stream>>>(h->d_draws[0], n_tot, N, h->cfg.gid_offset, d_birth, d_times, n_weeks, seed, d_tot);
+    else k_weekly_tracking<5><<<dim3(gx, gy), 256, smem, h->stream>>>(h->d_draws[0], n_tot, N, h->cfg.gid_offset, d_birth, d_times, n_weeks, seed, d_tot);
+    h->launches++;
+    e = cudaGetLastError();
+  }
+  std::vector<unsigned long long> tot((size_t)n_weeks);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tot.data(), d_tot, sizeof(unsigned long long) * n_weeks, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_birth); cudaFree(d_times); cudaFree(d_tot);
+  if (e != cudaSuccess) return fail(h, CLV_ERR_CUDA, "clv_weekly_tracking failed: %s", cudaGetErrorString(e));
+  for (int w = 0; w < n_weeks; ++w) inc_mean[w] = (double)tot[w] / (double)n_tot;   // analysis_abe.py:459
   return CLV_OK;
 }
 

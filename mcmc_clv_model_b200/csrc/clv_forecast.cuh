@@ -55,14 +55,14 @@ __device__ __forceinline__ long long poisson_inversion_screened(float mf, float 
 // Large means (production path only): Hoermann's transformed rejection "PTRS" (the algorithm NumPy uses for lam >= 10),
 // exact, ~1.2 attempts whatever the mean -- a customer with lambda * T_star in the hundreds must not cost hundreds of
 // dependent fp64 iterations per draw.  Attempt t takes its two uniforms from Philox block (gid, draw, 64 + t).
-__device__ __noinline__ long long poisson_ptrs(double lam, uint32_t gid, uint32_t gdraw, PhiloxKey key) {
+__device__ __noinline__ long long poisson_ptrs(double lam, uint32_t gid, uint32_t gdraw, PhiloxKey key, uint32_t slot0 = 64u) {
   const double slam = sqrt(lam), loglam = log(lam);
   const double b = 0.931 + 2.53 * slam;
   const double a = -0.059 + 0.02483 * b;
   const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
   const double vr = 0.9277 - 3.6224 / (b - 2.0);
   for (uint32_t t = 0; t < 4096u; ++t) {
-    const uint4 r = philox4x32_10(gid, gdraw, 64u + t, DOM_FORECAST, key);
+    const uint4 r = philox4x32_10(gid, gdraw, slot0 + t, DOM_FORECAST, key);
     const double U = u53(r.x, r.y) - 0.5, V = u53(r.z, r.w);
     const double us = 0.5 - fabs(U);
     const double kd = floor((2.0 * a / us + b) * U + lam + 0.43);
@@ -229,6 +229,127 @@ __global__ void __launch_bounds__(256) k_forecast_reduce(ForecastArgs a, double*
       atomicAdd(&sum_z[i], (double)sz);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// "next" rows of SURVEY 8f on the draws resident in HBM
+// ------------------------------------------------------------------------------------------------
+constexpr int SUMMARY_COLS = 10;   // mean lambda, q2.5, q97.5 | capped mean mu, q2.5, q97.5 | mean z | mean tau | mean mu | mean eta
+
+__device__ __forceinline__ void bitonic_sort_shared(double* v, int n_pad) {
+  for (int k = 2; k <= n_pad; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < n_pad; t += blockDim.x) {
+        const int p = t ^ j;
+        if (p > t) {
+          const double a = v[t], b = v[p];
+          const bool up = (t & k) == 0;
+          if ((a > b) == up) { v[t] = b; v[p] = a; }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+// np.percentile(..., method="linear") of a sorted array
+__device__ __forceinline__ double percentile_sorted(const double* v, int n, double q) {
+  const double pos = q * 0.01 * (double)(n - 1);
+  const int lo = (int)floor(pos);
+  const int hi = min(lo + 1, n - 1);
+  const double t = pos - (double)lo, a = v[lo], b = v[hi];
+  return (t < 0.5) ? a + (b - a) * t : b - (b - a) * (1.0 - t);
+}
+
+// Per-customer posterior summaries over every resident draw (Table 4 inputs: utils/analysis_bi_helpers.py:75-110,
+// post_mean_lambdas/mus :15-27).  One block per customer; its draws are gathered into shared memory and sorted there.
+template <int NCOL>
+__global__ void __launch_bounds__(256) k_posterior_summary(const double* level1, long long n_tot, long long N, int n_pad,
+                                                           double mu_cap, double* out) {
+  extern __shared__ double sh[];
+  __shared__ double red[8][8];
+  for (long long i = blockIdx.x; i < N; i += gridDim.x) {
+    double acc[6] = {0, 0, 0, 0, 0, 0};   // lambda, capped mu, z, tau, mu, eta
+    for (int pass = 0; pass < 2; ++pass) {          // pass 0: lambda column, pass 1: mu column
+      for (long long d = threadIdx.x; d < n_pad; d += blockDim.x) {
+        double val = CUDART_INF;
+        if (d < n_tot) {
+          const double* row = level1 + (d * N + i) * NCOL;
+          val = row[pass];
+          if (pass == 0) {
+            acc[0] += val; acc[2] += row[3]; acc[3] += row[2];
+            if (NCOL == 5) acc[5] += row[4];
+          } else {
+            acc[1] += fmin(val, mu_cap); acc[4] += val;
+          }
+        }
+        sh[d] = val;
+      }
+      __syncthreads();
+      bitonic_sort_shared(sh, n_pad);
+      if (threadIdx.x == 0) {
+        out[i * SUMMARY_COLS + 3 * pass + 1] = percentile_sorted(sh, (int)n_tot, 2.5);
+        out[i * SUMMARY_COLS + 3 * pass + 2] = percentile_sorted(sh, (int)n_tot, 97.5);
+      }
+      __syncthreads();
+    }
+    // block reduction of the six sums
+    for (int c = 0; c < 6; ++c) {
+      double v = acc[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot[6] = {0, 0, 0, 0, 0, 0};
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+        for (int c = 0; c < 6; ++c) tot[c] += red[w][c];
+      const double inv = 1.0 / (double)n_tot;
+      out[i * SUMMARY_COLS + 0] = tot[0] * inv;
+      out[i * SUMMARY_COLS + 3] = tot[1] * inv;
+      out[i * SUMMARY_COLS + 6] = tot[2] * inv;
+      out[i * SUMMARY_COLS + 7] = tot[3] * inv;
+      out[i * SUMMARY_COLS + 8] = tot[4] * inv;
+      out[i * SUMMARY_COLS + 9] = tot[5] * inv;
+    }
+    __syncthreads();
+  }
+}
+
+// Weekly tracking simulation (Figure 2; bivariate/analysis_abe.py:446-464): for every resident draw and every week t,
+// sum over customers of Poisson(lambda_i) while birth_i < t <= birth_i + tau_i.  One thread per (customer, draw);
+// uniforms: Philox (gid, draw, 256 + w/4, DOM_FORECAST), word w%4, 32-bit; totals are integers => order independent.
+template <int NCOL>
+__global__ void __launch_bounds__(256) k_weekly_tracking(const double* level1, long long n_tot, long long N, long long gid_offset,
+                                                         const double* birth, const double* times, int n_weeks, uint64_t seed,
+                                                         unsigned long long* totals) {
+  extern __shared__ unsigned long long s_week[];
+  const PhiloxKey key = chain_key(seed, 0u);
+  for (int w = threadIdx.x; w < n_weeks; w += blockDim.x) s_week[w] = 0ull;
+  __syncthreads();
+  for (long long d = blockIdx.y; d < n_tot; d += gridDim.y)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+      const double* row = level1 + (d * N + i) * NCOL;
+      const double lam = __ldcs(row), tau = __ldcs(row + 2);
+      const double b0 = birth[i], b1 = b0 + tau;
+      const float lamf = (float)lam;
+      const uint32_t gid = (uint32_t)(gid_offset + i);
+      uint4 r = make_uint4(0, 0, 0, 0);
+      int have = -1;
+      for (int w = 0; w < n_weeks; ++w) {
+        const double t = times[w];
+        if (!(t > b0 && t <= b1)) continue;
+        if ((w >> 2) != have) { have = w >> 2; r = philox4x32_10(gid, (uint32_t)d, 256u + (uint32_t)have, DOM_FORECAST, key); }
+        const uint32_t word = (w & 3) == 0 ? r.x : (w & 3) == 1 ? r.y : (w & 3) == 2 ? r.z : r.w;
+        long long inc;
+        if (lam >= PTRS_MIN_MEAN) inc = poisson_ptrs(lam, gid, (uint32_t)d, key, 65536u + 64u * (uint32_t)w);
+        else inc = poisson_inversion_screened(lamf, u24f(word), [&](double& m, double& u) { m = lam; u = u32d(word); });
+        if (inc) atomicAdd(&s_week[w], (unsigned long long)inc);
+      }
+    }
+  __syncthreads();
+  for (int w = threadIdx.x; w < n_weeks; w += blockDim.x)
+    if (s_week[w]) atomicAdd(&totals[w], s_week[w]);
 }
 
 __global__ void k_scale(double* a, double* b, long long n, double f) {

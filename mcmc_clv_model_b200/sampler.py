@@ -231,3 +231,24 @@ class Sampler:
                                                xs.ctypes.data_as(L.c_int64_p) if xs is not None else None,
                                                L.dptr(mx), L.dptr(pa), C.byref(ms)), self.h)
         return dict(mean_x_star=mx, p_alive=pa, x_star=xs, kernel_ms=ms.value, n_draws_total=self.chains * nd.value)
+
+    # ---- analysis reductions on the resident draws -------------------------------------
+    SUMMARY_COLUMNS = ("mean_lambda", "lambda_2.5", "lambda_97.5", "mean_mu_capped", "mu_2.5", "mu_97.5", "p_alive",
+                       "mean_tau", "mean_mu", "mean_eta")
+
+    def posterior_summary(self, mu_cap=0.05):
+        """Per-customer posterior means / percentiles over every resident draw (compute_table4's inputs,
+        utils/analysis_bi_helpers.py:75-110) -> dict of (N,) arrays keyed by SUMMARY_COLUMNS."""
+        out = np.empty((self.N, len(self.SUMMARY_COLUMNS)))
+        L.check(self.lib.clv_posterior_summary(self.h, float(mu_cap), L.dptr(out)), self.h)
+        return {k: out[:, j].copy() for j, k in enumerate(self.SUMMARY_COLUMNS)}
+
+    def weekly_tracking(self, birth_week, times, seed=0):
+        """Mean over resident draws of the weekly incremental repeat transactions (Figure 2,
+        bivariate/analysis_abe.py:446-464); np.cumsum of the result is the tracking curve."""
+        b = np.ascontiguousarray(birth_week, dtype=np.float64)
+        t = np.ascontiguousarray(times, dtype=np.float64)
+        out = np.empty(t.size)
+        L.check(self.lib.clv_weekly_tracking(self.h, L.dptr(b), L.dptr(t), int(t.size), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                             L.dptr(out)), self.h)
+        return out

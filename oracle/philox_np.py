@@ -205,3 +205,10 @@ def forecast_spend_normal(seed, gid, draw, j):
     r = philox4x32_10(np.asarray([gid], dtype=np.uint64), draw, 1 + j // 2, DOM_FORECAST, k0, k1)
     c, s = normal_pair_u53(r[0], r[1], r[2], r[3])
     return float(c[0] if j % 2 == 0 else s[0])
+
+
+def weekly_uniform(seed, gids, draw, w):
+    """Uniform of week index w for (customer, global draw): block (gid, draw, 256 + w//4), word w%4, 32 bits."""
+    k0, k1 = chain_key(seed, 0)
+    r = philox4x32_10(np.asarray(gids, dtype=np.uint64), draw, 256 + w // 4, DOM_FORECAST, k0, k1)
+    return u32(r[w % 4])

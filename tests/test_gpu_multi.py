@@ -25,3 +25,24 @@ def test_two_gpu_sharded_run_is_bit_identical(D):
                         "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "sharded_check.py"),
                         "150001", str(D)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_chains_across_gpus_equal_single_gpu():
+    """Chains are independent (bi:485-501): spreading them over two GPUs (one handle and host thread per GPU, no
+    communication) gives exactly the chains of the single-GPU call."""
+    import numpy as np
+    import pandas as pd
+    from conftest import load_golden
+    from mcmc_clv_model_b200 import mcmc_draw_parameters, mcmc_draw_parameters_rfm_m
+    d = load_golden("cdnow_abe.npz")
+    cbs = pd.DataFrame({k: d[k][:800] for k in ("x", "t_x", "T_cal", "first_sales_scaled", "log_s")})
+    kw = dict(covariates=["first_sales_scaled"], mcmc=12, burnin=20, thin=3, chains=5, seed=7, trace=0)
+    for fn in (mcmc_draw_parameters, mcmc_draw_parameters_rfm_m):
+        one = fn(cbs, devices=[0], **kw)
+        two = fn(cbs, devices=[0, 1], **kw)
+        assert len(two["level_1"]) == 5
+        for c in range(5):
+            np.testing.assert_array_equal(one["level_1"][c], two["level_1"][c])
+            np.testing.assert_array_equal(one["level_2"][c], two["level_2"][c])
+        assert one["log_likelihood"] == two["log_likelihood"]

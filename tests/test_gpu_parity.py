@@ -328,3 +328,40 @@ def test_screened_poisson_inversion_is_exact_on_adversarial_uniforms():
     L.check(L.load().clv_forecast_injected(C.byref(cfg), L.dptr(l1), L.dptr(np.full(N, 30.0)), L.dptr(np.ascontiguousarray(u[None])),
                                            None, 0, None, xs.ctypes.data_as(L.c_int64_p), None))
     np.testing.assert_array_equal(xs[0], ao.poisson_inversion(l1[0, :, 0] * 39.0, u))
+
+
+def test_posterior_summary_and_weekly_tracking_on_resident_draws(cdnow_abe):
+    """the on-device reductions equal NumPy on the same draws (the reference's
+    utils/analysis_bi_helpers.py arithmetic) and the weekly simulation equals its restatement on the same Philox uniforms."""
+    from oracle import philox_np as px
+    d = cdnow_abe
+    n = 400
+    with Sampler(d["x"][:n], d["t_x"][:n], d["T_cal"][:n], np.ones((n, 1)), chains=2, seed=3) as s:
+        out = s.run(30, 37, 1)
+        summ = s.posterior_summary(mu_cap=0.05)
+        rng = np.random.default_rng(0)
+        birth = rng.uniform(0, 12, n)
+        times = np.arange(1.0, 41.0)
+        inc = s.weekly_tracking(birth, times, seed=99)
+    l1 = np.concatenate(list(out["level_1"]), axis=0)                # (74, n, 4), chain-major like np.concatenate(draws["level_1"])
+    np.testing.assert_allclose(summ["mean_lambda"], l1[:, :, 0].mean(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(summ["mean_mu_capped"], np.clip(l1[:, :, 1], None, 0.05).mean(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(summ["mean_mu"], l1[:, :, 1].mean(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(summ["p_alive"], l1[:, :, 3].mean(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(summ["mean_tau"], l1[:, :, 2].mean(axis=0), rtol=1e-12)
+    for col, key in ((0, "lambda"), (1, "mu")):
+        np.testing.assert_allclose(summ[f"{key}_2.5"], np.percentile(l1[:, :, col], 2.5, axis=0), rtol=1e-12)
+        np.testing.assert_allclose(summ[f"{key}_97.5"], np.percentile(l1[:, :, col], 97.5, axis=0), rtol=1e-12)
+    # weekly tracking: exact restatement with the same counter-based uniforms
+    tot = np.zeros(times.size)
+    gids = np.arange(n)
+    for dd in range(l1.shape[0]):
+        lam, tau = l1[dd, :, 0], l1[dd, :, 2]
+        for w, t in enumerate(times):
+            active = (t > birth) & (t <= birth + tau)                 # analysis_abe.py:456
+            u = px.weekly_uniform(99, gids, dd, w)
+            tot[w] += ao.poisson_inversion(lam, u)[active].sum()
+    np.testing.assert_array_equal(inc, tot / l1.shape[0])
+    # and the expectation: sum_i lambda_i * active
+    expect = np.array([(l1[:, :, 0] * ((t > birth) & (t <= birth + l1[:, :, 2]))).sum(axis=1).mean() for t in times])
+    assert np.all(np.abs(inc - expect) < 6 * np.sqrt(expect / l1.shape[0]) + 0.5)

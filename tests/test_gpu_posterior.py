@@ -50,3 +50,50 @@ def test_c1_posterior_matches_reference(cdnow_abe, rng):
 def test_m2_posterior_matches_reference_including_beta_quirk(cdnow_abe):
     out, tail = _run(cdnow_abe, ["first_sales_scaled"], "fast")
     _check(out, tail, REF_M2, cdnow_abe["x"].size)
+
+
+def _golden_case(name, cbs, D, chains=16, rng="fast"):
+    """Pooled posterior means of every level-2 column vs the reference's own chains (tests/golden/post_*.npz,
+    produced by tests/golden/make_posterior_golden.py from the unmodified reference)."""
+    from conftest import load_golden
+    g = load_golden(f"post_{name}.npz")
+    cov = [str(c) for c in g["covariates"]]
+    X = np.column_stack([np.ones(cbs["x"].size)] + [cbs[c].astype(float) for c in cov])
+    log_s = cbs["log_s"] if D == 3 else None
+    with Sampler(cbs["x"], cbs["t_x"], cbs["T_cal"], X, log_s, model_dim=D, chains=chains, n_mh_steps=20, seed=123, rng=rng) as s:
+        out = s.run(int(g["burnin"]), int(g["mcmc"]), 1, store_level1=False)
+        tail = s.run(0, 200, 10, store_level1=True)
+    summ = summarize(out["level_2"])
+    worst = 0.0
+    for j in range(len(g["mean"])):
+        tol = 3.0 * np.hypot(g["mcse"][j], summ[j]["mcse_mean"])
+        worst = max(worst, abs(summ[j]["mean"] - g["mean"][j]) / tol)
+        assert abs(summ[j]["mean"] - g["mean"][j]) < tol, \
+            f"{name} level_2 column {j}: ours {summ[j]['mean']:.4f} vs reference {g['mean'][j]:.4f} (3 MCSE = {tol:.4f})"
+    l1 = np.concatenate(list(tail["level_1"]), axis=0).mean(axis=(0, 1))
+    ref1 = g["level1_col_means"]
+    assert abs(l1[0] / ref1[0] - 1) < 0.03 and abs(l1[3] - ref1[3]) < 0.02          # E[lambda], P(alive)
+    if D == 3:
+        assert abs(l1[4] / ref1[4] - 1) < 0.02                                      # E[eta]
+    assert abs((out["loglik_sum"] / cbs["x"].size).mean() - float(g["loglik"])) < 0.05
+    return worst
+
+
+def test_trivariate_k3_posterior_matches_reference(cdnow_abe):
+    _golden_case("tri_k3", cdnow_abe, 3)
+
+
+def test_bivariate_k4_posterior_matches_reference(cdnow_abe):
+    """K=4: the reference's beta-covariance ordering (bi:261) changes the law of beta; compat="reference"
+    reproduces it."""
+    _golden_case("bi_k4", cdnow_abe, 2)
+
+
+def test_full_cdnow_c2_c3_posteriors_match_reference(cdnow_full):
+    """BASELINE.json configs[1] and configs[2] on the full CDNOW data (23 570 customers)."""
+    import os
+    from conftest import GOLDEN
+    for name, D in (("c2_full_bi_k2", 2), ("c3_full_tri_k3", 3)):
+        if not os.path.exists(os.path.join(GOLDEN, f"post_{name}.npz")):
+            pytest.skip(f"golden post_{name}.npz not generated")
+        _golden_case(name, cdnow_full, D, chains=8)
