@@ -220,8 +220,12 @@ def run_ours(args):
     def make(rng="fast"):
         # CBS columns from pinned host memory -> device; exact init statistics on the device (+ NCCL when sharded)
         comm = (broadcast_unique_id(Sampler.comm_unique_id), rank, world) if world > 1 else None
-        return Sampler(pinned["x"][0], pinned["t_x"][0], pinned["T_cal"][0], pinned["X"][0], model_dim=2, chains=1,
-                       n_mh_steps=S_MH, seed=args.seed, rng=rng, device=local, n_global=n_tot, gid_offset=lo, comm=comm)
+        s = Sampler(pinned["x"][0], pinned["t_x"][0], pinned["T_cal"][0], pinned["X"][0], model_dim=2, chains=1,
+                    n_mh_steps=S_MH, seed=args.seed, rng=rng, device=local, n_global=n_tot, gid_offset=lo, comm=comm)
+        if world > 1 and args.collective == "p2p":
+            from mcmc_clv_model_b200.distributed import connect_p2p
+            connect_p2p(s)        # level-2 statistics all-reduced inside k_level2 over NVLink peer mailboxes
+        return s
 
     # ---- device-resident throughput ("value") -----------------------------------------------------
     clk = ClockSampler(local).start()
@@ -266,6 +270,21 @@ def run_ours(args):
         L.check(L.load().clv_measure_issue_peaks(local, pk))
         issue = {"peaks_gops": {"ffma": pk[0], "imad": pk[1], "mufu_ex2": pk[2], "dfma": pk[3]},
                  "customer_mh_steps_per_s_per_gpu": n_loc * S_MH / (k_ms * 1e-3)}
+        if os.path.exists(prof):
+            try:
+                pj = json.load(open(prof))
+                wi = pj["warp_instructions_per_warp_sweep"]                   # ncu: smsp__inst_executed.sum / warps
+                smc = torch.cuda.get_device_properties(local).multi_processor_count
+                mhz = clk.summary()["sm_mhz"] or 1965.0
+                achieved = (n_loc / 32.0) * wi / (k_ms * 1e-3)                  # warp-instructions issued per second
+                peak_issue = smc * 4 * mhz * 1e6                                # one warp-instruction per scheduler per clock
+                issue.update({"bound": "instruction issue", "warp_instructions_per_warp_sweep": wi,
+                              "achieved_warp_inst_per_s": achieved, "peak_warp_inst_per_s": peak_issue,
+                              "frac": achieved / peak_issue,
+                              "ncu_issue_active_pct": pj["metrics"].get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                              "source": "instruction count per warp from profiles/r01_sweep_metrics.json (ncu), rate from this run's CUDA events"})
+            except Exception:
+                pass
 
     # ---- end to end through the C-ABI with host buffers ----------------------------------------------
     barrier()
@@ -340,7 +359,8 @@ def run_ours(args):
                        "rng": "Philox4x32-10 counter-based; fp32 SFU proposal variates, fp64 target/accept/state",
                        "l2": "state + data = %.0f MB per GPU %s L2 (126 MB); the same state is re-read every sweep by design"
                              % (n_loc * 68 / 1e6, ">" if n_loc * 68 > 126e6 else "<"),
-                       "customer_mh_steps_per_sec": value * S_MH},
+                       "customer_mh_steps_per_sec": value * S_MH,
+                       "collective": ("none" if world == 1 else args.collective)},
             "gpu_launches": int(launches), "clocks": clk.summary(), "e2e": e2e, "roofline": roofline,
             "issue_roofline": issue, "cpu_baseline": cpu, "ess": ess, "forecast": forecast}
     print(json.dumps(line), flush=True)
@@ -363,6 +383,8 @@ def main():
     ap.add_argument("--customers", type=int, default=N_C4)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="customer-sharded runs: all-reduce of the level-2 statistics fused into k_level2 over peer memory, or NCCL")
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--no-forecast", action="store_true")
     ap.add_argument("--forecast-customers", type=int, default=1_000_000)

@@ -116,6 +116,13 @@ int clv_get_init_stats(clv_sampler* h, clv_init_stats* out, double* xtx_out);
 int clv_comm_unique_id(void* out128);
 int clv_comm_init(clv_sampler* h, const void* unique_id128, int rank, int world);
 
+/* Optional, after clv_comm_init + clv_init_state: replace the per-sweep NCCL all-reduce by a one-shot all-reduce over
+ * peer memory FUSED INTO the level-2 kernel (each rank stores its int64 partial sums into every rank's mailbox over
+ * NVLink/NVSwitch, publishes a flag, and adds the W partials it received).  Every rank exports its mailbox
+ * (64-byte cudaIpcMemHandle), the host all-gathers the handles, every rank connects.  world <= 16, one process per GPU. */
+int clv_p2p_export(clv_sampler* h, void* handle64);
+int clv_p2p_connect(clv_sampler* h, const void* handles /* world x 64 bytes */, int rank, int world);
+
 /* ---- the chain driver, _run_chain (bi:346-431, tri:465-574) ------------------------------- */
 /* Runs burnin+mcmc sweeps on every chain of the handle and writes, per chain c,
  *   level1 [c][n_draws][n_local][4|5] = lambda, mu, tau, z(, eta)       (bi:407-410, tri:544-548)

@@ -68,6 +68,8 @@ SIGNATURES = {
     "clv_get_init_stats": (C.c_int, [C.c_void_p, C.POINTER(InitStats), c_double_p]),
     "clv_comm_unique_id": (C.c_int, [C.c_void_p]),
     "clv_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "clv_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "clv_p2p_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "clv_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, c_double_p, c_double_p, c_double_p,
                           PROGRESS_CB, C.c_void_p, C.c_int64]),
     "clv_run_resident": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, c_double_p, c_double_p,

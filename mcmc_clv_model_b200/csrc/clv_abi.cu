@@ -96,6 +96,13 @@ struct clv_sampler {
   int grid_x = 1;
   // comm
   nccl_comm_t comm = nullptr; int world = 1, rank = 0;
+  // peer mailboxes (P2P all-reduce fused into k_level2)
+  void* d_mailbox = nullptr; size_t mailbox_bytes = 0, mailbox_flags_off = 0;
+  bool p2p = false;
+  long long* peer_data[P2P_MAX_WORLD] = {nullptr};
+  unsigned long long* peer_flags[P2P_MAX_WORLD] = {nullptr};
+  void* peer_base[P2P_MAX_WORLD] = {nullptr};
+  unsigned long long init_epoch = 0;     // bumped by every clv_init_state: mailbox flags never repeat
   // statistics computed by clv_init_state(h, NULL)
   clv_init_stats last_stats{};
   std::vector<double> last_xtx;
@@ -232,7 +239,7 @@ void launch_sweep_kernel(clv_sampler* h, const SweepArgs& a, int mode) {
 }
 
 int allreduce_acc(clv_sampler* h) {
-  if (!h->comm) return 0;
+  if (!h->comm || h->p2p) return 0;    // p2p: the level-2 kernel reduces over the peer mailboxes itself
   int r = g_nccl.AllReduce(h->d_acc, h->d_acc, (size_t)h->chains * NSTAT_MAX, NCCL_INT64, NCCL_SUM, h->comm, h->stream);
   if (r != 0) return fail(h, CLV_ERR_COMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   return 0;
@@ -240,6 +247,7 @@ int allreduce_acc(clv_sampler* h) {
 
 // One Gibbs sweep in the reference's block order (bi:387-399 / tri:512-536).
 int enqueue_sweep(clv_sampler* h, SweepArgs a, Level2Args l2, int mode) {
+  l2.flag_value = (h->init_epoch << 32) | (unsigned long long)l2.sweep;
   auto do_l2 = [&]() {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) { e0 = pool_event(h); e1 = pool_event(h); cudaEventRecord(e0, h->stream); }
@@ -278,6 +286,8 @@ Level2Args base_l2(clv_sampler* h) {
   l.sweep = 0; l.chain_offset = (uint32_t)h->cfg.chain_offset; l.seed = h->cfg.seed;
   l.injected = 0; l.iw_norm = l.iw_chi2 = l.beta_norm = nullptr;
   l.error_flag = h->d_err;
+  l.world = h->p2p ? h->world : 0; l.rank = h->rank; l.n_chains = h->chains;
+  for (int r = 0; r < P2P_MAX_WORLD; ++r) { l.peer_data[r] = h->peer_data[r]; l.peer_flags[r] = h->peer_flags[r]; }
   return l;
 }
 
@@ -293,6 +303,7 @@ int check_device_error(clv_sampler* h) {
   CK(h, cudaMemcpyAsync(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
   if (h->timing) collect_timing(h);
+  if (flag == 2) return fail(h, CLV_ERR_COMM, "peer mailbox all-reduce timed out (a rank stopped?) at sweep <= %lld", h->sweeps_done);
   if (flag) return fail(h, CLV_ERR_NUMERIC, "level-2 scale matrix not positive definite or non-finite (sweep <= %lld)", h->sweeps_done);
   return 0;
 }
@@ -408,6 +419,9 @@ void clv_destroy(clv_sampler* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  for (int r = 0; r < P2P_MAX_WORLD; ++r)
+    if (h->peer_base[r] && r != h->rank) cudaIpcCloseMemHandle(h->peer_base[r]);
+  if (h->d_mailbox) cudaFree(h->d_mailbox);
   if (h->d_acc3) cudaFree(h->d_acc3);
   if (h->d_barrier) cudaFree(h->d_barrier);
   void* ptrs[] = {h->d_mc, h->d_params, h->d_x, h->d_tx, h->d_T, h->d_Xc, h->d_logs, h->d_ll, h->d_lm, h->d_le,
@@ -628,6 +642,7 @@ int clv_init_state(clv_sampler* h, const clv_init_stats* st) {
   h->launches++;
   CK(h, cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
   h->inited = true;
+  h->init_epoch++;
   if (int r = recompute_stats(h)) return r;
   CK(h, cudaStreamSynchronize(h->stream));
   h->sweeps_done = 0;
@@ -673,6 +688,47 @@ int clv_comm_init(clv_sampler* h, const void* unique_id128, int rank, int world)
   return CLV_OK;
 }
 
+int clv_p2p_export(clv_sampler* h, void* handle64) {
+  if (!h || !handle64) return fail(h, CLV_ERR_ARG, "null argument");
+  CK(h, cudaSetDevice(h->cfg.device));
+  if (!h->d_mailbox) {
+    const size_t data = sizeof(long long) * 2 * P2P_MAX_WORLD * (size_t)h->chains * NSTAT_MAX;
+    const size_t flags = sizeof(unsigned long long) * 2 * P2P_MAX_WORLD * (size_t)h->chains;
+    h->mailbox_flags_off = data;
+    h->mailbox_bytes = data + flags;
+    CK(h, cudaMalloc(&h->d_mailbox, h->mailbox_bytes));
+    CK(h, cudaMemset(h->d_mailbox, 0, h->mailbox_bytes));
+  }
+  cudaIpcMemHandle_t hd;
+  CK(h, cudaIpcGetMemHandle(&hd, h->d_mailbox));
+  static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(handle64, &hd, 64);
+  return CLV_OK;
+}
+
+int clv_p2p_connect(clv_sampler* h, const void* handles, int rank, int world) {
+  if (!h || !handles) return fail(h, CLV_ERR_ARG, "null argument");
+  if (world < 2 || world > P2P_MAX_WORLD || rank < 0 || rank >= world) return fail(h, CLV_ERR_ARG, "p2p: world must be in [2, %d]", P2P_MAX_WORLD);
+  if (!h->d_mailbox) return fail(h, CLV_ERR_STATE, "clv_p2p_connect: call clv_p2p_export first");
+  if (h->cfg.sweep_mode == CLV_SWEEP_PERSISTENT) return fail(h, CLV_ERR_ARG, "persistent sweep mode is single-shard only");
+  CK(h, cudaSetDevice(h->cfg.device));
+  h->rank = rank; h->world = world;
+  for (int r = 0; r < world; ++r) {
+    void* base = h->d_mailbox;
+    if (r != rank) {
+      cudaIpcMemHandle_t hd;
+      std::memcpy(&hd, (const char*)handles + 64 * r, 64);
+      cudaError_t e = cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(h, CLV_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+    }
+    h->peer_base[r] = base;
+    h->peer_data[r] = (long long*)base;
+    h->peer_flags[r] = (unsigned long long*)((char*)base + h->mailbox_flags_off);
+  }
+  h->p2p = true;
+  return CLV_OK;
+}
+
 int64_t clv_sweeps_done(const clv_sampler* h) { return h ? h->sweeps_done : -1; }
 int64_t clv_kernel_launches(const clv_sampler* h) { return h ? h->launches : -1; }
 
@@ -702,7 +758,7 @@ int clv_kernel_time_ms(clv_sampler* h, double* sweep_ms, double* l2_ms, int64_t*
 namespace {
 
 bool want_persistent(const clv_sampler* h) {
-  if (h->comm || h->timing || h->persist_grid_x <= 0 || h->cfg.rng_mode == CLV_RNG_INJECTED) return false;
+  if (h->comm || h->p2p || h->timing || h->persist_grid_x <= 0 || h->cfg.rng_mode == CLV_RNG_INJECTED) return false;
   if (h->cfg.sweep_mode == CLV_SWEEP_PERSISTENT) return true;
   return h->cfg.sweep_mode == CLV_SWEEP_AUTO && h->persist_fits;
 }

@@ -20,6 +20,7 @@ constexpr int MAXK = 16;
 constexpr int MAXD = 3;
 constexpr int NSTAT_MAX = MAXK * MAXD + 6;
 constexpr int SWEEP_THREADS = 128;
+constexpr int P2P_MAX_WORLD = 16;
 // 8 resident blocks of 128 threads per SM (<= 64 registers): measured 25% faster than the 80-register build,
 // the sweep being latency/issue bound (profiles/r01_kernel_ab.txt)
 #ifndef CLV_MINBLOCKS
@@ -549,6 +550,12 @@ struct Level2Args {
   int injected;
   const double *iw_norm, *iw_chi2, *beta_norm;   // injected variates [chains][...]
   int* error_flag;
+  // customer-sharded runs with peer mailboxes (NVLink/NVSwitch P2P stores): the all-reduce of the statistics is done
+  // HERE, inside the level-2 kernel, instead of a separate NCCL call.  world == 0: not used.
+  int world, rank, n_chains;
+  unsigned long long flag_value;             // (init epoch << 32) | sweep: never repeats over the life of a handle
+  long long* peer_data[P2P_MAX_WORLD];           // rank r's mailbox data  [2][P2P_MAX_WORLD][chains][NSTAT_MAX]
+  unsigned long long* peer_flags[P2P_MAX_WORLD]; // rank r's mailbox flags [2][P2P_MAX_WORLD][chains]
 };
 
 // Shared-memory scratch of one level-2 draw (one warp).
@@ -679,10 +686,45 @@ __global__ void __launch_bounds__(32) k_level2(Level2Args a) {
   const int chain = blockIdx.x, lane = threadIdx.x;
   const int K = mc.K;
   const int nstat = K * D + D * (D + 1) / 2;
-  for (int t = lane; t < nstat; t += 32) {
-    unsigned long long* p = &a.acc[chain * NSTAT_MAX + t];
-    sc.st[t] = (double)(long long)(*p) * mc.fx_inv;
-    *p = 0ull;
+  if (a.world <= 1) {
+    for (int t = lane; t < nstat; t += 32) {
+      unsigned long long* p = &a.acc[chain * NSTAT_MAX + t];
+      sc.st[t] = (double)(long long)(*p) * mc.fx_inv;
+      *p = 0ull;
+    }
+  } else {
+    // One-shot all-reduce over peer memory: every rank stores its partial sums into every rank's mailbox, publishes
+    // the sweep number as the flag, waits for the other ranks' flags and adds the W partials (int64: exact, so every
+    // rank gets the same totals whatever the arrival order).  Mailboxes are double-buffered by sweep parity: a rank
+    // can only reach sweep s+2 after every peer published s+1, i.e. after they finished reading parity s.
+    const int par = (int)(a.sweep & 1u);
+    const size_t slot = ((size_t)par * P2P_MAX_WORLD + a.rank) * a.n_chains + chain;
+    for (int t = lane; t < nstat; t += 32) {
+      unsigned long long* p = &a.acc[chain * NSTAT_MAX + t];
+      const long long v = (long long)(*p);
+      *p = 0ull;
+      for (int r = 0; r < a.world; ++r) __stcg(&a.peer_data[r][slot * NSTAT_MAX + t], v);
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane < a.world) *((volatile unsigned long long*)&a.peer_flags[lane][slot]) = a.flag_value;
+    if (lane < a.world) {
+      const size_t src = ((size_t)par * P2P_MAX_WORLD + lane) * a.n_chains + chain;
+      volatile unsigned long long* f = (volatile unsigned long long*)&a.peer_flags[a.rank][src];
+      const long long t0 = clock64();
+      while (*f != a.flag_value)
+        if (clock64() - t0 > 8000000000ll) { *a.error_flag = 2; break; }   // a peer died: give up after ~4 s
+    }
+    __threadfence_system();
+    __syncwarp();
+    for (int t = lane; t < nstat; t += 32) {
+      long long tot = 0;
+      for (int r = 0; r < a.world; ++r) {
+        const size_t src = ((size_t)par * P2P_MAX_WORLD + r) * a.n_chains + chain;
+        tot += __ldcv(&a.peer_data[a.rank][src * NSTAT_MAX + t]);
+      }
+      sc.st[t] = (double)tot * mc.fx_inv;
+    }
   }
   __syncwarp();
   ChainParams& cp = a.params[chain];

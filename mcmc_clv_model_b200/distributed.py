@@ -60,3 +60,14 @@ def gather_level1(local_draws: np.ndarray, group=None):
     if objs is None:
         return None
     return np.concatenate(objs, axis=1)
+
+
+def connect_p2p(sampler, group=None):
+    """Switch a customer-sharded sampler from the NCCL all-reduce to the peer-mailbox all-reduce fused into the
+    level-2 kernel: all-gather the CUDA IPC handles of the mailboxes and connect every rank to every other."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    handles = [None] * world
+    dist.all_gather_object(handles, sampler.p2p_export(), group=group)
+    sampler.p2p_connect(handles, rank, world)
+    dist.barrier(group)

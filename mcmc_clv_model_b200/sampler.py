@@ -130,6 +130,16 @@ class Sampler:
         buf = C.create_string_buffer(unique_id, 128)
         L.check(self.lib.clv_comm_init(self.h, buf, int(rank), int(world)), self.h)
 
+    def p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        L.check(self.lib.clv_p2p_export(self.h, buf), self.h)
+        return buf.raw
+
+    def p2p_connect(self, handles, rank: int, world: int):
+        """handles: list of the `world` 64-byte mailbox handles (p2p_export of every rank, all-gathered)."""
+        blob = C.create_string_buffer(b"".join(handles), 64 * world)
+        L.check(self.lib.clv_p2p_connect(self.h, blob, int(rank), int(world)), self.h)
+
     # ---- sweeps ------------------------------------------------------------------------------
     def run(self, burnin, mcmc, thin, store_level1=True, trace=0, progress=None, pinned=False):
         """burnin + mcmc sweeps; returns dict(level_1 [chains] of (n_draws,N,ncol) | None,

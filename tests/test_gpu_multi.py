@@ -19,11 +19,12 @@ def _ngpu():
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("D", [2, 3])
-def test_two_gpu_sharded_run_is_bit_identical(D):
+@pytest.mark.parametrize("D,p2p", [(2, "0"), (3, "0"), (2, "1"), (3, "1")])
+def test_two_gpu_sharded_run_is_bit_identical(D, p2p):
+    """p2p=1: the all-reduce runs inside k_level2 over peer mailboxes (NVLink P2P stores) instead of NCCL."""
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "sharded_check.py"),
-                        "150001", str(D)], capture_output=True, text=True, timeout=600)
+                        "150001", str(D)], capture_output=True, text=True, timeout=600, env=dict(os.environ, CLV_P2P=p2p))
     assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 

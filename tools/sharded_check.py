@@ -19,8 +19,12 @@ lo, hi = shard_bounds(N, world)[rank]
 c = generate_cbs_arrays(hi - lo, C4_BETA, C4_GAMMA, T_cal=C4_T_CAL, seed=C4_SEED, gid_offset=lo, device=local, with_truth=False)
 log_s = (0.5 * c["X"][:, 1] + 3.0 + 0.1 * np.cos(np.arange(lo, hi))) if D == 3 else None
 comm = (broadcast_unique_id(Sampler.comm_unique_id), rank, world)
+P2P = os.environ.get("CLV_P2P") == "1"
 with Sampler(c["x"], c["t_x"], c["T_cal"], c["X"], log_s, model_dim=D, chains=2, seed=9, device=local, n_global=N, gid_offset=lo,
              comm=comm) as s:
+    if P2P:
+        from mcmc_clv_model_b200.distributed import connect_p2p
+        connect_p2p(s)
     out = s.run(5, 6, 2)
     stats = s.init_stats
 l1 = gather_level1(np.ascontiguousarray(np.moveaxis(out["level_1"], 0, 1).reshape(out["level_1"].shape[1], -1, 1)))  # noqa
@@ -38,6 +42,6 @@ if rank == 0:
     assert np.array_equal(out["level_2"], ref["level_2"]), np.abs(out["level_2"] - ref["level_2"]).max()
     assert np.array_equal(out["level_1"], ref["level_1"][:, :, lo:hi, :])
     assert np.array_equal(ll.cpu().numpy(), ref["loglik_sum"])
-    print(f"SHARDED_OK world={world} N={N} D={D}: level_2, level_1, loglik and init statistics bit-identical to the 1-GPU run")
+    print(f"SHARDED_OK world={world} N={N} D={D} p2p={P2P}: level_2, level_1, loglik and init statistics bit-identical to the 1-GPU run")
 dist.barrier()
 dist.destroy_process_group()
