@@ -14,4 +14,4 @@ with Sampler(fc["x"], fc["t_x"], fc["T_cal"], fc["X"], chains=1, seed=7) as s:
     s.run_resident(20, nd, 1)
     best = min(s.forecast_resident(T_star=39.0, seed=42)["kernel_ms"] for _ in range(reps))
 cells = n * nd
-print(f"forecast n={n} draws={nd}: {best:.3f} ms  {cells/(best*1e-3):.4g} cells/s  {cells*32/(best*1e-3)/1e9:.0f} GB/s")
+print(os.path.basename(os.environ.get("CLV_B200_LIB","default")), end=" "); print(f"forecast n={n} draws={nd}: {best:.3f} ms  {cells/(best*1e-3):.4g} cells/s  {cells*32/(best*1e-3)/1e9:.0f} GB/s")
