@@ -89,6 +89,7 @@ struct clv_sampler {
   // persistent mode
   unsigned long long* d_acc3 = nullptr;
   unsigned int* d_barrier = nullptr;
+  size_t stats_smem = 0;           // dynamic shared memory of the sweep kernels: (nstat + 1) int64 columns x 128 threads
   int persist_grid_x = 0;          // 0: cooperative launch not possible for this problem
   bool persist_fits = false;       // every tile has its own co-resident block (small problems: AUTO picks persistent)
   // bookkeeping
@@ -233,9 +234,10 @@ cudaEvent_t pool_event(clv_sampler* h) {
 template <int D>
 void launch_sweep_kernel(clv_sampler* h, const SweepArgs& a, int mode) {
   dim3 grid(h->grid_x, h->chains), block(SWEEP_THREADS);
-  if (mode == MODE_FAST) k_sweep<D, MODE_FAST><<<grid, block, 0, h->stream>>>(a);
-  else if (mode == MODE_STRICT) k_sweep<D, MODE_STRICT><<<grid, block, 0, h->stream>>>(a);
-  else k_sweep<D, MODE_INJECT><<<grid, block, 0, h->stream>>>(a);
+  const size_t sm = h->stats_smem;
+  if (mode == MODE_FAST) k_sweep<D, MODE_FAST><<<grid, block, sm, h->stream>>>(a);
+  else if (mode == MODE_STRICT) k_sweep<D, MODE_STRICT><<<grid, block, sm, h->stream>>>(a);
+  else k_sweep<D, MODE_INJECT><<<grid, block, sm, h->stream>>>(a);
 }
 
 int allreduce_acc(clv_sampler* h) {
@@ -313,7 +315,7 @@ int recompute_stats(clv_sampler* h) {
   if (h->D == 2) {   // bivariate: the next sweep starts with a level-2 draw from the current state (bi:393)
     SweepArgs a = base_args(h);
     dim3 grid(h->grid_x, h->chains);
-    k_stats_only<2><<<grid, SWEEP_THREADS, 0, h->stream>>>(a);
+    k_stats_only<2><<<grid, SWEEP_THREADS, h->stats_smem, h->stream>>>(a);
     h->launches++;
     CK(h, cudaGetLastError());
   }
@@ -393,6 +395,21 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   long long ntiles = (h->N + SWEEP_THREADS - 1) / SWEEP_THREADS;
   long long want = ((long long)h->sm_count * 32 + h->chains - 1) / h->chains;
   h->grid_x = (int)std::max<long long>(1, std::min(ntiles, want));
+  h->stats_smem = (size_t)(h->K * h->D + h->D * (h->D + 1) / 2 + 1) * SWEEP_THREADS * sizeof(long long);
+  if (h->stats_smem > 48 * 1024) {
+    const int bytes = (int)h->stats_smem;
+    cudaFuncSetAttribute(k_sweep<2, MODE_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_sweep<2, MODE_STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_sweep<2, MODE_INJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_sweep<3, MODE_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_sweep<3, MODE_STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_sweep<3, MODE_INJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_stats_only<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_persistent<2, MODE_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_persistent<2, MODE_STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_persistent<3, MODE_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_persistent<3, MODE_STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  }
   // persistent cooperative mode: all blocks must be co-resident
   CKC(dmalloc(&h->d_acc3, 3 * C * NSTAT_MAX));
   CKC(dmalloc(&h->d_barrier, 2));
@@ -401,8 +418,8 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
     int coop = 0, per_sm = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
     cudaError_t eo = (h->D == 2)
-        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<2, MODE_FAST>, SWEEP_THREADS, 0)
-        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<3, MODE_FAST>, SWEEP_THREADS, 0);
+        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<2, MODE_FAST>, SWEEP_THREADS, h->stats_smem)
+        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<3, MODE_FAST>, SWEEP_THREADS, h->stats_smem);
     long long maxb = (eo == cudaSuccess && coop) ? (long long)per_sm * h->sm_count : 0;
     if (maxb >= h->chains) {
       h->persist_grid_x = (int)std::min<long long>(ntiles, maxb / h->chains);
@@ -801,7 +818,7 @@ int launch_persistent(clv_sampler* h, const RunCtx& rc, long long n, bool store_
   const bool strict = h->cfg.rng_mode == CLV_RNG_PHILOX_STRICT;
   if (h->D == 2) fn = strict ? (const void*)k_persistent<2, MODE_STRICT> : (const void*)k_persistent<2, MODE_FAST>;
   else fn = strict ? (const void*)k_persistent<3, MODE_STRICT> : (const void*)k_persistent<3, MODE_FAST>;
-  CK(h, cudaLaunchCooperativeKernel(fn, grid, block, args, 0, h->stream));
+  CK(h, cudaLaunchCooperativeKernel(fn, grid, block, args, h->stats_smem, h->stream));
   h->launches++;
   if (h->D == 2)
     CK(h, cudaMemcpyAsync(h->d_acc, h->d_acc3 + (size_t)(last % 3u) * h->chains * NSTAT_MAX, slot_bytes,

@@ -106,10 +106,10 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
   return (long long)slo + ((long long)smid << 26) + (long long)((unsigned long long)(long long)shi << 52);
 }
 
-// exp(x) for |x| <= 70 (the clip range of bi:323-324), ~1 ulp, branch-free:
+// exp(x) for |x| <= 700 (in particular the clip range +-70 of bi:323-324), ~1 ulp, branch-free:
 //   n = rint(x 64/ln2), r = x - n ln2/64 (|r| <= 0.0055), exp(x) = 2^(n>>6) * 2^((n&63)/64) * (1 + r + ... + r^5/120)
 // 2^(j/64) comes from a 64-entry shared-memory table; the degree-5 remainder is < 4e-17.
-__device__ __forceinline__ double exp_clip70(double x, const double* __restrict__ tab) {
+__device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
   const double t = fma(x, 92.332482616893656877, 6755399441055744.0);   // 64/ln2 ; 1.5 * 2^52 rounds to nearest
   const int n = __double2loint(t);
   const double nd = t - 6755399441055744.0;
@@ -126,11 +126,17 @@ __device__ __forceinline__ double exp_clip70(double x, const double* __restrict_
   return __hiloint2double(hi, __double2loint(v));
 }
 
+// exp for any argument: the table path where it is valid (results stay normal numbers), libm beyond
+__device__ __noinline__ double exp_slow(double x) { return exp(x); }
+__device__ __forceinline__ double exp_any(double x, const double* __restrict__ tab) {
+  return (fabs(x) <= 700.0) ? exp_tab(x, tab) : exp_slow(x);
+}
+
 // Level-1 target, bi:291-310.  Tz = z*T_cal + (1-z)*tau, omz = 1-z.  ll, lm in [-70, 70].
 __device__ __forceinline__ double log_post(double ll, double lm, double xd, double omz, double Tz, double m0,
                                            double m1, double P00, double P01, double P11, const double* tab) {
   double dl = ll - m0, dm = lm - m1;
-  double lik = xd * ll + omz * lm - (exp_clip70(ll, tab) + exp_clip70(lm, tab)) * Tz;
+  double lik = xd * ll + omz * lm - (exp_tab(ll, tab) + exp_tab(lm, tab)) * Tz;
   double prior = -0.5 * (dl * dl * P00 + 2.0 * dl * dm * P01 + dm * dm * P11);
   double res = lik + prior;
   return (lm > 5.0) ? -CUDART_INF : res;
@@ -161,31 +167,48 @@ __device__ __forceinline__ double clip70(double v) {
   return v;
 }
 
+// Level-2 sufficient statistics.  Every thread owns one column of the dynamic shared array s_priv[(stat)][128]
+// (int64 fixed point) and adds its customers' terms there, tile after tile; flush_stats() reduces the columns once per
+// block and sweep.  All sums are integers => the result does not depend on any of this.
 template <int D>
 __device__ __forceinline__ void accumulate_stats(const ModelConst& mc, const double* __restrict__ Xc, long long N,
                                                  long long i, bool valid, double yc0, double yc1, double yc2,
-                                                 unsigned long long* s_acc, int lane) {
+                                                 long long* s_priv) {
+  if (!valid) return;
   const double sc = mc.fx_scale;
   const int K = mc.K;
-  double y[3] = {yc0, yc1, yc2};
+  const double y[3] = {yc0, yc1, yc2};
+  long long* col = s_priv + threadIdx.x;
   for (int k = 0; k < K; ++k) {
-    double xk = 0.0;
-    if (valid) xk = (k == 0) ? 1.0 : Xc[(long long)(k - 1) * N + i];
+    const double xk = (k == 0) ? 1.0 : Xc[(long long)(k - 1) * N + i];
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      long long v = warp_sum_ll(valid ? to_fx(xk * y[d], sc) : 0ll);
-      if (lane == 0) atomicAdd(&s_acc[k * D + d], (unsigned long long)v);
-    }
+    for (int d = 0; d < D; ++d) col[(k * D + d) * SWEEP_THREADS] += to_fx(xk * y[d], sc);
   }
   int t = K * D;
 #pragma unroll
   for (int d = 0; d < D; ++d)
 #pragma unroll
     for (int e = d; e < D; ++e) {
-      long long v = warp_sum_ll(valid ? to_fx(y[d] * y[e], sc) : 0ll);
-      if (lane == 0) atomicAdd(&s_acc[t], (unsigned long long)v);
+      col[t * SWEEP_THREADS] += to_fx(y[d] * y[e], sc);
       ++t;
     }
+}
+
+// columns 0..nstat-1: statistics, column nstat: log-likelihood sum of a kept draw.  Adds the block totals to s_acc
+// (slot NSTAT_MAX for the log-likelihood) and clears the columns.
+__device__ __forceinline__ void flush_stats(long long* s_priv, unsigned long long* s_acc, int nstat, bool with_loglik) {
+  const int lane = threadIdx.x & 31;
+  long long* col = s_priv + threadIdx.x;
+  const int ncol = nstat + (with_loglik ? 1 : 0);
+  for (int t = 0; t < ncol; ++t) {
+    const long long v = warp_sum_ll(col[t * SWEEP_THREADS]);
+    col[t * SWEEP_THREADS] = 0;
+    if (lane == 0 && v) atomicAdd(&s_acc[t == nstat ? NSTAT_MAX : t], (unsigned long long)v);
+  }
+}
+
+__device__ __forceinline__ void clear_stats(long long* s_priv, int nstat) {
+  for (int t = 0; t <= nstat; ++t) s_priv[t * SWEEP_THREADS + threadIdx.x] = 0;
 }
 
 // Per-sweep scalars (kernel arguments in stream mode, computed on the device in persistent mode).
@@ -202,9 +225,9 @@ struct SweepStep {
 // the level-2 statistics.  cp / s_beta / s_tab / s_acc live in shared memory.
 template <int D, int MODE>
 __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst& mc, const ChainParams& cp,
-                                           const double* s_beta, const double* s_tab, unsigned long long* s_acc,
+                                           const double* s_beta, const double* s_tab, long long* s_priv,
                                            const SweepStep& sw, int chain, long long tile, PhiloxKey key) {
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int K = mc.K, S = mc.S;
   const long long N = mc.N;
   const long long cN = (long long)chain * N;
@@ -228,7 +251,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
       if (D == 3) m2 = fma(xk, s_beta[k * D + 2], m2);
     }
     // ---- z (bi:193-200) and tau (bi:203-227) from the current lambda, mu -------------------------
-    const double lam = exp_clip70(ll, s_tab), mu = exp_clip70(lm, s_tab);   // |ll|, |lm| <= 70 by construction
+    const double lam = exp_tab(ll, s_tab), mu = exp_tab(lm, s_tab);   // |ll|, |lm| <= 70 by construction
     double uz, ut, et;
     if (MODE == MODE_INJECT) {
       uz = a.u_z[cN + i];
@@ -241,16 +264,24 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
       et = 0.0;
     }
     const double ml = mu + lam;
-    const double e = exp(-(ml * (T - tx)));
+    const double e = exp_any(-(ml * (T - tx)), s_tab);
     const double pa = (ml * e) / (ml * e + mu * (1.0 - e));
     const bool alive = uz < pa;
     double tau;
-    if (alive) {
-      if (MODE != MODE_INJECT) et = -log(ut);
-      tau = T + (1.0 / mu) * et;
+    if (MODE == MODE_INJECT) {
+      if (alive) {
+        tau = T + (1.0 / mu) * et;
+      } else {
+        double mtx = fmin(700.0, ml * tx), mT = fmin(700.0, ml * T);
+        tau = -log((1.0 - ut) * exp(-mtx) + ut * exp(-mT)) / ml;
+      }
     } else {
-      double mtx = fmin(700.0, ml * tx), mT = fmin(700.0, ml * T);
-      tau = -log((1.0 - ut) * exp(-mtx) + ut * exp(-mT)) / ml;
+      // both cases share one logarithm and one division (no divergent branches): alive -> T - ln(u)/mu (an Exp(mu)
+      // beyond T_cal, bi:217); churned -> -ln((1-u) e^{-ml t_x} + u e^{-ml T}) / ml (bi:223-226)
+      const double mtx = fmin(700.0, ml * tx), mT = fmin(700.0, ml * T);
+      const double mix = (1.0 - ut) * exp_tab(-mtx, s_tab) + ut * exp_tab(-mT, s_tab);
+      const double lg = -log(alive ? ut : mix);
+      tau = (alive ? T : 0.0) + lg / (alive ? mu : ml);
     }
     const double zf = alive ? 1.0 : 0.0;
     const double omz = 1.0 - zf;
@@ -312,7 +343,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
     }
     // ---- kept draw: lambda, mu, tau, z(, eta)   bi:407-410, tri:544-548 -------------------------
     if (keep) {
-      const double lam_n = exp_clip70(ll, s_tab), mu_n = exp_clip70(lm, s_tab);
+      const double lam_n = exp_tab(ll, s_tab), mu_n = exp_tab(lm, s_tab);
       constexpr int NC = (D == 2) ? 4 : 5;
       if (sw.draws) {           // level-1 storage is optional (clv_run with level1 == NULL)
         double* o = sw.draws + (((long long)chain * sw.chunk_cap + sw.slot) * N + i) * NC;
@@ -330,15 +361,13 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
     yc1 = lm - mc.center[1];
     if (D == 3) yc2 = le - mc.center[2];
   }
-  accumulate_stats<D>(mc, a.Xc, N, i, valid, yc0, yc1, yc2, s_acc, lane);
-  if (keep) {
-    long long v = warp_sum_ll(valid ? to_fx(lik, mc.ll_scale) : 0ll);
-    if (lane == 0) atomicAdd(&s_acc[NSTAT_MAX], (unsigned long long)v);
-  }
+  accumulate_stats<D>(mc, a.Xc, N, i, valid, yc0, yc1, yc2, s_priv);
+  if (keep && valid) s_priv[(K * D + D * (D + 1) / 2) * SWEEP_THREADS + tid] += to_fx(lik, mc.ll_scale);
 }
 
 template <int D, int MODE>
 __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArgs a) {
+  extern __shared__ long long s_priv[];          // [(nstat + 1)][SWEEP_THREADS]
   __shared__ double s_beta[MAXK * MAXD];
   __shared__ double s_tab[64];
   __shared__ unsigned long long s_acc[NSTAT_MAX + 1];
@@ -346,10 +375,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArg
   const int chain = blockIdx.y;
   const int tid = threadIdx.x;
   const int K = mc.K;
+  const int nstat = K * D + D * (D + 1) / 2;
   const ChainParams& cp = a.params[chain];
   for (int t = tid; t < K * D; t += SWEEP_THREADS) s_beta[t] = cp.beta[t];
   if (tid < 64) s_tab[tid] = c_exptab[tid];
   for (int t = tid; t < NSTAT_MAX + 1; t += SWEEP_THREADS) s_acc[t] = 0ull;
+  clear_stats(s_priv, nstat);
   __syncthreads();
   const PhiloxKey key = chain_key(a.seed, a.chain_offset + (uint32_t)chain);
   SweepStep sw;
@@ -357,9 +388,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArg
   sw.draws = a.draws;
   const long long ntiles = (mc.N + SWEEP_THREADS - 1) / SWEEP_THREADS;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-    sweep_tile<D, MODE>(a, mc, cp, s_beta, s_tab, s_acc, sw, chain, tile, key);
+    sweep_tile<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, key);
+  flush_stats(s_priv, s_acc, nstat, sw.keep != 0);
   __syncthreads();
-  const int nstat = K * D + D * (D + 1) / 2;
   for (int t = tid; t < nstat; t += SWEEP_THREADS)
     if (s_acc[t]) atomicAdd(&a.acc[chain * NSTAT_MAX + t], s_acc[t]);
   if (sw.keep && tid == 0)
@@ -370,11 +401,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArg
 // Statistics of the current state only (first level-2 draw of the bivariate order, bi:393).
 template <int D>
 __global__ void __launch_bounds__(SWEEP_THREADS) k_stats_only(SweepArgs a) {
+  extern __shared__ long long s_priv[];
   __shared__ unsigned long long s_acc[NSTAT_MAX + 1];
   const ModelConst& mc = *a.mc;
-  const int chain = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int chain = blockIdx.y, tid = threadIdx.x;
   const long long N = mc.N, cN = (long long)chain * N;
+  const int nstat = mc.K * D + D * (D + 1) / 2;
   for (int t = tid; t < NSTAT_MAX + 1; t += SWEEP_THREADS) s_acc[t] = 0ull;
+  clear_stats(s_priv, nstat);
   __syncthreads();
   const long long ntiles = (N + SWEEP_THREADS - 1) / SWEEP_THREADS;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -386,10 +420,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_stats_only(SweepArgs a) {
       yc1 = a.lm[cN + i] - mc.center[1];
       if (D == 3) yc2 = a.le[cN + i] - mc.center[2];
     }
-    accumulate_stats<D>(mc, a.Xc, N, i, valid, yc0, yc1, yc2, s_acc, lane);
+    accumulate_stats<D>(mc, a.Xc, N, i, valid, yc0, yc1, yc2, s_priv);
   }
+  flush_stats(s_priv, s_acc, nstat, false);
   __syncthreads();
-  const int nstat = mc.K * D + D * (D + 1) / 2;
   for (int t = tid; t < nstat; t += SWEEP_THREADS)
     if (s_acc[t]) atomicAdd(&a.acc[chain * NSTAT_MAX + t], s_acc[t]);
 }
@@ -780,6 +814,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nbl
 // barrier after its last reader and one before its next writer.
 template <int D, int MODE>
 __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(PersistArgs pa) {
+  extern __shared__ long long s_priv[];
   __shared__ double s_beta[MAXK * MAXD];
   __shared__ double s_tab[64];
   __shared__ unsigned long long s_acc[NSTAT_MAX + 1];
@@ -795,6 +830,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(Per
   const PhiloxKey key = chain_key(a.seed, a.chain_offset + (uint32_t)chain);
   const long long csz = (long long)gridDim.y * NSTAT_MAX;
   if (tid < 64) s_tab[tid] = c_exptab[tid];
+  clear_stats(s_priv, nstat);
   {
     const double* src = reinterpret_cast<const double*>(&pa.params[chain]);
     double* dst = reinterpret_cast<double*>(&s_cp);
@@ -837,7 +873,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(Per
     sw.sweep = sweep; sw.keep = kept; sw.store_zt = (pa.store_zt_last && it + 1 == pa.n_sweeps);
     sw.slot = kept ? draw - pa.chunk_base : 0; sw.chunk_cap = a.chunk_cap; sw.draws = a.draws;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-      sweep_tile<D, MODE>(a, mc, s_cp, s_beta, s_tab, s_acc, sw, chain, tile, key);
+      sweep_tile<D, MODE>(a, mc, s_cp, s_beta, s_tab, s_priv, sw, chain, tile, key);
+    flush_stats(s_priv, s_acc, nstat, kept);
     __syncthreads();
     for (int t = tid; t < nstat; t += SWEEP_THREADS)
       if (s_acc[t]) atomicAdd(&slot_cur[chain * NSTAT_MAX + t], s_acc[t]);
