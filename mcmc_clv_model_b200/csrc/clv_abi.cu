@@ -218,6 +218,7 @@ SweepArgs base_args(clv_sampler* h) {
   a.loglik_stride = 1;
   a.draws = nullptr; a.chunk_cap = 1; a.slot = -1; a.draw_index = 0;
   a.sweep = 0; a.chain_offset = (uint32_t)h->cfg.chain_offset; a.seed = h->cfg.seed;
+  a.rk = round_keys(h->cfg.seed);
   a.store_zt = 0;
   return a;
 }

@@ -133,7 +133,7 @@ __device__ __forceinline__ long long forecast_cell(double lam, double tau, doubl
 // One thread per (customer, pair of draws): x* (and spend) for every cell.
 template <int NCOL, bool INJECT>
 __global__ void __launch_bounds__(256) k_forecast(ForecastArgs a) {
-  const PhiloxKey key = chain_key(a.seed, 0u);
+  const PhiloxKey key = seed_key(a.seed);
   const bool spend = (NCOL == 5) && a.spend_out != nullptr;
   const float T_star_f = (float)a.T_star;
   const long long gp0 = a.draw_offset >> 1, gp1 = (a.draw_offset + a.n_draws - 1) >> 1;   // global pair range
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) k_forecast(ForecastArgs a) {
 // spills): the kernel is latency bound and occupancy beats register comfort (2.8 -> 3.45 TB/s measured).
 template <int NCOL>
 __global__ void __launch_bounds__(256, 6) k_forecast_reduce(ForecastArgs a, double* sum_x, double* sum_z) {
-  const PhiloxKey key = chain_key(a.seed, 0u);
+  const PhiloxKey key = seed_key(a.seed);
   const float T_star_f = (float)a.T_star;
   const long long npairs = (a.n_draws + 1) >> 1;
   const long long per = (npairs + gridDim.y - 1) / gridDim.y;
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(256) k_weekly_tracking(const double* level1, l
                                                          const double* birth, const double* times, int n_weeks, uint64_t seed,
                                                          unsigned long long* totals) {
   extern __shared__ unsigned long long s_week[];
-  const PhiloxKey key = chain_key(seed, 0u);
+  const PhiloxKey key = seed_key(seed);
   for (int w = threadIdx.x; w < n_weeks; w += blockDim.x) s_week[w] = 0ull;
   __syncthreads();
   for (long long d = blockIdx.y; d < n_tot; d += gridDim.y)
@@ -380,7 +380,7 @@ struct GenerateArgs {
 };
 
 __global__ void __launch_bounds__(256) k_generate(GenerateArgs a) {
-  const PhiloxKey key = chain_key(a.seed, 0u);
+  const PhiloxKey key = seed_key(a.seed);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
        i += (long long)gridDim.x * blockDim.x) {
     const uint32_t gid = (uint32_t)(a.gid_offset + i);

@@ -82,6 +82,7 @@ struct SweepArgs {
   uint32_t sweep;              // 1-based sweep number (Philox counter)
   uint32_t chain_offset;
   uint64_t seed;
+  PhiloxRoundKeys rk;          // round keys of `seed` (launch constants)
   int store_zt;                // write z/tau state arrays
   // injected variates (MODE_INJECT)
   const double *u_z, *e_tau, *u_tau, *t3_l, *t3_m, *u_acc, *n_eta;
@@ -145,26 +146,30 @@ __device__ __forceinline__ double log_post(double ll, double lm, double xd, doub
 // MH accept rule of bi:329-330: exp(prop - cur) > u, NaN compares false.  An fp32 SFU screen in log space
 // (uf = fp32 image of u) settles all but ~1e-5 of the decisions; the tie zone is re-decided with the exact fp64
 // expression, so the outcome always equals `exp(d) > u`.
-template <typename ExactU>
+template <bool GUARD_U, typename ExactU>
 __device__ __forceinline__ bool mh_accept(double d, float uf, ExactU exact_u) {
-  if (d >= 0.0) return true;       // exp(d) >= 1 > u
+  // one rarely taken branch: accept / reject are decided branch-free unless d - ln u falls in the guard band
+  // (d >= 0 gives df >= 0 > ln u; d = -inf or d < -80 gives df < ln u - tol since ln u >= -23; NaN fails both tests)
   const float df = (float)d;
-  if (uf > 1e-30f) {
-    if (df < -80.0f) return false; // exp(d) < 2e-35 < u (also d = -inf: the lm > 5 cap of bi:309)
-    const float lu = 0.69314718055994531f * lg2_ftz(uf);
-    const float tol = 1e-5f * (1.0f + fabsf(lu));
-    if (df > lu + tol) return true;
-    if (df < lu - tol) return false;
-  }
-  return exp(d) > exact_u();       // NaN -> false; d = -inf -> 0 > u false
+  const float lu = 0.69314718055994531f * lg2_ftz(uf);
+  const float tol = 1e-5f * (1.0f + fabsf(lu));
+  bool acc = df > lu + tol;
+  const bool rej = df < lu - tol;
+  bool sure = acc || rej;
+  if (GUARD_U) sure = sure && uf > 1e-30f;       // injected uniforms may be 0 or denormal
+  if (!sure) acc = (d >= 0.0) || exp(d) > exact_u();
+  return acc;
 }
 
-// np.clip(v, -70, 70) of bi:323-324; the comparison runs on the high word so the common case costs two integer ops
-__device__ __noinline__ double clip70_slow(double v) { return fmin(fmax(v, -70.0), 70.0); }
-__device__ __forceinline__ double clip70(double v) {
-  // a real (never if-converted) branch: |v| >= 70 is a once-in-a-run event
-  if (((unsigned)__double2hiint(v) & 0x7fffffffu) >= 0x40518000u) v = clip70_slow(v);
-  return v;
+// np.clip(v, -70, 70) of bi:323-324 for both proposals; the test runs on the high words so the common case costs a few
+// integer ops and one never-taken branch (|v| >= 70 is a once-in-a-run event)
+__device__ __noinline__ void clip70_slow(double& a, double& b) {
+  a = fmin(fmax(a, -70.0), 70.0);
+  b = fmin(fmax(b, -70.0), 70.0);
+}
+__device__ __forceinline__ void clip70_pair(double& a, double& b) {
+  const unsigned ha = (unsigned)__double2hiint(a) & 0x7fffffffu, hb = (unsigned)__double2hiint(b) & 0x7fffffffu;
+  if (max(ha, hb) >= 0x40518000u) clip70_slow(a, b);
 }
 
 // Level-2 sufficient statistics.  Every thread owns one column of the dynamic shared array s_priv[(stat)][128]
@@ -226,7 +231,7 @@ struct SweepStep {
 template <int D, int MODE>
 __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst& mc, const ChainParams& cp,
                                            const double* s_beta, const double* s_tab, long long* s_priv,
-                                           const SweepStep& sw, int chain, long long tile, PhiloxKey key) {
+                                           const SweepStep& sw, int chain, long long tile, uint32_t c3) {
   const int tid = threadIdx.x;
   const int K = mc.K, S = mc.S;
   const long long N = mc.N;
@@ -258,7 +263,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
       ut = a.u_tau[cN + i];
       et = a.e_tau[cN + i];
     } else {
-      uint4 r = philox4x32_10(gid, sw.sweep, 0u, DOM_SAMPLER, key);
+      uint4 r = philox4x32_10_rk(gid, sw.sweep, 0u, c3, a.rk);
       uz = u53(r.x, r.y);
       ut = u53(r.z, r.w);
       et = 0.0;
@@ -299,8 +304,8 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
         ua = a.u_acc[o];
         uaf = (float)ua;
       } else {
-        uint4 ra = philox4x32_10(gid, sw.sweep, 1u + 2u * s, DOM_SAMPLER, key);
-        uint4 rb = philox4x32_10(gid, sw.sweep, 2u + 2u * s, DOM_SAMPLER, key);
+        uint4 ra = philox4x32_10_rk(gid, sw.sweep, 1u + 2u * s, c3, a.rk);
+        uint4 rb = philox4x32_10_rk(gid, sw.sweep, 2u + 2u * s, c3, a.rk);
         if (MODE == MODE_STRICT) {
           tl = t3_strict(ra.x, ra.y, ra.z);
           tm = t3_strict(ra.w, rb.x, rb.y);
@@ -311,10 +316,10 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
         ur = rb.z;
         uaf = u32f(ur);
       }
-      const double pl = clip70(ll + s_l * tl);                 // bi:318-324
-      const double pm = clip70(lm + s_m * tm);
+      double pl = ll + s_l * tl, pm = lm + s_m * tm;           // bi:318-324
+      clip70_pair(pl, pm);
       const double prop = log_post(pl, pm, xd, omz, Tz, m0, m1, P00, P01, P11, s_tab);
-      if (mh_accept(prop - cur, uaf, [&]() { return MODE == MODE_INJECT ? ua : u32d(ur); })) {
+      if (mh_accept<MODE == MODE_INJECT>(prop - cur, uaf, [&]() { return MODE == MODE_INJECT ? ua : u32d(ur); })) {
         ll = pl;
         lm = pm;
         cur = prop;
@@ -330,7 +335,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
         n = a.n_eta[cN + i];
       } else {
         double ns;
-        normal_pair_u53(philox4x32_10(gid, sw.sweep, 1u + 2u * (uint32_t)S, DOM_SAMPLER, key), &n, &ns);
+        normal_pair_u53(philox4x32_10_rk(gid, sw.sweep, 1u + 2u * (uint32_t)S, c3, a.rk), &n, &ns);
       }
       const double prior_var = cp.Sigma[8];
       double post_mean = cp.eta_post_var * (a.log_s[i] / mc.omega2 + m2 / prior_var);
@@ -382,13 +387,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArg
   for (int t = tid; t < NSTAT_MAX + 1; t += SWEEP_THREADS) s_acc[t] = 0ull;
   clear_stats(s_priv, nstat);
   __syncthreads();
-  const PhiloxKey key = chain_key(a.seed, a.chain_offset + (uint32_t)chain);
+  const uint32_t c3 = dom_word(DOM_SAMPLER, a.chain_offset + (uint32_t)chain);
   SweepStep sw;
   sw.sweep = a.sweep; sw.keep = a.slot >= 0; sw.store_zt = a.store_zt; sw.slot = a.slot; sw.chunk_cap = a.chunk_cap;
   sw.draws = a.draws;
   const long long ntiles = (mc.N + SWEEP_THREADS - 1) / SWEEP_THREADS;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-    sweep_tile<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, key);
+    sweep_tile<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, c3);
   flush_stats(s_priv, s_acc, nstat, sw.keep != 0);
   __syncthreads();
   for (int t = tid; t < nstat; t += SWEEP_THREADS)
@@ -607,20 +612,20 @@ struct Level2Scratch {
 // sc.st must be filled (and visible to the warp) on entry; cp (shared or global memory) receives beta, Sigma, P.
 template <int D>
 __device__ __forceinline__ void level2_draw(const ModelConst& mc, Level2Scratch& sc, ChainParams& cp, PhiloxKey key,
-                                            uint32_t sweep, int injected, const double* iw_norm, const double* iw_chi2,
+                                            uint32_t c3, uint32_t sweep, int injected, const double* iw_norm, const double* iw_chi2,
                                             const double* beta_norm, int lane) {
   const int K = mc.K;
   constexpr int ntril = D * (D - 1) / 2;
   const int nb = D * K;
   // variates (fp64 Philox transforms are long dependent chains: one per lane)
   for (int t = lane; t < ntril + D + nb; t += 32) {
-    if (t < ntril) sc.trn[t] = injected ? iw_norm[t] : level2_normal(key, sweep, (uint32_t)t);
+    if (t < ntril) sc.trn[t] = injected ? iw_norm[t] : level2_normal(key, c3, sweep, (uint32_t)t);
     else if (t < ntril + D) {
       const int i = t - ntril;
-      sc.chi[i] = injected ? iw_chi2[i] : level2_chi2(key, sweep, 16u + i, mc.nu_n - D + 1 + i);   // chi2(nu_n - D + 1 + i)
+      sc.chi[i] = injected ? iw_chi2[i] : level2_chi2(key, c3, sweep, 16u + i, mc.nu_n - D + 1 + i);   // chi2(nu_n - D + 1 + i)
     } else {
       const int j = t - ntril - D;
-      sc.zb[j] = injected ? beta_norm[j] : level2_normal(key, sweep, 32u + (uint32_t)j);
+      sc.zb[j] = injected ? beta_norm[j] : level2_normal(key, c3, sweep, 32u + (uint32_t)j);
     }
   }
   // R = X'Yc + A0 B0c                                           bi:250
@@ -762,9 +767,9 @@ __global__ void __launch_bounds__(32) k_level2(Level2Args a) {
   }
   __syncwarp();
   ChainParams& cp = a.params[chain];
-  const PhiloxKey key = chain_key(a.seed, a.chain_offset + (uint32_t)chain);
+  const PhiloxKey key = seed_key(a.seed);
   constexpr int ntril = D * (D - 1) / 2;
-  level2_draw<D>(mc, sc, cp, key, a.sweep, a.injected, a.injected ? a.iw_norm + chain * ntril : nullptr,
+  level2_draw<D>(mc, sc, cp, key, dom_word(DOM_LEVEL2, a.chain_offset + (uint32_t)chain), a.sweep, a.injected, a.injected ? a.iw_norm + chain * ntril : nullptr,
                  a.injected ? a.iw_chi2 + chain * D : nullptr, a.injected ? a.beta_norm + chain * D * K : nullptr, lane);
   if (lane == 0 && !sc.ok) *a.error_flag = 1;
   if (a.draw_index >= 0)
@@ -827,7 +832,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(Per
   const int nstat = K * D + D * (D + 1) / 2;
   const unsigned int nblocks = gridDim.x * gridDim.y;
   const long long ntiles = (mc.N + SWEEP_THREADS - 1) / SWEEP_THREADS;
-  const PhiloxKey key = chain_key(a.seed, a.chain_offset + (uint32_t)chain);
+  const PhiloxKey key = seed_key(a.seed);
+  const uint32_t c3 = dom_word(DOM_SAMPLER, a.chain_offset + (uint32_t)chain);
+  const uint32_t c3_l2 = dom_word(DOM_LEVEL2, a.chain_offset + (uint32_t)chain);
   const long long csz = (long long)gridDim.y * NSTAT_MAX;
   if (tid < 64) s_tab[tid] = c_exptab[tid];
   clear_stats(s_priv, nstat);
@@ -844,7 +851,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(Per
       for (int t = lane; t < nstat; t += 32)
         sc.st[t] = (double)(long long)__ldcg(&slot_read[chain * NSTAT_MAX + t]) * mc.fx_inv;
       __syncwarp();
-      level2_draw<D>(mc, sc, s_cp, key, sweep, 0, nullptr, nullptr, nullptr, lane);
+      level2_draw<D>(mc, sc, s_cp, key, c3_l2, sweep, 0, nullptr, nullptr, nullptr, lane);
       if (lane == 0 && !sc.ok) *pa.error_flag = 1;
       if (blockIdx.x == 0 && draw_index >= 0)
         write_level2_row<D>(mc, s_cp, pa.level2_draws + ((long long)chain * pa.n_draws + draw_index) * (D * K + D * (D + 1) / 2), lane);
@@ -873,7 +880,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(Per
     sw.sweep = sweep; sw.keep = kept; sw.store_zt = (pa.store_zt_last && it + 1 == pa.n_sweeps);
     sw.slot = kept ? draw - pa.chunk_base : 0; sw.chunk_cap = a.chunk_cap; sw.draws = a.draws;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-      sweep_tile<D, MODE>(a, mc, s_cp, s_beta, s_tab, s_priv, sw, chain, tile, key);
+      sweep_tile<D, MODE>(a, mc, s_cp, s_beta, s_tab, s_priv, sw, chain, tile, c3);
     flush_stats(s_priv, s_acc, nstat, kept);
     __syncthreads();
     for (int t = tid; t < nstat; t += SWEEP_THREADS)

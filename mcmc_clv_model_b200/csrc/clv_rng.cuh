@@ -1,8 +1,10 @@
 // clv_rng.cuh — counter-based random numbers for the sampler.
 //
-// Philox4x32-10 keyed by (seed + global chain index), counter (customer_gid, sweep, slot, domain):
+// Philox4x32-10 keyed by the 64-bit seed, counter (customer_gid, sweep, slot, domain | global_chain << 4):
 // a draw depends only on WHICH customer/chain/sweep it belongs to, never on the thread, block,
-// shard or GPU that computes it.  oracle/philox_np.py restates this contract in NumPy; the STRICT
+// shard or GPU that computes it.  The key being the same for every chain, the ten round keys are
+// launch constants: the host passes them as kernel parameters and the hot loop reads them straight
+// from the constant bank (no per-round key arithmetic).  oracle/philox_np.py restates this contract in NumPy; the STRICT
 // transforms below (fp64) are what it reproduces, the FAST ones (fp32 through the SFU: MUFU.LG2 /
 // MUFU.SIN / MUFU.COS / MUFU.RSQ) draw from the same laws.
 #pragma once
@@ -17,9 +19,24 @@ struct PhiloxKey {
   uint32_t k0, k1;
 };
 
-__host__ __device__ inline PhiloxKey chain_key(uint64_t seed, uint32_t global_chain) {
-  uint64_t s = seed + (uint64_t)global_chain;
-  return PhiloxKey{(uint32_t)s, (uint32_t)(s >> 32)};
+__host__ __device__ inline PhiloxKey seed_key(uint64_t seed) { return PhiloxKey{(uint32_t)seed, (uint32_t)(seed >> 32)}; }
+// fourth counter word: domain in the low 4 bits, global chain index above
+__host__ __device__ inline uint32_t dom_word(uint32_t domain, uint32_t global_chain) { return domain | (global_chain << 4); }
+
+// the ten round keys of a seed (k0 + r W0, k1 + r W1), for kernels that take them as parameters
+struct PhiloxRoundKeys {
+  uint32_t k[20];
+};
+__host__ __device__ inline PhiloxRoundKeys round_keys(uint64_t seed) {
+  PhiloxRoundKeys rk;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    rk.k[2 * r] = k0;
+    rk.k[2 * r + 1] = k1;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return rk;
 }
 
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, PhiloxKey key) {
@@ -35,6 +52,21 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     const uint32_t n2 = hi0 ^ c3 ^ k1;
     c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
     k0 += W0; k1 += W1;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// same function with the round keys precomputed (kernel parameters => constant-bank operands)
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxRoundKeys& rk) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t lo0, hi0, lo1, hi1;
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo0), "=r"(hi0) : "r"(c0), "r"(M0));
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo1), "=r"(hi1) : "r"(c2), "r"(M1));
+    const uint32_t n0 = hi1 ^ c1 ^ rk.k[2 * r];
+    const uint32_t n2 = hi0 ^ c3 ^ rk.k[2 * r + 1];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
   }
   return make_uint4(c0, c1, c2, c3);
 }
@@ -92,21 +124,21 @@ __device__ __forceinline__ void normal_pair_u53(uint4 r, double* nc, double* ns)
 }
 
 // ---- level-2 domain (one thread per chain; always fp64) -----------------------------------------
-__device__ inline double level2_normal(PhiloxKey key, uint32_t sweep, uint32_t idx) {
+__device__ inline double level2_normal(PhiloxKey key, uint32_t c3, uint32_t sweep, uint32_t idx) {
   double c, s;
-  normal_pair_u53(philox4x32_10(idx, sweep, 0u, DOM_LEVEL2, key), &c, &s);
+  normal_pair_u53(philox4x32_10(idx, sweep, 0u, c3, key), &c, &s);
   return c;
 }
 
 // chi2(df) = 2 Gamma(df/2, 1), Marsaglia-Tsang (df >= 2)
-__device__ inline double level2_chi2(PhiloxKey key, uint32_t sweep, uint32_t idx, double df) {
+__device__ inline double level2_chi2(PhiloxKey key, uint32_t c3, uint32_t sweep, uint32_t idx, double df) {
   double a = 0.5 * df;
   double d = a - 1.0 / 3.0;
   double c = 1.0 / sqrt(9.0 * d);
   for (uint32_t attempt = 0; attempt < 4096u; ++attempt) {
     double x, unused;
-    normal_pair_u53(philox4x32_10(idx, sweep, 2u * attempt, DOM_LEVEL2, key), &x, &unused);
-    uint4 rb = philox4x32_10(idx, sweep, 2u * attempt + 1u, DOM_LEVEL2, key);
+    normal_pair_u53(philox4x32_10(idx, sweep, 2u * attempt, c3, key), &x, &unused);
+    uint4 rb = philox4x32_10(idx, sweep, 2u * attempt + 1u, c3, key);
     double u = u53(rb.x, rb.y);
     double v = 1.0 + c * x;
     if (v <= 0.0) continue;

@@ -8,8 +8,8 @@ so that the GPU's "strict f64" Philox mode can be replayed through the oracle
 
 Contract
 --------
-key     = (lo32(seed + chain), hi32(seed + chain))
-counter = (customer_gid, sweep, slot, domain)
+key     = (lo32(seed), hi32(seed))
+counter = (customer_gid, sweep, slot, domain | chain << 4)
 domain  : 0 sampler level-1, 1 level-2 draw, 2 forecast, 3 synthetic generator
 """
 from __future__ import annotations
@@ -49,9 +49,14 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
 
 
-def chain_key(seed: int, chain: int):
-    s = (int(seed) + int(chain)) & 0xFFFFFFFFFFFFFFFF
+def chain_key(seed: int, chain: int = 0):
+    """The key is the seed; the chain index travels in the counter (dom_word)."""
+    s = int(seed) & 0xFFFFFFFFFFFFFFFF
     return s & 0xFFFFFFFF, s >> 32
+
+
+def dom_word(domain: int, chain: int = 0) -> int:
+    return (domain | (int(chain) << 4)) & 0xFFFFFFFF
 
 
 def u53(a, b):
@@ -96,7 +101,8 @@ def sampler_variates(seed, chain, gids, sweep, n_mh_steps, with_eta=False):
     depending on z)."""
     k0, k1 = chain_key(seed, chain)
     gids = np.asarray(gids, dtype=np.uint64)
-    r = philox4x32_10(gids, sweep, 0, DOM_SAMPLER, k0, k1)
+    c3 = dom_word(DOM_SAMPLER, chain)
+    r = philox4x32_10(gids, sweep, 0, c3, k0, k1)
     u_z = u53(r[0], r[1])
     u_t = u53(r[2], r[3])
     out = dict(u_z=u_z, u_tau=u_t, e_tau=-np.log(u_t))
@@ -105,14 +111,14 @@ def sampler_variates(seed, chain, gids, sweep, n_mh_steps, with_eta=False):
     t3_m = np.empty((S, gids.size))
     u_acc = np.empty((S, gids.size))
     for s in range(S):
-        a = philox4x32_10(gids, sweep, 1 + 2 * s, DOM_SAMPLER, k0, k1)
-        b = philox4x32_10(gids, sweep, 2 + 2 * s, DOM_SAMPLER, k0, k1)
+        a = philox4x32_10(gids, sweep, 1 + 2 * s, c3, k0, k1)
+        b = philox4x32_10(gids, sweep, 2 + 2 * s, c3, k0, k1)
         t3_l[s] = t3_from_words(a[0], a[1], a[2])
         t3_m[s] = t3_from_words(a[3], b[0], b[1])
         u_acc[s] = u32(b[2])
     out.update(t3_l=t3_l, t3_m=t3_m, u_acc=u_acc)
     if with_eta:
-        e = philox4x32_10(gids, sweep, 1 + 2 * S, DOM_SAMPLER, k0, k1)
+        e = philox4x32_10(gids, sweep, 1 + 2 * S, c3, k0, k1)
         out["n_eta"] = normal_pair_u53(e[0], e[1], e[2], e[3])[0]
     return out
 
@@ -122,7 +128,7 @@ def sampler_variates(seed, chain, gids, sweep, n_mh_steps, with_eta=False):
 # ---------------------------------------------------------------------------
 def level2_normal(seed, chain, sweep, idx):
     k0, k1 = chain_key(seed, chain)
-    r = philox4x32_10(np.asarray([idx]), sweep, 0, DOM_LEVEL2, k0, k1)
+    r = philox4x32_10(np.asarray([idx]), sweep, 0, dom_word(DOM_LEVEL2, chain), k0, k1)
     return float(normal_pair_u53(r[0], r[1], r[2], r[3])[0][0])
 
 
@@ -134,8 +140,8 @@ def level2_chi2(seed, chain, sweep, idx, df):
     c = 1.0 / np.sqrt(9.0 * d)
     attempt = 0
     while True:
-        ra = philox4x32_10(np.asarray([idx]), sweep, 2 * attempt, DOM_LEVEL2, k0, k1)
-        rb = philox4x32_10(np.asarray([idx]), sweep, 2 * attempt + 1, DOM_LEVEL2, k0, k1)
+        ra = philox4x32_10(np.asarray([idx]), sweep, 2 * attempt, dom_word(DOM_LEVEL2, chain), k0, k1)
+        rb = philox4x32_10(np.asarray([idx]), sweep, 2 * attempt + 1, dom_word(DOM_LEVEL2, chain), k0, k1)
         x = float(normal_pair_u53(ra[0], ra[1], ra[2], ra[3])[0][0])
         u = float(u53(rb[0], rb[1])[0])
         attempt += 1
