@@ -230,6 +230,11 @@ int clv_generate(const clv_generate_config* cfg, const double* beta /*K x 2*/, c
                  int X_given, int T_cal_given, int32_t* x, double* t_x, double* T_cal, double* X, int32_t* x_star,
                  double* lambda_true, double* mu_true, double* tau_true);
 
+/* ---- test hook: the level-1 variates of MH step 0 (two Student-t3 proposals, accept uniform) that customers
+ * 0..n-1 of chain 0 consume in sweep `sweep`, as the sweep kernel generates them in rng_mode fast / strict. */
+int clv_debug_variates(int device, uint64_t seed, uint32_t sweep, int rng_mode, int64_t n, double* t3_l, double* t3_m,
+                       double* u_acc);
+
 /* ---- micro-benchmarks used by bench.py for the issue-rate roofline -------------------------- */
 /* Measures, on `device`, sustained warp-instruction throughput of dependent-free loops of
  * FFMA, IMAD (32-bit), MUFU.EX2 and DFMA.  out[4] = giga thread-ops/s for each. */

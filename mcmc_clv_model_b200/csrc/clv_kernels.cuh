@@ -163,13 +163,13 @@ __device__ __forceinline__ bool mh_accept(double d, float uf, ExactU exact_u) {
 
 // np.clip(v, -70, 70) of bi:323-324 for both proposals; the test runs on the high words so the common case costs a few
 // integer ops and one never-taken branch (|v| >= 70 is a once-in-a-run event)
-__device__ __noinline__ void clip70_slow(double& a, double& b) {
-  a = fmin(fmax(a, -70.0), 70.0);
-  b = fmin(fmax(b, -70.0), 70.0);
-}
+__device__ __noinline__ double clip70_slow(double v) { return fmin(fmax(v, -70.0), 70.0); }   // by value: no stack traffic
 __device__ __forceinline__ void clip70_pair(double& a, double& b) {
   const unsigned ha = (unsigned)__double2hiint(a) & 0x7fffffffu, hb = (unsigned)__double2hiint(b) & 0x7fffffffu;
-  if (max(ha, hb) >= 0x40518000u) clip70_slow(a, b);
+  if (max(ha, hb) >= 0x40518000u) {
+    a = clip70_slow(a);
+    b = clip70_slow(b);
+  }
 }
 
 // Level-2 sufficient statistics.  Every thread owns one column of the dynamic shared array s_priv[(stat)][128]
@@ -237,7 +237,9 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
   const long long N = mc.N;
   const long long cN = (long long)chain * N;
   const double P00 = cp.P00, P01 = cp.P01, P11 = cp.P11;
-  const double s_l = cp.Sigma[0], s_m = cp.Sigma[D + 1];   // proposal scales are variances (bi:316-317, Q2)
+  // proposal scales are variances (bi:316-317, Q2); t3_fast returns t / sqrt(3)
+  const double t3s = (MODE == MODE_FAST) ? 1.7320508075688772 : 1.0;
+  const double s_l = cp.Sigma[0] * t3s, s_m = cp.Sigma[D + 1] * t3s;
   const bool keep = sw.keep != 0;
   const long long i = tile * SWEEP_THREADS + tid;
   const bool valid = i < N;
@@ -431,6 +433,24 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_stats_only(SweepArgs a) {
   __syncthreads();
   for (int t = tid; t < nstat; t += SWEEP_THREADS)
     if (s_acc[t]) atomicAdd(&a.acc[chain * NSTAT_MAX + t], s_acc[t]);
+}
+
+// Test hook: the level-1 variates of MH step 0 (proposal t3 for log lambda / log mu, accept uniform) that customer gid
+// of chain 0 consumes in sweep `sweep`, exactly as sweep_tile generates them (FAST: including the 1/sqrt(3) convention).
+template <int MODE>
+__global__ void k_debug_variates(PhiloxRoundKeys rk, uint32_t sweep, long long n, double* t3l, double* t3m, double* uacc) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t gid = (uint32_t)i, c3 = dom_word(DOM_SAMPLER, 0u);
+    const uint4 ra = philox4x32_10_rk(gid, sweep, 1u, c3, rk), rb = philox4x32_10_rk(gid, sweep, 2u, c3, rk);
+    if (MODE == MODE_STRICT) {
+      t3l[i] = t3_strict(ra.x, ra.y, ra.z);
+      t3m[i] = t3_strict(ra.w, rb.x, rb.y);
+    } else {
+      t3l[i] = 1.7320508075688772 * (double)t3_fast(ra.x, ra.y, ra.z);
+      t3m[i] = 1.7320508075688772 * (double)t3_fast(ra.w, rb.x, rb.y);
+    }
+    uacc[i] = u32d(rb.z);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -101,16 +101,17 @@ __device__ __forceinline__ double t3_strict(uint32_t ra, uint32_t rb, uint32_t r
   return n0 / sqrt(chi2 / 3.0);
 }
 
+// FAST variant, returns t / sqrt(3) (the caller folds sqrt(3) into the proposal scale).  With a = -lg2 u1, b = -lg2 u3
+// the -2 ln 2 factors of the Box-Muller radius and of the chi-square cancel:
+//   t / sqrt(3) = cos(th) sqrt(a) / sqrt(a sin^2(th) + b) = cos(th) * rsqrt(sin^2(th) + b / a)
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float t3_fast(uint32_t ra, uint32_t rb, uint32_t rc) {
-  constexpr float NEG2LN2 = -1.3862943611198906f;  // -2 ln 2
-  const float u1 = u24f(ra), u3 = u24f(rc);
-  const float r2 = NEG2LN2 * lg2_ftz(u1);           // -2 ln u1
+  // both <= 0; u1 can round to 1.0f (lg2 = +0): keep the divisor strictly negative so that b / a -> +huge, t -> 0
+  const float l1 = fminf(lg2_ftz(u24f(ra)), -1e-30f), l3 = lg2_ftz(u24f(rc));
   // angle 2 pi (k + 0.5) 2^-24 straight from the integer
   const float ang = fmaf((float)(rb >> 8), 6.2831853071795865f * 0x1.0p-24f, 6.2831853071795865f * 0x1.0p-25f);
   const float s = sin_ftz(ang), c = cos_ftz(ang);
-  // n0 = sqrt(r2) c ; n1^2 = r2 s^2 ; t = n0 * rsqrt((n1^2 + e)/3)
-  const float chi2 = fmaf(r2 * s, s, NEG2LN2 * lg2_ftz(u3));
-  return c * sqrt_ftz(r2) * rsqrt_ftz(chi2 * 0.33333333333333333f);
+  return c * rsqrt_ftz(fmaf(s, s, l3 * rcp_approx(l1)));
 }
 
 // two standard normals from four words (53-bit uniforms, fp64): cos / sin branch

@@ -368,3 +368,31 @@ def test_posterior_summary_and_weekly_tracking_on_resident_draws(cdnow_abe):
     # and the expectation: sum_i lambda_i * active
     expect = np.array([(l1[:, :, 0] * ((t > birth) & (t <= birth + l1[:, :, 2]))).sum(axis=1).mean() for t in times])
     assert np.all(np.abs(inc - expect) < 6 * np.sqrt(expect / l1.shape[0]) + 0.5)
+
+
+def test_level1_variates_fast_vs_strict_vs_oracle():
+    """The sweep kernel's proposal variates: STRICT == the NumPy restatement of the Philox contract; FAST (fp32 SFU
+    transforms, algebraically simplified) == STRICT up to fp32 precision, variate by variate; both are Student-t(3)."""
+    import ctypes as C
+    from scipy import stats
+    from mcmc_clv_model_b200 import _lib as L
+    from oracle import philox_np as px
+    lib = L.load()
+    n, seed, sweep = 1_000_000, 777, 5
+    out = {}
+    for mode in (L.RNG_STRICT, L.RNG_FAST):
+        a, b, u = np.empty(n), np.empty(n), np.empty(n)
+        L.check(lib.clv_debug_variates(0, seed, sweep, mode, n, L.dptr(a), L.dptr(b), L.dptr(u)))
+        out[mode] = (a, b, u)
+    v = px.sampler_variates(seed, 0, np.arange(n), sweep, 1)
+    np.testing.assert_allclose(out[L.RNG_STRICT][0], v["t3_l"][0], rtol=1e-12)
+    np.testing.assert_allclose(out[L.RNG_STRICT][1], v["t3_m"][0], rtol=1e-12)
+    np.testing.assert_array_equal(out[L.RNG_STRICT][2], v["u_acc"][0])
+    np.testing.assert_array_equal(out[L.RNG_FAST][2], v["u_acc"][0])
+    for j in (0, 1):
+        s, f = out[L.RNG_STRICT][j], out[L.RNG_FAST][j]
+        err = np.abs(f - s) / (1e-3 + np.abs(s))
+        assert np.median(err) < 1e-5 and np.quantile(err, 0.999) < 1e-2, (np.median(err), np.quantile(err, 0.999))
+        assert stats.kstest(f, stats.t(3).cdf).pvalue > 1e-3
+        assert stats.kstest(s, stats.t(3).cdf).pvalue > 1e-3
+    assert abs(np.corrcoef(out[L.RNG_FAST][0], out[L.RNG_FAST][1])[0, 1]) < 0.01
