@@ -122,6 +122,9 @@ int clv_comm_init(clv_sampler* h, const void* unique_id128, int rank, int world)
  * (64-byte cudaIpcMemHandle), the host all-gathers the handles, every rank connects.  world <= 16, one process per GPU. */
 int clv_p2p_export(clv_sampler* h, void* handle64);
 int clv_p2p_connect(clv_sampler* h, const void* handles /* world x 64 bytes */, int rank, int world);
+/* Mailboxes and their peer mappings live for the life of the process; returns 1 when a connected set already exists for
+ * this (device, rank, world, n_chains): clv_p2p_connect can then be called with handles == NULL. */
+int clv_p2p_is_cached(clv_sampler* h, int rank, int world);
 
 /* ---- the chain driver, _run_chain (bi:346-431, tri:465-574) ------------------------------- */
 /* Runs burnin+mcmc sweeps on every chain of the handle and writes, per chain c,

@@ -70,6 +70,7 @@ SIGNATURES = {
     "clv_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "clv_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "clv_p2p_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "clv_p2p_is_cached": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "clv_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, c_double_p, c_double_p, c_double_p,
                           PROGRESS_CB, C.c_void_p, C.c_int64]),
     "clv_run_resident": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, c_double_p, c_double_p,

@@ -54,6 +54,15 @@ constexpr int NCCL_INT64 = 4, NCCL_SUM = 0;
 // ncclCommInitRank costs seconds, a sampler call should not pay it twice
 struct CachedComm { int device, rank, world; nccl_comm_t comm; };
 std::vector<CachedComm> g_comms;
+// peer mailboxes of the fused all-reduce are likewise created and connected once per (device, rank, world, chains)
+struct CachedMailbox {
+  int device, rank, world, chains;
+  void* base; size_t bytes, flags_off;
+  bool connected;
+  void* peer_base[P2P_MAX_WORLD];
+};
+std::vector<CachedMailbox> g_mailboxes;
+unsigned long long g_epoch = 0;     // process-wide: mailbox flags never repeat across handles
 
 }  // namespace
 
@@ -437,9 +446,6 @@ void clv_destroy(clv_sampler* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-  for (int r = 0; r < P2P_MAX_WORLD; ++r)
-    if (h->peer_base[r] && r != h->rank) cudaIpcCloseMemHandle(h->peer_base[r]);
-  if (h->d_mailbox) cudaFree(h->d_mailbox);
   if (h->d_acc3) cudaFree(h->d_acc3);
   if (h->d_barrier) cudaFree(h->d_barrier);
   void* ptrs[] = {h->d_mc, h->d_params, h->d_x, h->d_tx, h->d_T, h->d_Xc, h->d_logs, h->d_ll, h->d_lm, h->d_le,
@@ -660,7 +666,7 @@ int clv_init_state(clv_sampler* h, const clv_init_stats* st) {
   h->launches++;
   CK(h, cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
   h->inited = true;
-  h->init_epoch++;
+  h->init_epoch = ++g_epoch;
   if (int r = recompute_stats(h)) return r;
   CK(h, cudaStreamSynchronize(h->stream));
   h->sweeps_done = 0;
@@ -706,17 +712,29 @@ int clv_comm_init(clv_sampler* h, const void* unique_id128, int rank, int world)
   return CLV_OK;
 }
 
+static CachedMailbox* find_mailbox(const clv_sampler* h, int rank, int world) {
+  for (auto& m : g_mailboxes)
+    if (m.device == h->cfg.device && m.chains == h->chains && (world == 0 || (m.rank == rank && m.world == world))) return &m;
+  return nullptr;
+}
+
 int clv_p2p_export(clv_sampler* h, void* handle64) {
   if (!h || !handle64) return fail(h, CLV_ERR_ARG, "null argument");
   CK(h, cudaSetDevice(h->cfg.device));
-  if (!h->d_mailbox) {
+  CachedMailbox* m = find_mailbox(h, 0, 0);
+  if (!m) {
+    CachedMailbox nm{};
+    nm.device = h->cfg.device; nm.chains = h->chains; nm.rank = -1; nm.world = 0; nm.connected = false;
     const size_t data = sizeof(long long) * 2 * P2P_MAX_WORLD * (size_t)h->chains * NSTAT_MAX;
     const size_t flags = sizeof(unsigned long long) * 2 * P2P_MAX_WORLD * (size_t)h->chains;
-    h->mailbox_flags_off = data;
-    h->mailbox_bytes = data + flags;
-    CK(h, cudaMalloc(&h->d_mailbox, h->mailbox_bytes));
-    CK(h, cudaMemset(h->d_mailbox, 0, h->mailbox_bytes));
+    nm.flags_off = data;
+    nm.bytes = data + flags;
+    CK(h, cudaMalloc(&nm.base, nm.bytes));
+    CK(h, cudaMemset(nm.base, 0, nm.bytes));
+    g_mailboxes.push_back(nm);
+    m = &g_mailboxes.back();
   }
+  h->d_mailbox = m->base; h->mailbox_bytes = m->bytes; h->mailbox_flags_off = m->flags_off;
   cudaIpcMemHandle_t hd;
   CK(h, cudaIpcGetMemHandle(&hd, h->d_mailbox));
   static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -724,24 +742,41 @@ int clv_p2p_export(clv_sampler* h, void* handle64) {
   return CLV_OK;
 }
 
+/* 1 when this process already holds a connected mailbox set for (device, rank, world, chains): clv_p2p_connect may then
+ * be called with handles == NULL (no handle exchange needed). */
+int clv_p2p_is_cached(clv_sampler* h, int rank, int world) {
+  if (!h) return 0;
+  CachedMailbox* m = find_mailbox(h, rank, world);
+  return (m && m->connected) ? 1 : 0;
+}
+
 int clv_p2p_connect(clv_sampler* h, const void* handles, int rank, int world) {
-  if (!h || !handles) return fail(h, CLV_ERR_ARG, "null argument");
+  if (!h) return fail(h, CLV_ERR_ARG, "null argument");
   if (world < 2 || world > P2P_MAX_WORLD || rank < 0 || rank >= world) return fail(h, CLV_ERR_ARG, "p2p: world must be in [2, %d]", P2P_MAX_WORLD);
-  if (!h->d_mailbox) return fail(h, CLV_ERR_STATE, "clv_p2p_connect: call clv_p2p_export first");
   if (h->cfg.sweep_mode == CLV_SWEEP_PERSISTENT) return fail(h, CLV_ERR_ARG, "persistent sweep mode is single-shard only");
   CK(h, cudaSetDevice(h->cfg.device));
-  h->rank = rank; h->world = world;
-  for (int r = 0; r < world; ++r) {
-    void* base = h->d_mailbox;
-    if (r != rank) {
-      cudaIpcMemHandle_t hd;
-      std::memcpy(&hd, (const char*)handles + 64 * r, 64);
-      cudaError_t e = cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess);
-      if (e != cudaSuccess) return fail(h, CLV_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+  CachedMailbox* m = find_mailbox(h, rank, world);
+  if (!(m && m->connected)) {
+    m = find_mailbox(h, 0, 0);
+    if (!m || !handles) return fail(h, CLV_ERR_STATE, "clv_p2p_connect: call clv_p2p_export first and pass the gathered handles");
+    for (int r = 0; r < world; ++r) {
+      void* base = m->base;
+      if (r != rank) {
+        cudaIpcMemHandle_t hd;
+        std::memcpy(&hd, (const char*)handles + 64 * r, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(h, CLV_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+      }
+      m->peer_base[r] = base;
     }
-    h->peer_base[r] = base;
-    h->peer_data[r] = (long long*)base;
-    h->peer_flags[r] = (unsigned long long*)((char*)base + h->mailbox_flags_off);
+    m->rank = rank; m->world = world; m->connected = true;
+  }
+  h->rank = rank; h->world = world;
+  h->d_mailbox = m->base; h->mailbox_bytes = m->bytes; h->mailbox_flags_off = m->flags_off;
+  for (int r = 0; r < world; ++r) {
+    h->peer_base[r] = m->peer_base[r];
+    h->peer_data[r] = (long long*)m->peer_base[r];
+    h->peer_flags[r] = (unsigned long long*)((char*)m->peer_base[r] + m->flags_off);
   }
   h->p2p = true;
   return CLV_OK;

@@ -135,9 +135,13 @@ class Sampler:
         L.check(self.lib.clv_p2p_export(self.h, buf), self.h)
         return buf.raw
 
+    def p2p_is_cached(self, rank: int, world: int) -> bool:
+        return bool(self.lib.clv_p2p_is_cached(self.h, int(rank), int(world)))
+
     def p2p_connect(self, handles, rank: int, world: int):
-        """handles: list of the `world` 64-byte mailbox handles (p2p_export of every rank, all-gathered)."""
-        blob = C.create_string_buffer(b"".join(handles), 64 * world)
+        """handles: list of the `world` 64-byte mailbox handles (p2p_export of every rank, all-gathered); None when
+        p2p_is_cached()."""
+        blob = C.create_string_buffer(b"".join(handles), 64 * world) if handles is not None else None
         L.check(self.lib.clv_p2p_connect(self.h, blob, int(rank), int(world)), self.h)
 
     # ---- sweeps ------------------------------------------------------------------------------
