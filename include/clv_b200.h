@@ -233,6 +233,16 @@ int clv_generate(const clv_generate_config* cfg, const double* beta /*K x 2*/, c
                  int X_given, int T_cal_given, int32_t* x, double* t_x, double* T_cal, double* X, int32_t* x_star,
                  double* lambda_true, double* mu_true, double* tau_true);
 
+/* ---- event log -> CBS (src/models/utils/elog2cbs2param.py:33-94) --------------------------------- */
+/* Events in any order: cust ids, day numbers (days since any fixed epoch), sales (nullable: 1 per event, :45).  Same
+ * (cust, day) events are one transaction with summed sales (:62).  T_cal_day / T_tot_day: last calibration / observation
+ * day; unit_days: 7 for weeks.  Outputs (any nullable) have one row per customer with a calibration purchase, ascending
+ * cust id; the caller sizes them for the number of distinct customers (<= n_events); *n_customers returns the row count. */
+int clv_elog2cbs(int device, int64_t n_events, const int64_t* cust, const int32_t* day, const double* sales,
+                 int32_t T_cal_day, int32_t T_tot_day, double unit_days, int64_t* n_customers, int64_t* cust_out,
+                 int32_t* x, double* t_x, double* litt, double* sales_out, double* sales_x, int32_t* first_day,
+                 double* T_cal, double* T_star, int32_t* x_star, double* sales_star);
+
 /* ---- test hook: the level-1 variates of MH step 0 (two Student-t3 proposals, accept uniform) that customers
  * 0..n-1 of chain 0 consume in sweep `sweep`, as the sweep kernel generates them in rng_mode fast / strict. */
 int clv_debug_variates(int device, uint64_t seed, uint32_t sweep, int rng_mode, int64_t n, double* t3_l, double* t3_m,

@@ -16,6 +16,7 @@
 #include "../../include/clv_b200.h"
 #include "clv_kernels.cuh"
 #include "clv_forecast.cuh"
+#include "clv_cbs.cuh"
 
 using namespace clv;
 
@@ -1489,6 +1490,105 @@ int clv_generate(const clv_generate_config* cfg, const double* beta, const doubl
   }
   cleanup();
   if (e != cudaSuccess) return fail(nullptr, CLV_ERR_CUDA, "clv_generate failed: %s", cudaGetErrorString(e));
+  return CLV_OK;
+}
+
+// ---- event log -> CBS ---------------------------------------------------------------------------
+int clv_elog2cbs(int device, int64_t n_events, const int64_t* cust, const int32_t* day, const double* sales,
+                 int32_t T_cal_day, int32_t T_tot_day, double unit_days, int64_t* n_customers, int64_t* cust_out,
+                 int32_t* x, double* t_x, double* litt, double* sales_out, double* sales_x, int32_t* first_day,
+                 double* T_cal, double* T_star, int32_t* x_star, double* sales_star) {
+  if (!cust || !day || !n_customers || n_events < 1) return fail(nullptr, CLV_ERR_ARG, "clv_elog2cbs: bad argument");
+  if (!(unit_days > 0)) return fail(nullptr, CLV_ERR_ARG, "clv_elog2cbs: unit_days must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, CLV_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
+  CK(nullptr, cudaSetDevice(device));
+  const size_t n = (size_t)n_events;
+  std::vector<void*> allocs;
+  auto dm = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, std::max<size_t>(bytes, 8)) != cudaSuccess) return nullptr; allocs.push_back(p); return p; };
+  auto cleanup = [&]() { for (void* p : allocs) cudaFree(p); };
+  long long *k0 = (long long*)dm(n * 8), *k1 = (long long*)dm(n * 8);
+  int *d0 = (int*)dm(n * 4), *d1 = (int*)dm(n * 4), *head = (int*)dm(n * 4), *idx = (int*)dm(n * 4);
+  unsigned *p0 = (unsigned*)dm(n * 4), *p1 = (unsigned*)dm(n * 4);
+  double *s0 = sales ? (double*)dm(n * 8) : nullptr, *s1 = sales ? (double*)dm(n * 8) : nullptr;
+  if (!k0 || !k1 || !d0 || !d1 || !head || !idx || !p0 || !p1 || (sales && (!s0 || !s1))) { cleanup(); return fail(nullptr, CLV_ERR_CUDA, "clv_elog2cbs: out of device memory"); }
+  cudaError_t e = cudaMemcpy(k0, cust, n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d0, day, n * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && sales) e = cudaMemcpy(s0, sales, n * 8, cudaMemcpyHostToDevice);
+  // permutation-carrying stable sorts: by day, then by customer  =>  sorted by (cust, day), input order within ties
+  std::vector<unsigned> iota(n);
+  for (size_t i = 0; i < n; ++i) iota[i] = (unsigned)i;
+  if (e == cudaSuccess) e = cudaMemcpy(p0, iota.data(), n * 4, cudaMemcpyHostToDevice);
+  // day may be negative (before the epoch): bias to unsigned order
+  std::vector<unsigned> dkey(n);
+  for (size_t i = 0; i < n; ++i) dkey[i] = (unsigned)day[i] ^ 0x80000000u;
+  unsigned *dk0 = (unsigned*)dm(n * 4), *dk1 = (unsigned*)dm(n * 4);
+  if (!dk0 || !dk1) { cleanup(); return fail(nullptr, CLV_ERR_CUDA, "clv_elog2cbs: out of device memory"); }
+  if (e == cudaSuccess) e = cudaMemcpy(dk0, dkey.data(), n * 4, cudaMemcpyHostToDevice);
+  size_t tb1 = 0, tb2 = 0, tb3 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb1, dk0, dk1, p0, p1, (int)n);
+  cub::DeviceRadixSort::SortPairs(nullptr, tb2, k0, k1, p0, p1, (int)n);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb3, head, idx, (int)n);
+  void* tmp = dm(std::max(tb1, std::max(tb2, tb3)));
+  if (!tmp) { cleanup(); return fail(nullptr, CLV_ERR_CUDA, "clv_elog2cbs: out of device memory"); }
+  // pass 1: permutation sorted by day
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tb1, dk0, dk1, p0, p1, (int)n);
+  // gather customer keys in that order, pass 2: stable sort by customer (int64 with sign bias through the signed overload)
+  // (gathers are done with thrust-free tiny kernels below)
+  auto gather = [&](auto* dst, const auto* src, const unsigned* perm) {
+    using T = std::remove_pointer_t<decltype(dst)>;
+    k_gather<T><<<(int)std::min<size_t>((n + 255) / 256, 148 * 32), 256>>>(dst, src, perm, (long long)n);
+  };
+  if (e == cudaSuccess) { gather(k1, k0, p1); e = cudaGetLastError(); }
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tb2, k1, k0, p1, p0, (int)n);   // k0 = sorted cust, p0 = final perm
+  if (e == cudaSuccess) { gather(d1, d0, p0); if (sales) gather(s1, s0, p0); e = cudaGetLastError(); }
+  const int gb = (int)std::min<size_t>((n + 255) / 256, 148 * 32);
+  if (e == cudaSuccess) { k_cbs_heads<<<gb, 256>>>(k0, (long long)n, head); e = cudaGetLastError(); }
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tb3, head, idx, (int)n);
+  int last_head = 0, last_idx = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&last_head, head + n - 1, 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(&last_idx, idx + n - 1, 4, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { cleanup(); return fail(nullptr, CLV_ERR_CUDA, "clv_elog2cbs failed: %s", cudaGetErrorString(e)); }
+  const long long nc = (long long)last_idx + last_head;
+  long long* starts = (long long*)dm((size_t)nc * 8);
+  CbsOut o{};
+  o.cust = (long long*)dm(nc * 8); o.x = (int*)dm(nc * 4); o.t_x = (double*)dm(nc * 8); o.litt = (double*)dm(nc * 8);
+  o.sales = (double*)dm(nc * 8); o.sales_x = (double*)dm(nc * 8); o.first_day = (int*)dm(nc * 4); o.T_cal = (double*)dm(nc * 8);
+  o.T_star = (double*)dm(nc * 8); o.x_star = (int*)dm(nc * 4); o.sales_star = (double*)dm(nc * 8); o.keep = (int*)dm(nc * 4);
+  if (!starts || !o.cust || !o.x || !o.t_x || !o.litt || !o.sales || !o.sales_x || !o.first_day || !o.T_cal || !o.T_star || !o.x_star || !o.sales_star || !o.keep) {
+    cleanup(); return fail(nullptr, CLV_ERR_CUDA, "clv_elog2cbs: out of device memory");
+  }
+  k_cbs_starts<<<gb, 256>>>(head, idx, (long long)n, starts);
+  k_cbs_customers<<<(int)std::min<long long>((nc + 255) / 256, 148 * 32), 256>>>(k0, d1, sales ? s1 : nullptr, starts, (long long)n, nc,
+                                                                               T_cal_day, T_tot_day, unit_days, o);
+  e = cudaGetLastError();
+  // compact kept customers on the host (the table is small: one row per customer)
+  std::vector<long long> h_cust(nc);
+  std::vector<int> h_x(nc), h_first(nc), h_xs(nc), h_keep(nc);
+  std::vector<double> h_tx(nc), h_litt(nc), h_s(nc), h_sx(nc), h_T(nc), h_Ts(nc), h_ss(nc);
+  auto dl = [&](void* dst, const void* src, size_t bytes) { if (e == cudaSuccess) e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); };
+  dl(h_cust.data(), o.cust, nc * 8); dl(h_x.data(), o.x, nc * 4); dl(h_first.data(), o.first_day, nc * 4); dl(h_xs.data(), o.x_star, nc * 4);
+  dl(h_keep.data(), o.keep, nc * 4); dl(h_tx.data(), o.t_x, nc * 8); dl(h_litt.data(), o.litt, nc * 8); dl(h_s.data(), o.sales, nc * 8);
+  dl(h_sx.data(), o.sales_x, nc * 8); dl(h_T.data(), o.T_cal, nc * 8); dl(h_Ts.data(), o.T_star, nc * 8); dl(h_ss.data(), o.sales_star, nc * 8);
+  cleanup();
+  if (e != cudaSuccess) return fail(nullptr, CLV_ERR_CUDA, "clv_elog2cbs failed: %s", cudaGetErrorString(e));
+  long long m = 0;
+  for (long long c = 0; c < nc; ++c) {
+    if (!h_keep[c]) continue;
+    if (cust_out) cust_out[m] = h_cust[c];
+    if (x) x[m] = h_x[c];
+    if (t_x) t_x[m] = h_tx[c];
+    if (litt) litt[m] = h_litt[c];
+    if (sales_out) sales_out[m] = h_s[c];
+    if (sales_x) sales_x[m] = h_sx[c];
+    if (first_day) first_day[m] = h_first[c];
+    if (T_cal) T_cal[m] = h_T[c];
+    if (T_star) T_star[m] = h_Ts[c];
+    if (x_star) x_star[m] = h_xs[c];
+    if (sales_star) sales_star[m] = h_ss[c];
+    ++m;
+  }
+  *n_customers = m;
   return CLV_OK;
 }
 

@@ -17,6 +17,8 @@ Outputs (all small, committed):
   kat_bi_m1.npz, kat_bi_m2.npz, kat_tri.npz    real-RNG known-answer chains
   inj_bi_k1.npz, inj_bi_k2.npz, inj_tri_k3.npz, inj_edge.npz   injected-stream trajectories
   fc_bi.npz, fc_tri.npz              forecast with injected uniforms / normals
+  elog_abe.npz, elog_full.npz        event logs + the reference's elog2cbs output (`make_golden.py cbs` regenerates only these)
+(post_*.npz come from make_posterior_golden.py)
 """
 import os
 import sys
@@ -277,5 +279,25 @@ def main():
     print("golden fixtures written to", HERE)
 
 
+
+
+def make_cbs_golden():
+    """Event log -> CBS with the reference's own elog2cbs (src/models/utils/elog2cbs2param.py), as the data-processing
+    scripts call it (src/data_processing/2A_cdnow_elog2cbs_abe.py: units="W", T_cal="1997-09-30", T_tot="1998-06-30")."""
+    from src.models.utils.elog2cbs2param import elog2cbs
+    for name in ("abe", "full"):
+        elog = pd.read_csv(f"{REF}/data/raw/cdnow_{name}Elog.csv")
+        elog["date"] = pd.to_datetime(elog["date"])
+        cbs = elog2cbs(elog, units="W", T_cal="1997-09-30", T_tot="1998-06-30")
+        day = ((elog["date"] - pd.Timestamp("1970-01-01")) // pd.Timedelta(days=1)).to_numpy().astype(np.int32)
+        np.savez_compressed(f"{HERE}/elog_{name}.npz", cust=elog["cust"].to_numpy().astype(np.int64), day=day,
+                            sales=elog["sales"].to_numpy(float),
+                            **{f"cbs_{c}": cbs[c].to_numpy() for c in ("cust", "x", "t_x", "litt", "sales", "sales_x", "T_cal",
+                                                                      "T_star", "x_star", "sales_star")},
+                            cbs_first=((cbs["first"] - pd.Timestamp("1970-01-01")) // pd.Timedelta(days=1)).to_numpy().astype(np.int32))
+
+
 if __name__ == "__main__":
-    main()
+    if "cbs" not in sys.argv[1:]:
+        main()
+    make_cbs_golden()

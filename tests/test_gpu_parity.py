@@ -396,3 +396,29 @@ def test_level1_variates_fast_vs_strict_vs_oracle():
         assert stats.kstest(f, stats.t(3).cdf).pvalue > 1e-3
         assert stats.kstest(s, stats.t(3).cdf).pvalue > 1e-3
     assert abs(np.corrcoef(out[L.RNG_FAST][0], out[L.RNG_FAST][1])[0, 1]) < 0.01
+
+
+@pytest.mark.parametrize("name", ["abe", "full"])
+def test_elog2cbs_vs_reference(name):
+    """device CBS builder == the reference's pandas `elog2cbs` on the CDNOW event logs (counts and
+    day arithmetic exact, sums to 1e-12), events fed in shuffled order."""
+    import pandas as pd
+    from mcmc_clv_model_b200.cbs import elog2cbs
+    g = load_golden(f"elog_{name}.npz")
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(g["cust"].size)
+    elog = pd.DataFrame({"cust": g["cust"][perm], "date": pd.Timestamp("1970-01-01") + pd.to_timedelta(g["day"][perm].astype(np.int64), unit="D"),
+                         "sales": g["sales"][perm]})
+    cbs = elog2cbs(elog, units="W", T_cal="1997-09-30", T_tot="1998-06-30")
+    assert list(cbs.columns) == ["cust", "x", "t_x", "litt", "sales", "sales_x", "first", "T_cal", "T_star", "x_star", "sales_star"]
+    np.testing.assert_array_equal(cbs["cust"].to_numpy(), g["cbs_cust"])
+    np.testing.assert_array_equal(cbs["x"].to_numpy(), g["cbs_x"])
+    np.testing.assert_array_equal(cbs["x_star"].to_numpy(), g["cbs_x_star"])
+    np.testing.assert_array_equal(((cbs["first"] - pd.Timestamp("1970-01-01")) // pd.Timedelta(days=1)).to_numpy(), g["cbs_first"])
+    for c in ("t_x", "T_cal", "T_star"):
+        np.testing.assert_allclose(cbs[c].to_numpy(), g[f"cbs_{c}"], rtol=1e-14, atol=1e-14)
+    for c in ("litt", "sales", "sales_x", "sales_star"):
+        np.testing.assert_allclose(cbs[c].to_numpy(), g[f"cbs_{c}"], rtol=1e-12, atol=1e-10)
+    # no hold-out, no sales column
+    c2 = elog2cbs(elog[["cust", "date"]], units="D")
+    assert list(c2.columns) == ["cust", "x", "t_x", "litt", "sales", "sales_x", "first", "T_cal"] and (c2["sales"] == c2["x"] + 1).all()
