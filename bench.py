@@ -330,6 +330,15 @@ def run_ours(args):
                "wall_s": wall, "customer_updates_per_sec": 2357 * 4 * 14000 / wall, "min_ess_bulk": me_b,
                "min_ess_geyer": me_g, "ess_per_sec": me_g / wall,
                "reference_numpy_1core": {"wall_s": 653.6, "min_ess_geyer": 60, "ess_per_sec": 0.09, "source": "BASELINE.md §2"}}
+        # the same data with the GPU filled: 64 chains (the per-sweep latency barely changes, ESS adds up over chains)
+        t0 = time.perf_counter()
+        with Sampler(d["x"], d["t_x"], d["T_cal"], X1, model_dim=2, chains=64, n_mh_steps=20, seed=42, device=local) as s4:
+            o64 = s4.run(10000, 4000, 1, store_level1=False)
+        wall64 = time.perf_counter() - t0
+        g64 = min_ess(o64["level_2"], "geyer")
+        ess["wide"] = {"chains": 64, "wall_s": wall64, "customer_updates_per_sec": 2357 * 64 * 14000 / wall64,
+                       "min_ess_geyer": g64, "min_ess_bulk": min_ess(o64["level_2"], "bulk"), "ess_per_sec": g64 / wall64,
+                       "level_1": "not stored (level-2 draws only)"}
 
     # ---- forecast (C5-shaped): x*, P(alive) over customers x posterior draws, draws resident in HBM ----------------
     forecast = None
