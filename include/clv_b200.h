@@ -203,6 +203,10 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
                           double* p_alive, double* kernel_ms /* nullable: CUDA-event time of the kernel */);
 
 /* ---- analysis reductions on the resident draws (SURVEY 8f "next" rows) ---------------------- */
+/* Place host draws [chains][n_draws][n_local][4|5] (e.g. an unpickled "level_1" list, chain-major) into the handle's
+ * resident buffer, so that the reductions below / clv_forecast_resident can serve draws that were not produced by this
+ * handle.  Needs only clv_create (clv_forecast_resident additionally needs clv_set_data for T_cal). */
+int clv_upload_draws(clv_sampler* h, const double* level1, int64_t n_draws);
 #define CLV_SUMMARY_COLS 10
 /* Per-customer posterior summaries over all resident draws of all chains (post_mean_lambdas/mus and compute_table4,
  * src/models/utils/analysis_bi_helpers.py:15-27, 75-110): out [n_local][CLV_SUMMARY_COLS] =

@@ -90,6 +90,7 @@ SIGNATURES = {
     "clv_forecast_injected": (C.c_int, [C.POINTER(ForecastConfig), c_double_p, c_double_p, c_double_p, c_double_p,
                                         C.c_int64, c_int64_p, c_int64_p, c_double_p]),
     "clv_forecast_resident": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, c_int64_p, c_double_p, c_double_p, c_double_p]),
+    "clv_upload_draws": (C.c_int, [C.c_void_p, c_double_p, C.c_int64]),
     "clv_posterior_summary": (C.c_int, [C.c_void_p, C.c_double, c_double_p]),
     "clv_weekly_tracking": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int, C.c_uint64, c_double_p]),
     "clv_generate": (C.c_int, [C.POINTER(GenerateConfig), c_double_p, c_double_p, C.c_int, C.c_int, c_int32_p, c_double_p, c_double_p,

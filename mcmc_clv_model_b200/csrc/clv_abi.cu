@@ -1375,6 +1375,23 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
 }
 
 // ---- "next" rows on the resident draws -----------------------------------------------------------
+int clv_upload_draws(clv_sampler* h, const double* level1, int64_t n_draws) {
+  if (!h || !level1 || n_draws < 1) return fail(h, CLV_ERR_ARG, "clv_upload_draws: bad argument");
+  CK(h, cudaSetDevice(h->cfg.device));
+  const long long bytes = (long long)h->chains * n_draws * h->N * h->ncol * (long long)sizeof(double);
+  if (h->draws_cap_bytes[0] < bytes) {
+    if (h->d_draws[0]) cudaFree(h->d_draws[0]);
+    h->d_draws[0] = nullptr; h->draws_cap_bytes[0] = 0;
+    cudaError_t e = cudaMalloc((void**)&h->d_draws[0], (size_t)bytes);
+    if (e != cudaSuccess) return fail(h, CLV_ERR_CUDA, "cannot allocate %lld bytes for the draws: %s", bytes, cudaGetErrorString(e));
+    h->draws_cap_bytes[0] = bytes;
+  }
+  CK(h, cudaMemcpyAsync(h->d_draws[0], level1, (size_t)bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->resident_draws = n_draws;
+  return CLV_OK;
+}
+
 int clv_posterior_summary(clv_sampler* h, double mu_cap, double* out) {
   if (!h || !out) return fail(h, CLV_ERR_ARG, "null argument");
   if (h->resident_draws <= 0) return fail(h, CLV_ERR_STATE, "no resident draws: call clv_run (single device chunk) or clv_run_resident first");

@@ -422,3 +422,27 @@ def test_elog2cbs_vs_reference(name):
     # no hold-out, no sales column
     c2 = elog2cbs(elog[["cust", "date"]], units="D")
     assert list(c2.columns) == ["cust", "x", "t_x", "litt", "sales", "sales_x", "first", "T_cal"] and (c2["sales"] >= c2["x"] + 1).all()   # same-day events merge: sales counts events
+
+
+def test_analysis_helpers_on_a_draws_dict(cdnow_abe):
+    """The analysis reductions on an (unpickled-style) draws dict: upload once, reduce on the device; Table-4 columns
+    against the reference's formulas in NumPy (utils/analysis_bi_helpers.py:75-110)."""
+    import pandas as pd
+    from mcmc_clv_model_b200 import mcmc_draw_parameters
+    from mcmc_clv_model_b200.analysis import posterior_summary, table4_inputs, weekly_tracking
+    d = cdnow_abe
+    n = 250
+    cbs = pd.DataFrame({k: d[k][:n] for k in ("x", "t_x", "T_cal")})
+    draws = mcmc_draw_parameters(cbs, mcmc=40, burnin=30, thin=2, chains=3, seed=8, trace=0)
+    allv = np.concatenate(draws["level_1"], axis=0)
+    s = posterior_summary(draws)
+    np.testing.assert_allclose(s["mean_lambda"], allv[:, :, 0].mean(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(s["mu_97.5"], np.percentile(allv[:, :, 1], 97.5, axis=0), rtol=1e-12)
+    t4 = table4_inputs(draws)
+    mean_mu = np.clip(allv[:, :, 1], None, 0.05).mean(axis=0)
+    mean_z = allv[:, :, 3].mean(axis=0)
+    np.testing.assert_allclose(t4["Exp # of trans in val period"],
+                               mean_z * (allv[:, :, 0].mean(axis=0) / mean_mu) * (1 - np.exp(-mean_mu * 39)), rtol=1e-10)
+    inc = weekly_tracking(draws, np.zeros(n), np.arange(1.0, 30.0), seed=1)
+    expect = np.array([(allv[:, :, 0] * (t <= allv[:, :, 2])).sum(axis=1).mean() for t in np.arange(1.0, 30.0)])
+    assert np.all(np.abs(inc - expect) < 6 * np.sqrt(expect / allv.shape[0]) + 0.5)
