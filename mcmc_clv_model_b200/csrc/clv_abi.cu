@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -64,6 +65,7 @@ struct CachedMailbox {
 };
 std::vector<CachedMailbox> g_mailboxes;
 unsigned long long g_epoch = 0;     // process-wide: mailbox flags never repeat across handles
+std::mutex g_cache_mutex;           // guards g_comms / g_mailboxes / g_epoch (handles may live on different host threads)
 
 }  // namespace
 
@@ -667,7 +669,7 @@ int clv_init_state(clv_sampler* h, const clv_init_stats* st) {
   h->launches++;
   CK(h, cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
   h->inited = true;
-  h->init_epoch = ++g_epoch;
+  { std::lock_guard<std::mutex> lock(g_cache_mutex); h->init_epoch = ++g_epoch; }
   if (int r = recompute_stats(h)) return r;
   CK(h, cudaStreamSynchronize(h->stream));
   h->sweeps_done = 0;
@@ -703,6 +705,7 @@ int clv_comm_init(clv_sampler* h, const void* unique_id128, int rank, int world)
   if (!g_nccl.load(err)) return fail(h, CLV_ERR_COMM, "%s", err.c_str());
   CK(h, cudaSetDevice(h->cfg.device));
   h->world = world; h->rank = rank;
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
   for (auto& c : g_comms)
     if (c.device == h->cfg.device && c.rank == rank && c.world == world) { h->comm = c.comm; return CLV_OK; }
   NcclUid id;
@@ -722,6 +725,7 @@ static CachedMailbox* find_mailbox(const clv_sampler* h, int rank, int world) {
 int clv_p2p_export(clv_sampler* h, void* handle64) {
   if (!h || !handle64) return fail(h, CLV_ERR_ARG, "null argument");
   CK(h, cudaSetDevice(h->cfg.device));
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
   CachedMailbox* m = find_mailbox(h, 0, 0);
   if (!m) {
     CachedMailbox nm{};
@@ -747,6 +751,7 @@ int clv_p2p_export(clv_sampler* h, void* handle64) {
  * be called with handles == NULL (no handle exchange needed). */
 int clv_p2p_is_cached(clv_sampler* h, int rank, int world) {
   if (!h) return 0;
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
   CachedMailbox* m = find_mailbox(h, rank, world);
   return (m && m->connected) ? 1 : 0;
 }
@@ -756,6 +761,7 @@ int clv_p2p_connect(clv_sampler* h, const void* handles, int rank, int world) {
   if (world < 2 || world > P2P_MAX_WORLD || rank < 0 || rank >= world) return fail(h, CLV_ERR_ARG, "p2p: world must be in [2, %d]", P2P_MAX_WORLD);
   if (h->cfg.sweep_mode == CLV_SWEEP_PERSISTENT) return fail(h, CLV_ERR_ARG, "persistent sweep mode is single-shard only");
   CK(h, cudaSetDevice(h->cfg.device));
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
   CachedMailbox* m = find_mailbox(h, rank, world);
   if (!(m && m->connected)) {
     m = find_mailbox(h, 0, 0);
@@ -1516,6 +1522,7 @@ int clv_elog2cbs(int device, int64_t n_events, const int64_t* cust, const int32_
                  int32_t* x, double* t_x, double* litt, double* sales_out, double* sales_x, int32_t* first_day,
                  double* T_cal, double* T_star, int32_t* x_star, double* sales_star) {
   if (!cust || !day || !n_customers || n_events < 1) return fail(nullptr, CLV_ERR_ARG, "clv_elog2cbs: bad argument");
+  if (n_events >= (1ll << 31)) return fail(nullptr, CLV_ERR_ARG, "clv_elog2cbs: at most 2^31 - 1 events per call");
   if (!(unit_days > 0)) return fail(nullptr, CLV_ERR_ARG, "clv_elog2cbs: unit_days must be positive");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, CLV_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");

@@ -446,3 +446,25 @@ def test_analysis_helpers_on_a_draws_dict(cdnow_abe):
     inc = weekly_tracking(draws, np.zeros(n), np.arange(1.0, 30.0), seed=1)
     expect = np.array([(allv[:, :, 0] * (t <= allv[:, :, 2])).sum(axis=1).mean() for t in np.arange(1.0, 30.0)])
     assert np.all(np.abs(inc - expect) < 6 * np.sqrt(expect / allv.shape[0]) + 0.5)
+
+
+def test_exported_draw_z_and_draw_tau_blocks(cdnow_abe):
+    """`draw_z` / `draw_tau` of the reference's `__all__` (bi:193-227): same signature, same consumption of the NumPy
+    generator, arithmetic on the device; z bit-exact and tau to 1e-12 against the oracle driven by the same generator."""
+    import pandas as pd
+    from src.models.bivariate.mcmc import draw_tau, draw_z
+    d = cdnow_abe
+    n = 600
+    cbs = pd.DataFrame({k: d[k][:n] for k in ("x", "t_x", "T_cal")})
+    g = np.random.default_rng(3)
+    lam, mu = g.lognormal(-3.3, 1.0, n), g.lognormal(-3.5, 1.2, n)
+    z = draw_z(cbs, lam, mu, np.random.default_rng(10))
+    z_ref = ao.draw_z(d["t_x"][:n], d["T_cal"][:n], lam, mu, np.random.default_rng(10).random(n))
+    np.testing.assert_array_equal(z, z_ref)
+    tau = draw_tau(cbs, lam, mu, z, np.random.default_rng(11))
+    r = np.random.default_rng(11)
+    e, u = np.zeros(n), np.zeros(n)
+    e[z] = r.standard_exponential(int(z.sum()))
+    u[~z] = r.random(int((~z).sum()))
+    np.testing.assert_allclose(tau, ao.draw_tau(d["t_x"][:n], d["T_cal"][:n], lam, mu, z, e, u), rtol=1e-12)
+    assert np.all(tau[z] > d["T_cal"][:n][z])
