@@ -344,6 +344,8 @@ int clv_abi_version(void) { return CLV_ABI_VERSION; }
 
 const char* clv_last_error(const clv_sampler* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
 
+static int upload_rk();   // reciprocal tables of the Poisson inversions (constant memory, once per device)
+
 int clv_create(clv_sampler** out, const clv_config* cfg) {
   if (!out || !cfg) return fail(nullptr, CLV_ERR_ARG, "clv_create: null argument");
   *out = nullptr;
@@ -396,14 +398,11 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   CKC(cudaMemset(h->d_acc, 0, sizeof(unsigned long long) * C * NSTAT_MAX));
   CKC(cudaMemset(h->d_params, 0, sizeof(ChainParams) * C));
   {
-    double rk[RK_TABLE + 1];
-    rk[0] = 0.0;
-    for (int k = 1; k <= RK_TABLE; ++k) rk[k] = 1.0 / (double)k;
-    CKC(cudaMemcpyToSymbol(c_rk, rk, sizeof rk));
     double et[64];
     for (int j = 0; j < 64; ++j) et[j] = (double)exp2l((long double)j / 64.0L);
     CKC(cudaMemcpyToSymbol(c_exptab, et, sizeof et));
   }
+  if (upload_rk()) { h->err = g_last_error; return bail(CLV_ERR_CUDA); }
   // grid: a few resident waves of 128-thread blocks, grid-stride over customer tiles
   long long ntiles = (h->N + SWEEP_THREADS - 1) / SWEEP_THREADS;
   long long want = ((long long)h->sm_count * 32 + h->chains - 1) / h->chains;
@@ -1235,6 +1234,9 @@ static int upload_rk() {
   rk[0] = 0.0;
   for (int k = 1; k <= RK_TABLE; ++k) rk[k] = 1.0 / (double)k;
   cudaError_t e = cudaMemcpyToSymbol(c_rk, rk, sizeof rk);
+  std::vector<float> rkf(RKF_TABLE, 0.0f);
+  for (int k = 1; k < RKF_TABLE; ++k) rkf[k] = 1.0f / (float)k;
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_rkf, rkf.data(), sizeof(float) * RKF_TABLE);
   if (e != cudaSuccess) return fail(nullptr, CLV_ERR_CUDA, "cudaMemcpyToSymbol failed: %s", cudaGetErrorString(e));
   if (dev >= 0 && dev < 64) done[dev] = true;
   return 0;
@@ -1250,6 +1252,7 @@ int clv_forecast_dev(const clv_forecast_config* cfg, const double* level1_dev, c
   a.T_star = cfg->T_star; a.sigma_s = cfg->sigma_s; a.seed = cfg->seed;
   a.gid_offset = cfg->gid_offset; a.draw_offset = cfg->draw_offset;
   a.x_out = (long long*)x_star_dev; a.spend_out = cfg->simulate_spend ? spend_dev : nullptr;
+  a.rk = round_keys(cfg->seed);
   return launch_forecast(cfg, a, false, (cudaStream_t)stream);
 }
 
@@ -1316,6 +1319,7 @@ static int forecast_host(const clv_forecast_config* cfg, const double* level1, c
     a.seed = cfg->seed; a.gid_offset = cfg->gid_offset; a.draw_offset = c2.draw_offset;
     a.u = d_u[b]; a.eps = d_eps; a.eps_offset = d_off[b];
     a.x_out = d_x[b]; a.spend_out = want_spend ? d_sp[b] : nullptr;
+    a.rk = round_keys(cfg->seed);
     if ((rc = launch_forecast(&c2, a, inject, st[b]))) { cleanup(); return rc; }
     CKF(cudaMemcpyAsync(x_star + (size_t)d0 * N, d_x[b], (size_t)(n * N) * 8, cudaMemcpyDeviceToHost, st[b]));
     if (want_spend) CKF(cudaMemcpyAsync(spend + (size_t)d0 * N, d_sp[b], (size_t)(n * N) * 8, cudaMemcpyDeviceToHost, st[b]));
@@ -1352,6 +1356,7 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
   // resident layout [chains][nd][N][ncol] with cap == nd is exactly the chain-major (chains*nd, N, ncol) of bi:530-531
   a.level1 = h->d_draws[0]; a.T_cal = h->d_T; a.n_draws = C * nd; a.N = N; a.T_star = T_star; a.sigma_s = 0.5;
   a.seed = seed; a.gid_offset = h->cfg.gid_offset; a.draw_offset = 0; a.x_out = d_x; a.spend_out = nullptr;
+  a.rk = round_keys(seed);
   int gx = (int)std::min<long long>((N + 255) / 256, 65535);
   // enough (customer, draw-range) threads to fill the GPU ~8 times over
   const long long npairs = (C * nd + 1) / 2;
@@ -1360,8 +1365,13 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, h->stream);
   if (gy > 1) { cudaMemsetAsync(d_mx, 0, sizeof(double) * N, h->stream); cudaMemsetAsync(d_pa, 0, sizeof(double) * N, h->stream); }
-  if (h->ncol == 4) k_forecast_reduce<4><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa);
-  else k_forecast_reduce<5><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa);
+  if (h->ncol == 4) {
+    if (d_x) k_forecast_reduce<4, true><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa);
+    else k_forecast_reduce<4, false><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa);
+  } else {
+    if (d_x) k_forecast_reduce<5, true><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa);
+    else k_forecast_reduce<5, false><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa);
+  }
   k_scale<<<h->sm_count * 4, 256, 0, h->stream>>>(d_mx, d_pa, N, 1.0 / (double)(C * nd));
   h->launches++;
   cudaEventRecord(e1, h->stream);

@@ -11,6 +11,8 @@ namespace clv {
 
 constexpr int RK_TABLE = 64;
 __constant__ double c_rk[RK_TABLE + 1];   // c_rk[k] = 1.0 / k
+constexpr int RKF_TABLE = 1032;
+__constant__ float c_rkf[RKF_TABLE];      // c_rkf[k] = 1.0f / k (fp32 screen of the Poisson inversion)
 
 // Poisson draw by sequential CDF inversion from zero; arithmetic fixed to match
 // oracle/abe_oracle.py:poisson_inversion bit for bit.
@@ -30,26 +32,34 @@ __device__ __noinline__ long long poisson_inversion(double m, double u) {
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// The same map u -> k, screened in fp32: the chop-down runs on the FP32/SFU pipes from fp32 images (mf, uf) of the mean
-// and the uniform; the result is accepted only when uf is further than a guard band (>> the fp32 error of the running
-// CDF, of mf and of uf) from both neighbouring CDF values, otherwise the fp64 reference loop decides on the exact
-// (m, u) -- which are only computed then.  Hence the returned k ALWAYS equals poisson_inversion(m, u).
-template <typename ExactMU>
-__device__ __forceinline__ long long poisson_inversion_screened(float mf, float uf, ExactMU exact) {
+// The same map u -> k, screened in fp32: the chop-down runs on the FP32 pipe from fp32 images (mf, uf) of the mean and
+// the uniform, four CDF terms per trip and branch-free inside a trip (k = number of CDF values below u; the lanes of a
+// warp stay in lockstep, so the reciprocal 1/k is a uniform constant-bank operand).  The result is accepted only when
+// uf is further than a guard band (>> the fp32 error of the running CDF, of mf and of uf) from both neighbouring CDF
+// values; otherwise `exact()` decides on the fp64 quantities -- which are only built then.  Hence the returned k ALWAYS
+// equals poisson_inversion(m, u).
+template <typename Exact>
+__device__ __forceinline__ long long poisson_inversion_screened(float mf, float uf, Exact exact) {
   if (mf >= 0.0f && mf < 60.0f) {
-    float p = ex2_ftz(-1.4426950408889634f * mf), cdf = p, prev = -1.0f, kf = 0.0f;
-    while (uf > cdf && kf < 1024.0f) {
-      kf += 1.0f;
-      prev = cdf;
-      p = (p * mf) * rcp_ftz(kf);
-      cdf += p;
+    float p = ex2_ftz(-1.4426950408889634f * mf), cdf = p, prev = -1.0f;
+    int k = 0, base = 0;
+    bool searching = uf > cdf;
+    while (searching && base < 1024) {
+#pragma unroll
+      for (int j = 1; j <= 4; ++j) {
+        const bool gt = uf > cdf;            // cdf == CDF(k): still below u?
+        prev = gt ? cdf : prev;
+        k += gt ? 1 : 0;
+        p = (p * mf) * c_rkf[base + j];
+        cdf = gt ? cdf + p : cdf;            // frozen at CDF(k) once found
+      }
+      base += 4;
+      searching = uf > cdf;
     }
     const float tol = 2e-6f * (8.0f + mf);
-    if (uf < cdf - tol && uf > prev + tol && kf < 1024.0f) return (long long)kf;
+    if (!searching && uf < cdf - tol && uf > prev + tol) return (long long)k;
   }
-  double m, u;
-  exact(m, u);
-  return poisson_inversion(m, u);
+  return exact();
 }
 
 // Large means (production path only): Hoermann's transformed rejection "PTRS" (the algorithm NumPy uses for lam >= 10),
@@ -93,6 +103,7 @@ struct ForecastArgs {
   const long long* eps_offset;   // [n_draws][N]
   long long* x_out;              // [n_draws][N] (nullable)
   double* spend_out;             // [n_draws][N] (nullable)
+  PhiloxRoundKeys rk;            // round keys of `seed` (launch constants; filled by the host)
 };
 
 // Forecast uniforms: one Philox block serves the two draws 2g, 2g+1 of a customer (global draw index, chain-major):
@@ -112,22 +123,34 @@ __device__ __forceinline__ void load_row(const double* row, double& lam, double&
   }
 }
 
-// x* of one (draw, customer) cell (bi:535-543).  The fp32 images feed the screen; the exact fp64 mean
-// lambda * clip(tau - T_cal, 0, T_star) and the 53-bit uniform are built only if the screen hands over.
-__device__ __forceinline__ long long forecast_cell(double lam, double tau, double zf, double T, double T_star, float T_star_f,
-                                                   uint32_t ua, uint32_t ub, uint32_t gid, uint32_t gdraw, PhiloxKey key) {
-  const bool alive = zf > 0.5;
-  const float hf = alive ? T_star_f : fminf(fmaxf((float)(tau - T), 0.0f), T_star_f);
-  const float mf = (float)lam * hf;
-  if (mf >= 59.0f) {                  // near or beyond the switch: decide on the exact mean
-    const double m = lam * future_horizon(T, tau, zf, T_star);
-    if (m >= PTRS_MIN_MEAN) return poisson_ptrs(m, gid, gdraw, key);
-  }
-  const float uf = u24f(ua);          // |uf - u53(ua, ub)| <= 2^-24
-  return poisson_inversion_screened(mf, uf, [&](double& m, double& u) {
-    m = lam * future_horizon(T, tau, zf, T_star);
-    u = u53(ua, ub);
-  });
+// Slow path of a cell: exact fp64 mean lambda * clip(tau - T_cal, 0, T_star) re-read from the level-1 row, then PTRS for
+// large means or the fp64 inversion on the 53-bit uniform.  Out of line: keeps the fast path's register count low.
+__device__ __noinline__ long long forecast_cell_slow(const double* row, double T, double T_star, uint32_t ua, uint32_t ub,
+                                                     uint32_t gid, uint32_t gdraw, PhiloxKey key) {
+  const double lam = row[0], tau = row[2], zf = row[3];
+  const double m = lam * future_horizon(T, tau, zf, T_star);
+  if (m >= PTRS_MIN_MEAN) return poisson_ptrs(m, gid, gdraw, key);
+  return poisson_inversion(m, u53(ua, ub));
+}
+
+// x* of one (draw, customer) cell (bi:535-543) from the fp32 images of its row.
+__device__ __forceinline__ long long forecast_cell(const double* row, float lamf, float dtf, bool alive, double T, double T_star,
+                                                   float T_star_f, uint32_t ua, uint32_t ub, uint32_t gid, uint32_t gdraw,
+                                                   PhiloxKey key) {
+  const float hf = alive ? T_star_f : fminf(fmaxf(dtf, 0.0f), T_star_f);
+  const float mf = lamf * hf;
+  if (!(mf < 59.0f)) return forecast_cell_slow(row, T, T_star, ua, ub, gid, gdraw, key);   // near / beyond the PTRS switch, NaN
+  return poisson_inversion_screened(mf, u24f(ua), [&]() { return forecast_cell_slow(row, T, T_star, ua, ub, gid, gdraw, key); });
+}
+
+// fp32 images of a level-1 row: lambda, tau - T_cal, alive
+template <int NCOL>
+__device__ __forceinline__ void load_row_f32(const double* row, double T, float& lamf, float& dtf, bool& alive) {
+  double lam, tau, zf, eta;
+  load_row<NCOL>(row, lam, tau, zf, eta);
+  lamf = (float)lam;
+  dtf = (float)(tau - T);
+  alive = zf > 0.5;
 }
 
 // One thread per (customer, pair of draws): x* (and spend) for every cell.
@@ -143,7 +166,7 @@ __global__ void __launch_bounds__(256) k_forecast(ForecastArgs a) {
       const uint32_t gid = (uint32_t)(a.gid_offset + i);
       const double T = a.T_cal[i];
       uint4 r = make_uint4(0, 0, 0, 0);
-      if (!INJECT) r = philox4x32_10(gid, (uint32_t)gp, 0u, DOM_FORECAST, key);
+      if (!INJECT) r = philox4x32_10_rk(gid, (uint32_t)gp, 0u, DOM_FORECAST, a.rk);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const long long gdraw = 2 * gp + h, d = gdraw - a.draw_offset;
@@ -152,16 +175,17 @@ __global__ void __launch_bounds__(256) k_forecast(ForecastArgs a) {
         double lam, tau, zf, eta;
         load_row<NCOL>(a.level1 + cell * NCOL, lam, tau, zf, eta);
         long long xs;                                                         // bi:543
+        const bool alive = zf > 0.5;
+        const float dtf = (float)(tau - T);
         if (INJECT) {
           const double u = a.u[cell];
-          const bool alive = zf > 0.5;
-          const float hf = alive ? T_star_f : fminf(fmaxf((float)(tau - T), 0.0f), T_star_f);
-          xs = poisson_inversion_screened((float)lam * hf, (float)u, [&](double& m, double& uu) {
-            m = lam * future_horizon(T, tau, zf, a.T_star);
-            uu = u;
+          const float hf = alive ? T_star_f : fminf(fmaxf(dtf, 0.0f), T_star_f);
+          xs = poisson_inversion_screened((float)lam * hf, (float)u, [&]() {
+            return poisson_inversion(lam * future_horizon(T, tau, zf, a.T_star), u);
           });
         } else {
-          xs = forecast_cell(lam, tau, zf, T, a.T_star, T_star_f, h ? r.z : r.x, h ? r.w : r.y, gid, (uint32_t)gdraw, key);
+          xs = forecast_cell(a.level1 + cell * NCOL, (float)lam, dtf, alive, T, a.T_star, T_star_f, h ? r.z : r.x, h ? r.w : r.y,
+                             gid, (uint32_t)gdraw, key);
         }
         if (a.x_out) __stcs(&a.x_out[cell], xs);
         if (spend) {
@@ -185,16 +209,16 @@ __global__ void __launch_bounds__(256) k_forecast(ForecastArgs a) {
 }
 
 // Fused reductions over the draws still resident in HBM (draw_offset == 0): per customer sum of x* and of z
-// (P(alive) = mean z, analysis_bi_helpers.py:98), x* optionally materialised.  blockIdx.y splits the draw pairs;
-// partial sums are integers, so the atomicAdd order does not matter.  6 resident blocks per SM (40 registers, a few
-// spills): the kernel is latency bound and occupancy beats register comfort (2.8 -> 3.45 TB/s measured).
-template <int NCOL>
+// (P(alive) = mean z, analysis_bi_helpers.py:98), x* optionally materialised (WRITE_X).  blockIdx.y splits the draw
+// pairs; partial sums are integers, so the atomicAdd order does not matter.  6 resident blocks per SM: the kernel is
+// latency bound and occupancy beats register comfort.
+template <int NCOL, bool WRITE_X>
 __global__ void __launch_bounds__(256, 6) k_forecast_reduce(ForecastArgs a, double* sum_x, double* sum_z) {
   const PhiloxKey key = seed_key(a.seed);
   const float T_star_f = (float)a.T_star;
-  const long long npairs = (a.n_draws + 1) >> 1;
-  const long long per = (npairs + gridDim.y - 1) / gridDim.y;
-  const long long pa = (long long)blockIdx.y * per, pb = min(npairs, pa + per);
+  const int npairs = (int)((a.n_draws + 1) >> 1);
+  const int per = (npairs + gridDim.y - 1) / gridDim.y;
+  const int pa = blockIdx.y * per, pb = min(npairs, pa + per);
   const long long stride = a.N * NCOL;                 // doubles between consecutive draws of one customer
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.N;
        i += (long long)gridDim.x * blockDim.x) {
@@ -202,25 +226,24 @@ __global__ void __launch_bounds__(256, 6) k_forecast_reduce(ForecastArgs a, doub
     const uint32_t gid = (uint32_t)(a.gid_offset + i);
     long long sx = 0;
     int sz = 0;
-    const double* row = a.level1 + (2 * pa * a.N + i) * NCOL;
-    long long* xo = a.x_out ? a.x_out + 2 * pa * a.N + i : nullptr;
-    for (long long gp = pa; gp < pb; ++gp, row += 2 * stride) {
-      const bool v1 = 2 * gp + 1 < a.n_draws;          // only the very last pair can be half empty
-      double lam0, tau0, z0, e0, lam1 = 0.0, tau1 = 0.0, z1 = 0.0, e1;
-      load_row<NCOL>(row, lam0, tau0, z0, e0);          // both rows in flight before the arithmetic starts
-      if (v1) load_row<NCOL>(row + stride, lam1, tau1, z1, e1);
-      const uint4 r = philox4x32_10(gid, (uint32_t)gp, 0u, DOM_FORECAST, key);
-      const long long x0 = forecast_cell(lam0, tau0, z0, T, a.T_star, T_star_f, r.x, r.y, gid, (uint32_t)(2 * gp), key);
+    const double* row = a.level1 + (2ll * pa * a.N + i) * NCOL;
+    for (int gp = pa; gp < pb; ++gp, row += 2 * stride) {
+      const bool v1 = 2ll * gp + 1 < a.n_draws;        // only the very last pair can be half empty
+      float lam0, dt0, lam1 = 0.0f, dt1 = 0.0f;
+      bool al0, al1 = false;
+      load_row_f32<NCOL>(row, T, lam0, dt0, al0);        // both rows in flight before the arithmetic starts
+      if (v1) load_row_f32<NCOL>(row + stride, T, lam1, dt1, al1);
+      const uint4 r = philox4x32_10_rk(gid, (uint32_t)gp, 0u, DOM_FORECAST, a.rk);
+      const long long x0 = forecast_cell(row, lam0, dt0, al0, T, a.T_star, T_star_f, r.x, r.y, gid, 2u * gp, key);
       sx += x0;
-      sz += (z0 > 0.5) ? 1 : 0;
-      if (xo) { __stcs(xo, x0); }
+      sz += al0 ? 1 : 0;
+      if (WRITE_X) __stcs(a.x_out + (2ll * gp) * a.N + i, x0);
       if (v1) {
-        const long long x1 = forecast_cell(lam1, tau1, z1, T, a.T_star, T_star_f, r.z, r.w, gid, (uint32_t)(2 * gp + 1), key);
+        const long long x1 = forecast_cell(row + stride, lam1, dt1, al1, T, a.T_star, T_star_f, r.z, r.w, gid, 2u * gp + 1u, key);
         sx += x1;
-        sz += (z1 > 0.5) ? 1 : 0;
-        if (xo) __stcs(xo + a.N, x1);
+        sz += al1 ? 1 : 0;
+        if (WRITE_X) __stcs(a.x_out + (2ll * gp + 1) * a.N + i, x1);
       }
-      if (xo) xo += 2 * a.N;
     }
     if (gridDim.y == 1) {
       sum_x[i] = (double)sx;
@@ -344,7 +367,7 @@ __global__ void __launch_bounds__(256) k_weekly_tracking(const double* level1, l
         const uint32_t word = (w & 3) == 0 ? r.x : (w & 3) == 1 ? r.y : (w & 3) == 2 ? r.z : r.w;
         long long inc;
         if (lam >= PTRS_MIN_MEAN) inc = poisson_ptrs(lam, gid, (uint32_t)d, key, 65536u + 64u * (uint32_t)w);
-        else inc = poisson_inversion_screened(lamf, u24f(word), [&](double& m, double& u) { m = lam; u = u32d(word); });
+        else inc = poisson_inversion_screened(lamf, u24f(word), [&]() { return poisson_inversion(lam, u32d(word)); });
         if (inc) atomicAdd(&s_week[w], (unsigned long long)inc);
       }
     }
