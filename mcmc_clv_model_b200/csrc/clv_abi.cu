@@ -146,8 +146,42 @@ int fail(clv_sampler* h, int code, const char* fmt, ...) {
       return fail(h, CLV_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// Device memory comes from the device's default stream-ordered pool with an unlimited release threshold: what a
+// handle frees stays cached in the process, so a sampler call does not pay cudaMalloc/cudaFree (measured: up to 1.5 s of
+// driver time per call for the GB-sized buffers of a 10 M-customer run) every time.  (The peer mailboxes stay on
+// cudaMalloc: CUDA IPC needs it.)
+thread_local cudaStream_t t_alloc_stream = nullptr;   // stream the calling API function allocates / frees on
+
+void ensure_pool(int dev) {
+  static bool done[64] = {false};
+  if (dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done[dev] = true;
+}
+
+// bytes a pool allocation can still obtain: free device memory plus what the pool holds but does not use
+size_t available_bytes(int dev) {
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 0;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long reserved = 0, used = 0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+      free_b += (size_t)(reserved - used);
+  }
+  return free_b;
+}
+
+cudaError_t pool_malloc(void** p, size_t bytes) { return cudaMallocAsync(p, std::max<size_t>(bytes, 8), t_alloc_stream); }
+cudaError_t dfree(void* p) { return p ? cudaFreeAsync(p, t_alloc_stream) : cudaSuccess; }
+
 template <typename T>
-cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
+cudaError_t dmalloc(T** p, size_t n) { return pool_malloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
 
 // ---- small dense host linear algebra (K <= 16) ------------------------------------------------
 bool chol_host(const double* A, double* L, int n) {
@@ -375,6 +409,8 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   h->sm_count = prop.multiProcessorCount;
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  t_alloc_stream = h->stream;
+  ensure_pool(cfg->device);
   for (int b = 0; b < 2; ++b) {
     CKC(cudaEventCreateWithFlags(&h->ev_chunk_ready[b], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_copy_done[b], cudaEventDisableTiming));
@@ -394,6 +430,7 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   CKC(dmalloc(&h->d_tau, C * N));
   CKC(dmalloc(&h->d_acc, C * NSTAT_MAX));
   CKC(dmalloc(&h->d_err, 1));
+  CKC(cudaStreamSynchronize(h->stream));      // pool allocations are stream ordered; the memsets below use the legacy stream
   CKC(cudaMemset(h->d_err, 0, sizeof(int)));
   CKC(cudaMemset(h->d_acc, 0, sizeof(unsigned long long) * C * NSTAT_MAX));
   CKC(cudaMemset(h->d_params, 0, sizeof(ChainParams) * C));
@@ -425,6 +462,7 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   // persistent cooperative mode: all blocks must be co-resident
   CKC(dmalloc(&h->d_acc3, 3 * C * NSTAT_MAX));
   CKC(dmalloc(&h->d_barrier, 2));
+  CKC(cudaStreamSynchronize(h->stream));
   CKC(cudaMemset(h->d_barrier, 0, 2 * sizeof(unsigned int)));
   {
     int coop = 0, per_sm = 0;
@@ -446,18 +484,21 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
 void clv_destroy(clv_sampler* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
+  t_alloc_stream = h->stream;
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-  if (h->d_acc3) cudaFree(h->d_acc3);
-  if (h->d_barrier) cudaFree(h->d_barrier);
+  if (h->d_acc3) dfree(h->d_acc3);
+  if (h->d_barrier) dfree(h->d_barrier);
   void* ptrs[] = {h->d_mc, h->d_params, h->d_x, h->d_tx, h->d_T, h->d_Xc, h->d_logs, h->d_ll, h->d_lm, h->d_le,
                   h->d_z, h->d_tau, h->d_acc, h->d_err, h->d_loglik, h->d_level2, h->d_draws[0], h->d_draws[1], h->d_inj};
-  for (void* p : ptrs) if (p) cudaFree(p);
+  for (void* p : ptrs) if (p) dfree(p);
   for (int b = 0; b < 2; ++b) {
     if (h->ev_chunk_ready[b]) cudaEventDestroy(h->ev_chunk_ready[b]);
     if (h->ev_copy_done[b]) cudaEventDestroy(h->ev_copy_done[b]);
   }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
+  if (h->stream) cudaStreamSynchronize(h->stream);   // the frees above are stream ordered
+  t_alloc_stream = nullptr;
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -468,7 +509,7 @@ int clv_set_data(clv_sampler* h, const int32_t* x, const double* t_x, const doub
   if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
   if (!x || !t_x || !T_cal || !X) return fail(h, CLV_ERR_ARG, "clv_set_data: null column");
   if (h->D == 3 && !log_s) return fail(h, CLV_ERR_ARG, "clv_set_data: log_s is required for the trivariate model");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   const size_t N = (size_t)h->N;
   CK(h, cudaMemcpyAsync(h->d_x, x, N * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->d_tx, t_x, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -484,10 +525,10 @@ int clv_set_data(clv_sampler* h, const int32_t* x, const double* t_x, const doub
       h->launches++;
       e = cudaGetLastError();
     }
-    if (e != cudaSuccess) { cudaFree(d_rows); return fail(h, CLV_ERR_CUDA, "design-matrix upload failed: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { dfree(d_rows); return fail(h, CLV_ERR_CUDA, "design-matrix upload failed: %s", cudaGetErrorString(e)); }
   }
   cudaError_t es = cudaStreamSynchronize(h->stream);
-  if (d_rows) cudaFree(d_rows);
+  if (d_rows) dfree(d_rows);
   if (es != cudaSuccess) return fail(h, CLV_ERR_CUDA, "clv_set_data failed: %s", cudaGetErrorString(es));
   h->have_data = true;
   h->inited = false;
@@ -585,8 +626,8 @@ static int device_init_stats(clv_sampler* h, clv_init_stats* out, std::vector<do
     out->omega2 = (D == 3) ? tot[1] / (n - 1.0) : 1.0;
     out->xtx = xtx.data();
   }
-  cudaFree(d_max);
-  cudaFree(d_sum);
+  dfree(d_max);
+  dfree(d_sum);
   return rc;
 }
 
@@ -596,7 +637,7 @@ int clv_init_state(clv_sampler* h, const clv_init_stats* st) {
   clv_init_stats computed{};
   std::vector<double> xtx_buf;
   if (!st) {
-    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
     if (int r = device_init_stats(h, &computed, xtx_buf)) return r;
     st = &computed;
     h->last_stats = computed;
@@ -605,7 +646,7 @@ int clv_init_state(clv_sampler* h, const clv_init_stats* st) {
   if (!st->xtx) return fail(h, CLV_ERR_ARG, "clv_init_state: stats without xtx");
   if (!(st->lam_init > 0.0) || !std::isfinite(st->lam_init) || !(st->mean_mu_init > 0.0))
     return fail(h, CLV_ERR_NUMERIC, "clv_init_state: lam_init / mean_mu_init must be positive and finite");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   const int K = h->K, D = h->D;
   ModelConst& mc = h->h_mc;
   std::memset(&mc, 0, sizeof mc);
@@ -702,7 +743,7 @@ int clv_comm_init(clv_sampler* h, const void* unique_id128, int rank, int world)
   if (h->cfg.sweep_mode == CLV_SWEEP_PERSISTENT) return fail(h, CLV_ERR_ARG, "persistent sweep mode is single-shard only");
   std::string err;
   if (!g_nccl.load(err)) return fail(h, CLV_ERR_COMM, "%s", err.c_str());
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   h->world = world; h->rank = rank;
   std::lock_guard<std::mutex> lock(g_cache_mutex);
   for (auto& c : g_comms)
@@ -723,7 +764,7 @@ static CachedMailbox* find_mailbox(const clv_sampler* h, int rank, int world) {
 
 int clv_p2p_export(clv_sampler* h, void* handle64) {
   if (!h || !handle64) return fail(h, CLV_ERR_ARG, "null argument");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   std::lock_guard<std::mutex> lock(g_cache_mutex);
   CachedMailbox* m = find_mailbox(h, 0, 0);
   if (!m) {
@@ -759,7 +800,7 @@ int clv_p2p_connect(clv_sampler* h, const void* handles, int rank, int world) {
   if (!h) return fail(h, CLV_ERR_ARG, "null argument");
   if (world < 2 || world > P2P_MAX_WORLD || rank < 0 || rank >= world) return fail(h, CLV_ERR_ARG, "p2p: world must be in [2, %d]", P2P_MAX_WORLD);
   if (h->cfg.sweep_mode == CLV_SWEEP_PERSISTENT) return fail(h, CLV_ERR_ARG, "persistent sweep mode is single-shard only");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   std::lock_guard<std::mutex> lock(g_cache_mutex);
   CachedMailbox* m = find_mailbox(h, rank, world);
   if (!(m && m->connected)) {
@@ -793,7 +834,7 @@ int64_t clv_kernel_launches(const clv_sampler* h) { return h ? h->launches : -1;
 
 int clv_set_timing(clv_sampler* h, int on) {
   if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   CK(h, cudaStreamSynchronize(h->stream));
   collect_timing(h);
   h->timing = on != 0;
@@ -803,7 +844,7 @@ int clv_set_timing(clv_sampler* h, int on) {
 
 int clv_kernel_time_ms(clv_sampler* h, double* sweep_ms, double* l2_ms, int64_t* n) {
   if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   CK(h, cudaStreamSynchronize(h->stream));
   collect_timing(h);
   if (sweep_ms) *sweep_ms = h->t_sweep_ms;
@@ -909,7 +950,7 @@ int clv_advance(clv_sampler* h, int64_t n_sweeps, int sync) {
   if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
   if (!h->inited) return fail(h, CLV_ERR_STATE, "clv_advance: call clv_init_state first");
   if (h->cfg.rng_mode == CLV_RNG_INJECTED) return fail(h, CLV_ERR_ARG, "handle is in injected-RNG mode; use clv_sweep_injected");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   RunCtx rc;
   // cooperative launches are bounded so that a runaway kernel cannot outlive the watchdog of a shared box
   for (int64_t done = 0; done < n_sweeps;) {
@@ -924,7 +965,7 @@ int clv_advance(clv_sampler* h, int64_t n_sweeps, int sync) {
 int clv_advance_timed(clv_sampler* h, int64_t n_sweeps, double* elapsed_ms) {
   if (!h || !elapsed_ms) return fail(h, CLV_ERR_ARG, "null argument");
   if (!h->inited) return fail(h, CLV_ERR_STATE, "clv_advance_timed: call clv_init_state first");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   cudaEvent_t e0, e1;
   CK(h, cudaEventCreate(&e0));
   CK(h, cudaEventCreate(&e1));
@@ -946,13 +987,13 @@ int clv_advance_timed(clv_sampler* h, int64_t n_sweeps, double* elapsed_ms) {
 static int ensure_run_buffers(clv_sampler* h, long long n_draws, bool want_level1, long long* chunk_cap) {
   const long long C = h->chains;
   if (h->loglik_cap < C * n_draws) {
-    if (h->d_loglik) cudaFree(h->d_loglik);
+    if (h->d_loglik) dfree(h->d_loglik);
     h->d_loglik = nullptr;
     CK(h, dmalloc(&h->d_loglik, (size_t)(C * n_draws)));
     h->loglik_cap = C * n_draws;
   }
   if (h->level2_cap < C * n_draws * h->P) {
-    if (h->d_level2) cudaFree(h->d_level2);
+    if (h->d_level2) dfree(h->d_level2);
     h->d_level2 = nullptr;
     CK(h, dmalloc(&h->d_level2, (size_t)(C * n_draws * h->P)));
     h->level2_cap = C * n_draws * h->P;
@@ -961,8 +1002,7 @@ static int ensure_run_buffers(clv_sampler* h, long long n_draws, bool want_level
   *chunk_cap = 0;
   if (!want_level1) return 0;
   const long long per_draw = C * h->N * h->ncol * (long long)sizeof(double);
-  size_t free_b = 0, total_b = 0;
-  CK(h, cudaMemGetInfo(&free_b, &total_b));
+  const size_t free_b = available_bytes(h->cfg.device);
   long long have = h->draws_cap_bytes[0] + h->draws_cap_bytes[1];
   long long budget = (long long)((double)(free_b + have) * 0.70);
   if (const char* env = getenv("CLV_DRAW_BUFFER_BYTES")) budget = std::min(budget, atoll(env));
@@ -975,9 +1015,9 @@ static int ensure_run_buffers(clv_sampler* h, long long n_draws, bool want_level
   for (int b = 0; b < 2; ++b) {
     long long need = (b < nbuf) ? cap * per_draw : 0;
     if (h->draws_cap_bytes[b] < need) {
-      if (h->d_draws[b]) cudaFree(h->d_draws[b]);
+      if (h->d_draws[b]) dfree(h->d_draws[b]);
       h->d_draws[b] = nullptr; h->draws_cap_bytes[b] = 0;
-      cudaError_t e = cudaMalloc((void**)&h->d_draws[b], (size_t)need);
+      cudaError_t e = pool_malloc((void**)&h->d_draws[b], (size_t)need);
       if (e != cudaSuccess) return fail(h, CLV_ERR_CUDA, "cannot allocate %lld bytes for the draw buffer: %s", need, cudaGetErrorString(e));
       h->draws_cap_bytes[b] = need;
     }
@@ -993,7 +1033,7 @@ static int run_impl(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, 
   if (h->cfg.rng_mode == CLV_RNG_INJECTED) return fail(h, CLV_ERR_ARG, "handle is in injected-RNG mode; use clv_sweep_injected");
   if (burnin < 0 || mcmc < 1 || thin < 1) return fail(h, CLV_ERR_ARG, "clv_run: need burnin >= 0, mcmc >= 1, thin >= 1");
   if (!level2) return fail(h, CLV_ERR_ARG, "clv_run: level2 output is required");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   const long long n_draws = (mcmc - 1) / thin + 1;      // bi:360
   const long long C = h->chains, N = h->N, nc = h->ncol;
   long long cap = 0;
@@ -1085,7 +1125,7 @@ int clv_get_state(clv_sampler* h, int chain, double* ll, double* lm, double* le,
   if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
   if (!h->inited) return fail(h, CLV_ERR_STATE, "state not initialised");
   if (chain < 0 || chain >= h->chains) return fail(h, CLV_ERR_ARG, "chain out of range");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   CK(h, cudaStreamSynchronize(h->stream));
   const size_t N = (size_t)h->N, o = (size_t)chain * N;
   if (ll) CK(h, cudaMemcpy(ll, h->d_ll + o, N * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1107,7 +1147,7 @@ int clv_set_state(clv_sampler* h, int chain, const double* ll, const double* lm,
   if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
   if (!h->inited) return fail(h, CLV_ERR_STATE, "state not initialised");
   if (chain < 0 || chain >= h->chains) return fail(h, CLV_ERR_ARG, "chain out of range");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   CK(h, cudaStreamSynchronize(h->stream));
   const size_t N = (size_t)h->N, o = (size_t)chain * N;
   // the sweep kernel's exp is exact on the clip range of bi:323-324 and well defined up to +-700: reject anything else
@@ -1142,12 +1182,12 @@ int clv_sweep_injected(clv_sampler* h, const clv_injected* v, int keep, double* 
   if (!v->u_z || !v->e_tau || !v->u_tau || !v->iw_chi2 || !v->beta_norm || (S > 0 && (!v->t3_l || !v->t3_m || !v->u_acc)) ||
       (D == 3 && !v->n_eta) || !v->iw_norm)
     return fail(h, CLV_ERR_ARG, "clv_sweep_injected: missing variate array");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   const long long C = h->chains, N = h->N;
   const long long n_cn = C * N, n_csn = C * S * N, ntril = D * (D - 1) / 2;
   const long long tot = 3 * n_cn + 3 * n_csn + (D == 3 ? n_cn : 0) + C * (ntril + D + D * K);
   if (h->inj_cap < tot) {
-    if (h->d_inj) cudaFree(h->d_inj);
+    if (h->d_inj) dfree(h->d_inj);
     h->d_inj = nullptr;
     CK(h, dmalloc(&h->d_inj, (size_t)tot));
     h->inj_cap = tot;
@@ -1245,7 +1285,7 @@ static int upload_rk() {
 int clv_forecast_dev(const clv_forecast_config* cfg, const double* level1_dev, const double* T_cal_dev,
                      int64_t* x_star_dev, double* spend_dev, void* stream) {
   if (int r = check_fc(cfg)) return r;
-  CK(nullptr, cudaSetDevice(cfg->device));
+  CK(nullptr, cudaSetDevice(cfg->device)); t_alloc_stream = nullptr; ensure_pool(cfg->device);
   if (int r = upload_rk()) return r;
   ForecastArgs a{};
   a.level1 = level1_dev; a.T_cal = T_cal_dev; a.n_draws = cfg->n_draws_total; a.N = cfg->n_customers;
@@ -1265,11 +1305,10 @@ static int forecast_host(const clv_forecast_config* cfg, const double* level1, c
   if (inject && !u) return fail(nullptr, CLV_ERR_ARG, "clv_forecast_injected: u is required");
   const bool want_spend = cfg->simulate_spend && cfg->ncol == 5 && spend;
   if (inject && want_spend && (!eps || !eps_offset)) return fail(nullptr, CLV_ERR_ARG, "clv_forecast_injected: eps/eps_offset required for spend");
-  CK(nullptr, cudaSetDevice(cfg->device));
+  CK(nullptr, cudaSetDevice(cfg->device)); t_alloc_stream = nullptr; ensure_pool(cfg->device);
   if (int r = upload_rk()) return r;
   const long long N = cfg->n_customers, nd = cfg->n_draws_total, nc = cfg->ncol;
-  size_t free_b = 0, total_b = 0;
-  CK(nullptr, cudaMemGetInfo(&free_b, &total_b));
+  const size_t free_b = available_bytes(cfg->device);
   const long long per_draw = N * (nc * 8 + 8 + (want_spend ? 8 : 0) + (inject ? 16 : 0));
   long long chunk = std::max<long long>(1, std::min<long long>(nd, (long long)(free_b * 0.35) / std::max<long long>(1, per_draw)));
   chunk = std::min<long long>(chunk, std::max<long long>(1, (1ll << 28) / std::max<long long>(1, N * nc * 8)));  // ~256 MB pieces pipeline well
@@ -1279,15 +1318,15 @@ static int forecast_host(const clv_forecast_config* cfg, const double* level1, c
   int rc = 0;
   auto cleanup = [&]() {
     for (int b = 0; b < 2; ++b) {
-      if (d_l1[b]) cudaFree(d_l1[b]);
-      if (d_sp[b]) cudaFree(d_sp[b]);
-      if (d_u[b]) cudaFree(d_u[b]);
-      if (d_x[b]) cudaFree(d_x[b]);
-      if (d_off[b]) cudaFree(d_off[b]);
+      if (d_l1[b]) dfree(d_l1[b]);
+      if (d_sp[b]) dfree(d_sp[b]);
+      if (d_u[b]) dfree(d_u[b]);
+      if (d_x[b]) dfree(d_x[b]);
+      if (d_off[b]) dfree(d_off[b]);
       cudaStreamDestroy(st[b]);
     }
-    if (d_T) cudaFree(d_T);
-    if (d_eps) cudaFree(d_eps);
+    if (d_T) dfree(d_T);
+    if (d_eps) dfree(d_eps);
   };
   for (int b = 0; b < 2; ++b) cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking);
 #define CKF(call) do { cudaError_t e3 = (call); if (e3 != cudaSuccess) { rc = fail(nullptr, CLV_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e3)); cleanup(); return rc; } } while (0)
@@ -1303,6 +1342,7 @@ static int forecast_host(const clv_forecast_config* cfg, const double* level1, c
     CKF(dmalloc(&d_eps, (size_t)n_eps));
     CKF(cudaMemcpy(d_eps, eps, (size_t)n_eps * 8, cudaMemcpyHostToDevice));
   }
+  CKF(cudaStreamSynchronize(nullptr));          // pool allocations were ordered on the legacy stream; they are used on st[]
   int b = 0;
   for (long long d0 = 0; d0 < nd; d0 += chunk, b ^= 1) {
     const long long n = std::min(chunk, nd - d0);
@@ -1344,7 +1384,7 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
                           double* kernel_ms) {
   if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
   if (h->resident_draws <= 0) return fail(h, CLV_ERR_STATE, "no resident draws: run clv_run with a level1 buffer that fits in one device chunk");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   if (int r = upload_rk()) return r;
   const long long C = h->chains, nd = h->resident_draws, N = h->N;
   double *d_mx = nullptr, *d_pa = nullptr;
@@ -1384,8 +1424,8 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
   if (e == cudaSuccess && p_alive) e = cudaMemcpyAsync(p_alive, d_pa, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess && x_star) e = cudaMemcpyAsync(x_star, d_x, (size_t)(C * nd * N) * 8, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(d_mx); cudaFree(d_pa);
-  if (d_x) cudaFree(d_x);
+  dfree(d_mx); dfree(d_pa);
+  if (d_x) dfree(d_x);
   if (e != cudaSuccess) return fail(h, CLV_ERR_CUDA, "clv_forecast_resident failed: %s", cudaGetErrorString(e));
   return CLV_OK;
 }
@@ -1393,12 +1433,12 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
 // ---- "next" rows on the resident draws -----------------------------------------------------------
 int clv_upload_draws(clv_sampler* h, const double* level1, int64_t n_draws) {
   if (!h || !level1 || n_draws < 1) return fail(h, CLV_ERR_ARG, "clv_upload_draws: bad argument");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   const long long bytes = (long long)h->chains * n_draws * h->N * h->ncol * (long long)sizeof(double);
   if (h->draws_cap_bytes[0] < bytes) {
-    if (h->d_draws[0]) cudaFree(h->d_draws[0]);
+    if (h->d_draws[0]) dfree(h->d_draws[0]);
     h->d_draws[0] = nullptr; h->draws_cap_bytes[0] = 0;
-    cudaError_t e = cudaMalloc((void**)&h->d_draws[0], (size_t)bytes);
+    cudaError_t e = pool_malloc((void**)&h->d_draws[0], (size_t)bytes);
     if (e != cudaSuccess) return fail(h, CLV_ERR_CUDA, "cannot allocate %lld bytes for the draws: %s", bytes, cudaGetErrorString(e));
     h->draws_cap_bytes[0] = bytes;
   }
@@ -1411,7 +1451,7 @@ int clv_upload_draws(clv_sampler* h, const double* level1, int64_t n_draws) {
 int clv_posterior_summary(clv_sampler* h, double mu_cap, double* out) {
   if (!h || !out) return fail(h, CLV_ERR_ARG, "null argument");
   if (h->resident_draws <= 0) return fail(h, CLV_ERR_STATE, "no resident draws: call clv_run (single device chunk) or clv_run_resident first");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   const long long n_tot = (long long)h->chains * h->resident_draws, N = h->N;
   int n_pad = 1;
   while (n_pad < n_tot) n_pad <<= 1;
@@ -1432,7 +1472,7 @@ int clv_posterior_summary(clv_sampler* h, double mu_cap, double* out) {
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(double) * N * SUMMARY_COLS, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(d_out);
+  dfree(d_out);
   if (e != cudaSuccess) return fail(h, CLV_ERR_CUDA, "clv_posterior_summary failed: %s", cudaGetErrorString(e));
   return CLV_OK;
 }
@@ -1442,7 +1482,7 @@ int clv_weekly_tracking(clv_sampler* h, const double* birth_week, const double* 
   if (!h || !birth_week || !times || !inc_mean) return fail(h, CLV_ERR_ARG, "null argument");
   if (n_weeks < 1 || n_weeks > 4096) return fail(h, CLV_ERR_ARG, "n_weeks must be in [1, 4096]");
   if (h->resident_draws <= 0) return fail(h, CLV_ERR_STATE, "no resident draws: call clv_run (single device chunk) or clv_run_resident first");
-  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   if (int r = upload_rk()) return r;
   const long long n_tot = (long long)h->chains * h->resident_draws, N = h->N;
   double *d_birth = nullptr, *d_times = nullptr;
@@ -1465,7 +1505,7 @@ int clv_weekly_tracking(clv_sampler* h, const double* birth_week, const double* 
   std::vector<unsigned long long> tot((size_t)n_weeks);
   if (e == cudaSuccess) e = cudaMemcpyAsync(tot.data(), d_tot, sizeof(unsigned long long) * n_weeks, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(d_birth); cudaFree(d_times); cudaFree(d_tot);
+  dfree(d_birth); dfree(d_times); dfree(d_tot);
   if (e != cudaSuccess) return fail(h, CLV_ERR_CUDA, "clv_weekly_tracking failed: %s", cudaGetErrorString(e));
   for (int w = 0; w < n_weeks; ++w) inc_mean[w] = (double)tot[w] / (double)n_tot;   // analysis_abe.py:459
   return CLV_OK;
@@ -1480,7 +1520,7 @@ int clv_generate(const clv_generate_config* cfg, const double* beta, const doubl
   int ndev = 0;
   cudaError_t e0 = cudaGetDeviceCount(&ndev);
   if (e0 != cudaSuccess || ndev == 0) return fail(nullptr, CLV_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
-  CK(nullptr, cudaSetDevice(cfg->device));
+  CK(nullptr, cudaSetDevice(cfg->device)); t_alloc_stream = nullptr; ensure_pool(cfg->device);
   if (int r = upload_rk()) return r;
   const long long n = cfg->n;
   const int K = cfg->n_cov;
@@ -1491,14 +1531,14 @@ int clv_generate(const clv_generate_config* cfg, const double* beta, const doubl
   if (!chol_host(gamma, a.Lg, 2)) return fail(nullptr, CLV_ERR_NUMERIC, "gamma is not positive definite");
   int rc = 0;
   std::vector<void*> allocs;
-  auto dm = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, std::max<size_t>(bytes, 8)) != cudaSuccess) { rc = -1; return nullptr; } allocs.push_back(p); return p; };
+  auto dm = [&](size_t bytes) -> void* { void* p = nullptr; if (pool_malloc(&p, bytes) != cudaSuccess) { rc = -1; return nullptr; } allocs.push_back(p); return p; };
   a.x = (int*)dm(n * 4); a.t_x = (double*)dm(n * 8); a.T_cal = (double*)dm(n * 8);
   a.Xc = (double*)dm((size_t)n * 8 * std::max(K - 1, 1));
   a.x_star = x_star ? (int*)dm(n * 4) : nullptr;
   a.lam = lambda_true ? (double*)dm(n * 8) : nullptr;
   a.mu = mu_true ? (double*)dm(n * 8) : nullptr;
   a.tau = tau_true ? (double*)dm(n * 8) : nullptr;
-  auto cleanup = [&]() { for (void* p : allocs) cudaFree(p); };
+  auto cleanup = [&]() { for (void* p : allocs) dfree(p); };
   if (rc) { cleanup(); return fail(nullptr, CLV_ERR_CUDA, "clv_generate: out of device memory"); }
   a.X_given = X_given; a.T_given = T_cal_given;
   if (T_cal_given && cudaMemcpy(a.T_cal, T_cal, n * 8, cudaMemcpyHostToDevice) != cudaSuccess) rc = -1;
@@ -1536,11 +1576,11 @@ int clv_elog2cbs(int device, int64_t n_events, const int64_t* cust, const int32_
   if (!(unit_days > 0)) return fail(nullptr, CLV_ERR_ARG, "clv_elog2cbs: unit_days must be positive");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, CLV_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
-  CK(nullptr, cudaSetDevice(device));
+  CK(nullptr, cudaSetDevice(device)); t_alloc_stream = nullptr; ensure_pool(device);
   const size_t n = (size_t)n_events;
   std::vector<void*> allocs;
-  auto dm = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, std::max<size_t>(bytes, 8)) != cudaSuccess) return nullptr; allocs.push_back(p); return p; };
-  auto cleanup = [&]() { for (void* p : allocs) cudaFree(p); };
+  auto dm = [&](size_t bytes) -> void* { void* p = nullptr; if (pool_malloc(&p, bytes) != cudaSuccess) return nullptr; allocs.push_back(p); return p; };
+  auto cleanup = [&]() { for (void* p : allocs) dfree(p); };
   long long *k0 = (long long*)dm(n * 8), *k1 = (long long*)dm(n * 8);
   int *d0 = (int*)dm(n * 4), *d1 = (int*)dm(n * 4), *head = (int*)dm(n * 4), *idx = (int*)dm(n * 4);
   unsigned *p0 = (unsigned*)dm(n * 4), *p1 = (unsigned*)dm(n * 4);
@@ -1632,7 +1672,7 @@ int clv_debug_variates(int device, uint64_t seed, uint32_t sweep, int rng_mode, 
   if (rng_mode != CLV_RNG_PHILOX_FAST && rng_mode != CLV_RNG_PHILOX_STRICT) return fail(nullptr, CLV_ERR_ARG, "rng_mode must be fast or strict");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, CLV_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
-  CK(nullptr, cudaSetDevice(device));
+  CK(nullptr, cudaSetDevice(device)); t_alloc_stream = nullptr; ensure_pool(device);
   double* d = nullptr;
   CK(nullptr, dmalloc(&d, (size_t)n * 3));
   const PhiloxRoundKeys rk = round_keys(seed);
@@ -1642,7 +1682,7 @@ int clv_debug_variates(int device, uint64_t seed, uint32_t sweep, int rng_mode, 
   if (e == cudaSuccess) e = cudaMemcpy(t3_l, d, sizeof(double) * n, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaMemcpy(t3_m, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaMemcpy(u_acc, d + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost);
-  cudaFree(d);
+  dfree(d);
   if (e != cudaSuccess) return fail(nullptr, CLV_ERR_CUDA, "clv_debug_variates failed: %s", cudaGetErrorString(e));
   return CLV_OK;
 }
@@ -1653,7 +1693,7 @@ int clv_measure_issue_peaks(int device, double* out4) {
   int ndev = 0;
   cudaError_t e0 = cudaGetDeviceCount(&ndev);
   if (e0 != cudaSuccess || ndev == 0) return fail(nullptr, CLV_ERR_CUDA, "no CUDA device available");
-  CK(nullptr, cudaSetDevice(device));
+  CK(nullptr, cudaSetDevice(device)); t_alloc_stream = nullptr; ensure_pool(device);
   cudaDeviceProp prop;
   CK(nullptr, cudaGetDeviceProperties(&prop, device));
   const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
@@ -1679,7 +1719,7 @@ int clv_measure_issue_peaks(int device, double* out4) {
     out4[w] = best;
   }
   cudaEventDestroy(e1); cudaEventDestroy(e2);
-  cudaFree(d_out);
+  dfree(d_out);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(nullptr, CLV_ERR_CUDA, "peak kernels failed: %s", cudaGetErrorString(e));
   return CLV_OK;
