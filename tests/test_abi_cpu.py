@@ -115,3 +115,28 @@ def test_exact_sum_is_partition_independent():
     assert abs(st["lam_init"] / lam - 1) < 1e-13
     assert abs(st["mean_mu_init"] / np.mean(1 / (t + 0.5 / lam)) - 1) < 1e-13
     np.testing.assert_allclose(st["xtx"], X.T @ X, rtol=1e-13)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    """No silent fallback when the CUDA library has not been built."""
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", os.path.join(ROOT, "mcmc_clv_model_b200", "no_such_lib.so"))
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        L.load()
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm: oracle port on all host cores) prints exactly one JSON line with the
+    contract's keys."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "customer_updates_per_sec" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["value"] > 1e4 and "workload" in d["config"]
