@@ -336,6 +336,18 @@ def run_ours(args):
                "wall_s": wall, "customer_updates_per_sec": 2357 * 4 * 14000 / wall, "min_ess_bulk": me_b,
                "min_ess_geyer": me_g, "ess_per_sec": me_g / wall,
                "reference_numpy_1core": {"wall_s": 653.6, "min_ess_geyer": 60, "ess_per_sec": 0.09, "source": "BASELINE.md §2"}}
+        if not args.no_cpu_baseline:
+            # the oracle port on the same C1 data, one chain x 200 sweeps on one host core of this box (the reference
+            # itself needs 653.6 s for the full run: BASELINE.md)
+            from oracle import abe_oracle as ao
+            from oracle.streams import NumpyOrderStreams
+            cb = ao.Cbs(x=d["x"].astype(np.int64), t_x=d["t_x"].astype(float), T_cal=d["T_cal"].astype(float), X=np.asfortranarray(X1))
+            t0 = time.perf_counter()
+            ao.run_chain(cb, ao.default_hyper(1, 2), NumpyOrderStreams(np.random.default_rng(42)), mcmc=100, burnin=100, thin=1, D=2)
+            dtc = time.perf_counter() - t0
+            ess["cpu_port_same_box"] = {"customer_updates_per_sec": 2357 * 200 / dtc, "cores": 1,
+                                        "sample": f"C1 data, 1 chain x 200 sweeps ({dtc:.1f} s)",
+                                        "extrapolated_full_run_s": dtc / 200 * 14000 * 4}
         # the same data with the GPU filled: 64 chains (the per-sweep latency barely changes, ESS adds up over chains)
         t0 = time.perf_counter()
         with Sampler(d["x"], d["t_x"], d["T_cal"], X1, model_dim=2, chains=64, n_mh_steps=20, seed=42, device=local) as s4:
