@@ -146,6 +146,9 @@ int clv_advance(clv_sampler* h, int64_t n_sweeps, int sync);
 /* Same, synchronous, bracketed by CUDA events on the handle's stream: *elapsed_ms = device time of the n sweeps. */
 int clv_advance_timed(clv_sampler* h, int64_t n_sweeps, double* elapsed_ms);
 int64_t clv_sweeps_done(const clv_sampler* h);
+/* Resume: after clv_set_state on a fresh handle, set the number of sweeps the restored chains have already made, so
+ * that the Philox counters (sweep = sweeps_done + 1, ...) continue where the checkpointed run stopped. */
+int clv_set_sweeps_done(clv_sampler* h, int64_t n);
 /* kernels launched by this handle so far (bench.py's gpu_launches) */
 int64_t clv_kernel_launches(const clv_sampler* h);
 /* CUDA-event time (ms) of the level-1 sweep kernel summed over the sweeps since the last call (0 if

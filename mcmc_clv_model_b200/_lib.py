@@ -80,6 +80,7 @@ SIGNATURES = {
     "clv_advance_timed": (C.c_int, [C.c_void_p, C.c_int64, c_double_p]),
     "clv_sweeps_done": (C.c_int64, [C.c_void_p]),
     "clv_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "clv_set_sweeps_done": (C.c_int, [C.c_void_p, C.c_int64]),
     "clv_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "clv_kernel_time_ms": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_int64_p]),
     "clv_get_state": (C.c_int, [C.c_void_p, C.c_int] + [c_double_p] * 7),

@@ -832,6 +832,12 @@ int clv_p2p_connect(clv_sampler* h, const void* handles, int rank, int world) {
 int64_t clv_sweeps_done(const clv_sampler* h) { return h ? h->sweeps_done : -1; }
 int64_t clv_kernel_launches(const clv_sampler* h) { return h ? h->launches : -1; }
 
+int clv_set_sweeps_done(clv_sampler* h, int64_t n) {
+  if (!h || n < 0 || n > 0xFFFFFFF0ll) return fail(h, CLV_ERR_ARG, "clv_set_sweeps_done: bad argument");
+  h->sweeps_done = n;
+  return CLV_OK;
+}
+
 int clv_set_timing(clv_sampler* h, int on) {
   if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
   CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);

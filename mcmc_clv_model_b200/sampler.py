@@ -184,6 +184,20 @@ class Sampler:
     def sweeps_done(self):
         return int(self.lib.clv_sweeps_done(self.h))
 
+    @sweeps_done.setter
+    def sweeps_done(self, n):
+        L.check(self.lib.clv_set_sweeps_done(self.h, int(n)), self.h)
+
+    def checkpoint(self):
+        """Everything needed to continue the chains in another process: per-chain state + the sweep counter."""
+        return dict(sweeps_done=self.sweeps_done, chains=[self.get_state(c) for c in range(self.chains)])
+
+    def restore(self, ck):
+        """Counterpart of checkpoint() on a sampler built from the same data, seed and options."""
+        for c, st in enumerate(ck["chains"]):
+            self.set_state(c, st["log_lambda"], st["log_mu"], st.get("log_eta"), st["beta"], st["Sigma"])
+        self.sweeps_done = ck["sweeps_done"]
+
     @property
     def kernel_launches(self):
         return int(self.lib.clv_kernel_launches(self.h))

@@ -468,3 +468,22 @@ def test_exported_draw_z_and_draw_tau_blocks(cdnow_abe):
     u[~z] = r.random(int((~z).sum()))
     np.testing.assert_allclose(tau, ao.draw_tau(d["t_x"][:n], d["T_cal"][:n], lam, mu, z, e, u), rtol=1e-12)
     assert np.all(tau[z] > d["T_cal"][:n][z])
+
+
+@pytest.mark.parametrize("D", [2, 3])
+def test_checkpoint_resume_is_bit_identical(cdnow_abe, D):
+    """The final state + sweep counter continue a chain in a fresh handle exactly (counter-based RNG: nothing else to save)."""
+    d = cdnow_abe
+    n = 900
+    X = np.column_stack([np.ones(n), d["age_scaled"][:n]])
+    args = (d["x"][:n], d["t_x"][:n], d["T_cal"][:n], X, d["log_s"][:n] if D == 3 else None)
+    kw = dict(model_dim=D, chains=2, seed=31)
+    with Sampler(*args, **kw) as s:
+        s.run(0, 9, 3)
+        ck = s.checkpoint()
+        ref = s.run(2, 6, 2)
+    with Sampler(*args, **kw) as s2:
+        s2.restore(ck)
+        out = s2.run(2, 6, 2)
+    for k in ("level_1", "level_2", "loglik_sum"):
+        np.testing.assert_array_equal(out[k], ref[k], err_msg=k)
