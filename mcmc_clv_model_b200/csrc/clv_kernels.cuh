@@ -472,6 +472,10 @@ struct InitQArgs {
 };
 
 __global__ void __launch_bounds__(256) k_init_quantities(InitQArgs a) {
+  __shared__ unsigned long long s_max[NQ_MAX];
+  __shared__ unsigned long long s_sum[2 * NQ_MAX];
+  for (int t = threadIdx.x; t < NQ_MAX; t += blockDim.x) { s_max[t] = 0ull; s_sum[2 * t] = 0ull; s_sum[2 * t + 1] = 0ull; }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long nwarp_tiles = (a.N + 31) / 32;
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -504,15 +508,25 @@ __global__ void __launch_bounds__(256) k_init_quantities(InitQArgs a) {
         unsigned long long m = (unsigned long long)__double_as_longlong(fabs(v));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_down_sync(0xffffffffu, m, o); m = t > m ? t : m; }
-        if (lane == 0 && m) atomicMax(&a.out_max[q], m);
+        if (lane == 0 && m) atomicMax(&s_max[q], m);
       } else {
         const long long term = __double2ll_rn(v * a.scale[q]);
         const long long lo = warp_sum_ll(term & 0xffffffffll), hi = warp_sum_ll(term >> 32);
         if (lane == 0) {
-          if (lo) atomicAdd((unsigned long long*)&a.out_sum[2 * q], (unsigned long long)lo);
-          if (hi) atomicAdd((unsigned long long*)&a.out_sum[2 * q + 1], (unsigned long long)hi);
+          if (lo) atomicAdd(&s_sum[2 * q], (unsigned long long)lo);
+          if (hi) atomicAdd(&s_sum[2 * q + 1], (unsigned long long)hi);
         }
       }
+    }
+  }
+  // one global atomic per quantity per block (the per-warp ones go to shared memory)
+  __syncthreads();
+  for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+    if (a.mode == 0) {
+      if (s_max[q]) atomicMax(&a.out_max[q], s_max[q]);
+    } else {
+      if (s_sum[2 * q]) atomicAdd((unsigned long long*)&a.out_sum[2 * q], s_sum[2 * q]);
+      if (s_sum[2 * q + 1]) atomicAdd((unsigned long long*)&a.out_sum[2 * q + 1], s_sum[2 * q + 1]);
     }
   }
 }

@@ -15,7 +15,9 @@ agg = collections.OrderedDict()
 for r in rows[1:]:
     if len(r) > vi:
         agg.setdefault(re.sub(r"\(.*", "", r[ki]), []).append(float(r[vi].replace(",", "")))
-tot = sum(sum(v) for k, v in agg.items() if "k_peak" not in k and "k_generate" not in k)
+STEP = ("k_sweep", "k_level2", "k_persistent")          # the kernels of one Gibbs sweep
+ONCE = ("k_split_columns", "k_init_quantities", "k_init_state", "k_derive_params", "k_stats_only")   # once per data set
+tot = sum(sum(v) for k, v in agg.items() if any(t in k for t in STEP))
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 r = list(csv.reader(io.StringIO(raw)))
@@ -48,7 +50,8 @@ with open(out_md, "w") as f:
     f.write("Source reports: `gpurun_out/` (scratch); this file and the JSON beside it are the committed summaries.\n\n")
     f.write("## Launch list (`--metrics gpu__time_duration.sum`; cold-cache, serialised: compare shares)\n\n| kernel | launches | mean us | total ms | share of step kernels |\n|---|---|---|---|---|\n")
     for k, v in agg.items():
-        share = f"{100 * sum(v) / tot:.1f} %" if "k_peak" not in k and "k_generate" not in k else "(not part of a step)"
+        share = (f"{100 * sum(v) / tot:.1f} %" if any(t in k for t in STEP) else
+                 "(once per data set)" if any(t in k for t in ONCE) else "(not part of a step)")
         f.write(f"| `{k}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {sum(v) / 1e6:.3f} | {share} |\n")
     f.write("\n## `k_sweep<2,FAST>` (full set)\n\n| metric | value |\n|---|---|\n")
     f.write(f"| duration | {js['duration_us']:.1f} us |\n| DRAM read / write per launch | {dr / 1e6:.1f} MB / {dw / 1e6:.1f} MB = {(dr + dw) / ncust:.1f} B per customer (algorithmic 84 B) |\n")
