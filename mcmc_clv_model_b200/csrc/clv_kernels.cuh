@@ -89,6 +89,9 @@ struct SweepArgs {
 };
 
 __constant__ double c_exptab[64];   // 2^(j/64), uploaded by clv_create
+// exp_tab constants: 64/ln2, -ln2/64 (high, low), 1/120, 1/24, 1/6
+__constant__ double c_expk[6] = {92.332482616893656877, -0x1.62e42fefa0000p-7, -0x1.cf79abc9e3b3ap-46,
+                                 8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01};
 
 __device__ __forceinline__ long long to_fx(double v, double scale) { return __double2ll_rn(v * scale); }
 
@@ -111,13 +114,15 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 //   n = rint(x 64/ln2), r = x - n ln2/64 (|r| <= 0.0055), exp(x) = 2^(n>>6) * 2^((n&63)/64) * (1 + r + ... + r^5/120)
 // 2^(j/64) comes from a 64-entry shared-memory table; the degree-5 remainder is < 4e-17.
 __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
-  const double t = fma(x, 92.332482616893656877, 6755399441055744.0);   // 64/ln2 ; 1.5 * 2^52 rounds to nearest
+  // the fp64 constants sit in the constant bank so that DFMA reads them as c[][] operands; written as literals ptxas
+  // rebuilds each one with two UMOVs on every call (26 extra issue slots per MH step)
+  const double t = fma(x, c_expk[0], 6755399441055744.0);                 // 64/ln2 ; 1.5 * 2^52 rounds to nearest
   const int n = __double2loint(t);
   const double nd = t - 6755399441055744.0;
-  double r = fma(nd, -0x1.62e42fefa0000p-7, x);                           // ln2/64, high part (low 16 bits zero: n*hi exact)
-  r = fma(nd, -0x1.cf79abc9e3b3ap-46, r);                                 // low part
-  double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
-  p = fma(p, r, 1.6666666666666666e-01);
+  double r = fma(nd, c_expk[1], x);                                       // -ln2/64, high part (low 16 bits zero: n*hi exact)
+  r = fma(nd, c_expk[2], r);                                              // low part
+  double p = fma(r, c_expk[3], c_expk[4]);
+  p = fma(p, r, c_expk[5]);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = p * r;
@@ -133,13 +138,19 @@ __device__ __forceinline__ double exp_any(double x, const double* __restrict__ t
   return (fabs(x) <= 700.0) ? exp_tab(x, tab) : exp_slow(x);
 }
 
-// Level-1 target, bi:291-310.  Tz = z*T_cal + (1-z)*tau, omz = 1-z.  ll, lm in [-70, 70].
+// Level-1 target, bi:291-310, without the lm > 5 cut (the caller applies it).  Tz = z*T_cal + (1-z)*tau, omz = 1-z,
+// ll, lm in [-70, 70].  The quadratic form takes the precision pre-scaled per chain, h00 = -P00/2, h01 = -P01,
+// h11 = -P11/2, and is folded into the likelihood by Horner steps: 7 fp64 instructions instead of 10.
+__device__ __forceinline__ double log_post_open(double ll, double lm, double xd, double omz, double Tz, double m0,
+                                                double m1, double h00, double h01, double h11, const double* tab) {
+  const double dl = ll - m0, dm = lm - m1;
+  const double lik = xd * ll + omz * lm - (exp_tab(ll, tab) + exp_tab(lm, tab)) * Tz;
+  return fma(dl, fma(h00, dl, h01 * dm), fma(dm, h11 * dm, lik));
+}
+// bi:308-309: the target is -inf where log mu > 5
 __device__ __forceinline__ double log_post(double ll, double lm, double xd, double omz, double Tz, double m0,
-                                           double m1, double P00, double P01, double P11, const double* tab) {
-  double dl = ll - m0, dm = lm - m1;
-  double lik = xd * ll + omz * lm - (exp_tab(ll, tab) + exp_tab(lm, tab)) * Tz;
-  double prior = -0.5 * (dl * dl * P00 + 2.0 * dl * dm * P01 + dm * dm * P11);
-  double res = lik + prior;
+                                           double m1, double h00, double h01, double h11, const double* tab) {
+  const double res = log_post_open(ll, lm, xd, omz, Tz, m0, m1, h00, h01, h11, tab);
   return (lm > 5.0) ? -CUDART_INF : res;
 }
 
@@ -162,7 +173,9 @@ __device__ __forceinline__ bool mh_accept(double d, float uf, ExactU exact_u) {
 }
 
 // np.clip(v, -70, 70) of bi:323-324 for both proposals; the test runs on the high words so the common case costs a few
-// integer ops and one never-taken branch (|v| >= 70 is a once-in-a-run event)
+// integer ops and one rarely taken branch (|v| >= 70 needs a t3 variate beyond ~47: about 1 proposal in 50,000).
+// Tried and dropped: leaving the loop for a clipping copy of the step instead of the call -- ptxas merges the copies
+// back into one loop and reloads the Philox keys through vector registers (spills).
 __device__ __noinline__ double clip70_slow(double v) { return fmin(fmax(v, -70.0), 70.0); }   // by value: no stack traffic
 __device__ __forceinline__ void clip70_pair(double& a, double& b) {
   const unsigned ha = (unsigned)__double2hiint(a) & 0x7fffffffu, hb = (unsigned)__double2hiint(b) & 0x7fffffffu;
@@ -236,7 +249,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
   const int K = mc.K, S = mc.S;
   const long long N = mc.N;
   const long long cN = (long long)chain * N;
-  const double P00 = cp.P00, P01 = cp.P01, P11 = cp.P11;
+  const double h00 = -0.5 * cp.P00, h01 = -cp.P01, h11 = -0.5 * cp.P11;
   // proposal scales are variances (bi:316-317, Q2); t3_fast returns t / sqrt(3)
   const double t3s = (MODE == MODE_FAST) ? 1.7320508075688772 : 1.0;
   const double s_l = cp.Sigma[0] * t3s, s_m = cp.Sigma[D + 1] * t3s;
@@ -294,7 +307,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
     const double omz = 1.0 - zf;
     const double Tz = alive ? T : tau;          // z*T_cal + (1-z)*tau, bi:298
     // ---- S Metropolis steps (bi:312-335) -------------------------------------------------------
-    double cur = log_post(ll, lm, xd, omz, Tz, m0, m1, P00, P01, P11, s_tab);
+    double cur = log_post(ll, lm, xd, omz, Tz, m0, m1, h00, h01, h11, s_tab);
     for (int s = 0; s < S; ++s) {
       double tl, tm, ua = 0.0;
       float uaf;
@@ -320,8 +333,12 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
       }
       double pl = ll + s_l * tl, pm = lm + s_m * tm;           // bi:318-324
       clip70_pair(pl, pm);
-      const double prop = log_post(pl, pm, xd, omz, Tz, m0, m1, P00, P01, P11, s_tab);
-      if (mh_accept<MODE == MODE_INJECT>(prop - cur, uaf, [&]() { return MODE == MODE_INJECT ? ua : u32d(ur); })) {
+      // a proposal with log mu > 5 has target -inf and is never accepted (exp(-inf - cur) = 0, or NaN when cur is
+      // -inf too); cur itself can be -inf only at the start, and then every admissible proposal is accepted (d = +inf)
+      const bool admissible = !(pm > 5.0);
+      const double prop = log_post_open(pl, pm, xd, omz, Tz, m0, m1, h00, h01, h11, s_tab);
+      if (mh_accept<MODE == MODE_INJECT>(prop - cur, uaf, [&]() { return MODE == MODE_INJECT ? ua : u32d(ur); }) &&
+          admissible) {
         ll = pl;
         lm = pm;
         cur = prop;

@@ -79,8 +79,9 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
 __device__ __forceinline__ double u32d(uint32_t a) { return ((double)a + 0.5) * 0x1.0p-32; }
 // fp32 image of u32d (24 significant bits), only used to screen MH decisions
 __device__ __forceinline__ float u32f(uint32_t a) { return fmaf((float)a, 0x1.0p-32f, 0x1.0p-33f); }
-// (k + 0.5) 2^-24, k = top 24 bits: exact in fp32, one FFMA
-__device__ __forceinline__ float u24f(uint32_t a) { return fmaf((float)(a >> 8), 0x1.0p-24f, 0x1.0p-25f); }
+// (k + 0.5) 2^-24, k = top 24 bits: exact in fp32.  Converting the whole word with round-toward-zero keeps exactly the
+// top 24 bits ((a >> 8) << 8), so the shift is folded into the conversion: one I2F.RZ + one FFMA.
+__device__ __forceinline__ float u24f(uint32_t a) { return fmaf(__uint2float_rz(a), 0x1.0p-32f, 0x1.0p-25f); }
 
 // SFU primitives without the denormal / IEEE-rounding fix-up code the default intrinsics carry
 __device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -101,17 +102,21 @@ __device__ __forceinline__ double t3_strict(uint32_t ra, uint32_t rb, uint32_t r
   return n0 / sqrt(chi2 / 3.0);
 }
 
-// FAST variant, returns t / sqrt(3) (the caller folds sqrt(3) into the proposal scale).  With a = -lg2 u1, b = -lg2 u3
-// the -2 ln 2 factors of the Box-Muller radius and of the chi-square cancel:
-//   t / sqrt(3) = cos(th) sqrt(a) / sqrt(a sin^2(th) + b) = cos(th) * rsqrt(sin^2(th) + b / a)
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// FAST variant, returns t / sqrt(3) (the caller folds sqrt(3) into the proposal scale).  With a = lg2 u1, b = lg2 u3
+// (both <= 0) the -2 ln 2 factors of the Box-Muller radius and of the chi-square cancel:
+//   t / sqrt(3) = cos(th) / sqrt(sin^2(th) + b / a) = cos(th) |a| rsqrt((sin^2(th) a + b) a),  sin^2 = 1 - cos^2
+// which needs four SFU operations (2 lg2, cos, rsqrt) instead of six (+ sin, rcp); the SFU pipe is the second busiest
+// of the sweep kernel.  The map is odd in cos(th), so the proposal stays exactly symmetric whatever the rounding.
 __device__ __forceinline__ float t3_fast(uint32_t ra, uint32_t rb, uint32_t rc) {
-  // both <= 0; u1 can round to 1.0f (lg2 = +0): keep the divisor strictly negative so that b / a -> +huge, t -> 0
-  const float l1 = fminf(lg2_ftz(u24f(ra)), -1e-30f), l3 = lg2_ftz(u24f(rc));
+  // u1 can round to 1.0f (lg2 = +0): keep a strictly negative (>= one grid step) so that the rsqrt argument stays
+  // a normal positive number
+  const float l1 = fminf(lg2_ftz(u24f(ra)), -0x1.0p-24f), l3 = lg2_ftz(u24f(rc));
   // angle 2 pi (k + 0.5) 2^-24 straight from the integer
-  const float ang = fmaf((float)(rb >> 8), 6.2831853071795865f * 0x1.0p-24f, 6.2831853071795865f * 0x1.0p-25f);
-  const float s = sin_ftz(ang), c = cos_ftz(ang);
-  return c * rsqrt_ftz(fmaf(s, s, l3 * rcp_approx(l1)));
+  const float ang = fmaf(__uint2float_rz(rb), 6.2831853071795865f * 0x1.0p-32f, 6.2831853071795865f * 0x1.0p-25f);
+  const float c = cos_ftz(ang);
+  const float s2 = fmaf(-c, c, 1.0f);
+  const float w = fmaf(s2, l1, l3);
+  return (c * fabsf(l1)) * rsqrt_ftz(w * l1);
 }
 
 // two standard normals from four words (53-bit uniforms, fp64): cos / sin branch
