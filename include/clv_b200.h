@@ -250,10 +250,10 @@ int clv_elog2cbs(int device, int64_t n_events, const int64_t* cust, const int32_
                  int32_t* x, double* t_x, double* litt, double* sales_out, double* sales_x, int32_t* first_day,
                  double* T_cal, double* T_star, int32_t* x_star, double* sales_star);
 
-/* ---- test hook: the level-1 variates of MH step 0 (two Student-t3 proposals, accept uniform) that customers
+/* ---- test hook: the level-1 variates of MH step `step` (two Student-t3 proposals, accept uniform) that customers
  * 0..n-1 of chain 0 consume in sweep `sweep`, as the sweep kernel generates them in rng_mode fast / strict. */
-int clv_debug_variates(int device, uint64_t seed, uint32_t sweep, int rng_mode, int64_t n, double* t3_l, double* t3_m,
-                       double* u_acc);
+int clv_debug_variates(int device, uint64_t seed, uint32_t sweep, int32_t step, int rng_mode, int64_t n, double* t3_l,
+                       double* t3_m, double* u_acc);
 
 /* ---- micro-benchmarks used by bench.py for the issue-rate roofline -------------------------- */
 /* Measures, on `device`, sustained warp-instruction throughput of dependent-free loops of

@@ -1673,8 +1673,8 @@ int clv_elog2cbs(int device, int64_t n_events, const int64_t* cust, const int32_
 }
 
 // ---- test hook: level-1 variates ------------------------------------------------------------------
-int clv_debug_variates(int device, uint64_t seed, uint32_t sweep, int rng_mode, int64_t n, double* t3_l, double* t3_m, double* u_acc) {
-  if (!t3_l || !t3_m || !u_acc || n < 1) return fail(nullptr, CLV_ERR_ARG, "clv_debug_variates: bad argument");
+int clv_debug_variates(int device, uint64_t seed, uint32_t sweep, int32_t step, int rng_mode, int64_t n, double* t3_l, double* t3_m, double* u_acc) {
+  if (!t3_l || !t3_m || !u_acc || n < 1 || step < 0) return fail(nullptr, CLV_ERR_ARG, "clv_debug_variates: bad argument");
   if (rng_mode != CLV_RNG_PHILOX_FAST && rng_mode != CLV_RNG_PHILOX_STRICT) return fail(nullptr, CLV_ERR_ARG, "rng_mode must be fast or strict");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, CLV_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
@@ -1682,8 +1682,8 @@ int clv_debug_variates(int device, uint64_t seed, uint32_t sweep, int rng_mode, 
   double* d = nullptr;
   CK(nullptr, dmalloc(&d, (size_t)n * 3));
   const PhiloxRoundKeys rk = round_keys(seed);
-  if (rng_mode == CLV_RNG_PHILOX_STRICT) k_debug_variates<MODE_STRICT><<<148 * 4, 256>>>(rk, sweep, n, d, d + n, d + 2 * n);
-  else k_debug_variates<MODE_FAST><<<148 * 4, 256>>>(rk, sweep, n, d, d + n, d + 2 * n);
+  if (rng_mode == CLV_RNG_PHILOX_STRICT) k_debug_variates<MODE_STRICT><<<148 * 4, 256>>>(rk, sweep, step, n, d, d + n, d + 2 * n);
+  else k_debug_variates<MODE_FAST><<<148 * 4, 256>>>(rk, sweep, step, n, d, d + n, d + 2 * n);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpy(t3_l, d, sizeof(double) * n, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaMemcpy(t3_m, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost);

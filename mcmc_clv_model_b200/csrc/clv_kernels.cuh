@@ -308,7 +308,8 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
     const double Tz = alive ? T : tau;          // z*T_cal + (1-z)*tau, bi:298
     // ---- S Metropolis steps (bi:312-335) -------------------------------------------------------
     double cur = log_post(ll, lm, xd, omz, Tz, m0, m1, h00, h01, h11, s_tab);
-    for (int s = 0; s < S; ++s) {
+    // one step from its six words (ignored when the variates are injected)
+    auto mh_step = [&](int s, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5) {
       double tl, tm, ua = 0.0;
       float uaf;
       uint32_t ur = 0u;
@@ -319,16 +320,14 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
         ua = a.u_acc[o];
         uaf = (float)ua;
       } else {
-        uint4 ra = philox4x32_10_rk(gid, sw.sweep, 1u + 2u * s, c3, a.rk);
-        uint4 rb = philox4x32_10_rk(gid, sw.sweep, 2u + 2u * s, c3, a.rk);
         if (MODE == MODE_STRICT) {
-          tl = t3_strict(ra.x, ra.y, ra.z);
-          tm = t3_strict(ra.w, rb.x, rb.y);
+          tl = t3_strict(w0, w1, w2);
+          tm = t3_strict(w3, w4, w5);
         } else {
-          tl = (double)t3_fast(ra.x, ra.y, ra.z);
-          tm = (double)t3_fast(ra.w, rb.x, rb.y);
+          tl = (double)t3_fast(w0, w1, w2);
+          tm = (double)t3_fast(w3, w4, w5);
         }
-        ur = rb.z;
+        ur = low_bytes(w0, w1, w2, w3);
         uaf = u32f(ur);
       }
       double pl = ll + s_l * tl, pm = lm + s_m * tm;           // bi:318-324
@@ -342,6 +341,26 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
         ll = pl;
         lm = pm;
         cur = prop;
+      }
+    };
+    if (MODE == MODE_INJECT) {
+      for (int s = 0; s < S; ++s) mh_step(s, 0u, 0u, 0u, 0u, 0u, 0u);
+    } else {
+      // two steps per trip share three Philox blocks (word layout: clv_rng.cuh)
+      int s = 0;
+      uint32_t slot = 1u;
+#pragma unroll 1
+      for (; s + 1 < S; s += 2, slot += 3u) {
+        const uint4 A = philox4x32_10_rk(gid, sw.sweep, slot, c3, a.rk);
+        const uint4 B = philox4x32_10_rk(gid, sw.sweep, slot + 1u, c3, a.rk);
+        mh_step(s, A.x, A.y, A.z, A.w, B.x, B.y);
+        const uint4 C = philox4x32_10_rk(gid, sw.sweep, slot + 2u, c3, a.rk);
+        mh_step(s + 1, B.z, B.w, C.x, C.y, C.z, C.w);
+      }
+      if (s < S) {
+        const uint4 A = philox4x32_10_rk(gid, sw.sweep, slot, c3, a.rk);
+        const uint4 B = philox4x32_10_rk(gid, sw.sweep, slot + 1u, c3, a.rk);
+        mh_step(s, A.x, A.y, A.z, A.w, B.x, B.y);
       }
     }
     a.ll[cN + i] = ll;
@@ -452,21 +471,30 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_stats_only(SweepArgs a) {
     if (s_acc[t]) atomicAdd(&a.acc[chain * NSTAT_MAX + t], s_acc[t]);
 }
 
-// Test hook: the level-1 variates of MH step 0 (proposal t3 for log lambda / log mu, accept uniform) that customer gid
-// of chain 0 consumes in sweep `sweep`, exactly as sweep_tile generates them (FAST: including the 1/sqrt(3) convention).
+// Test hook: the level-1 variates of MH step `step` (proposal t3 for log lambda / log mu, accept uniform) that customer
+// gid of chain 0 consumes in sweep `sweep`, exactly as sweep_tile generates them (FAST: times the sqrt(3) the kernel
+// folds into the proposal scale).
 template <int MODE>
-__global__ void k_debug_variates(PhiloxRoundKeys rk, uint32_t sweep, long long n, double* t3l, double* t3m, double* uacc) {
+__global__ void k_debug_variates(PhiloxRoundKeys rk, uint32_t sweep, int step, long long n, double* t3l, double* t3m,
+                                 double* uacc) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const uint32_t gid = (uint32_t)i, c3 = dom_word(DOM_SAMPLER, 0u);
-    const uint4 ra = philox4x32_10_rk(gid, sweep, 1u, c3, rk), rb = philox4x32_10_rk(gid, sweep, 2u, c3, rk);
-    if (MODE == MODE_STRICT) {
-      t3l[i] = t3_strict(ra.x, ra.y, ra.z);
-      t3m[i] = t3_strict(ra.w, rb.x, rb.y);
+    const uint32_t gid = (uint32_t)i, c3 = dom_word(DOM_SAMPLER, 0u), slot = 1u + 3u * (uint32_t)(step >> 1);
+    uint32_t w[6];
+    if (step & 1) {
+      const uint4 B = philox4x32_10_rk(gid, sweep, slot + 1u, c3, rk), C = philox4x32_10_rk(gid, sweep, slot + 2u, c3, rk);
+      w[0] = B.z; w[1] = B.w; w[2] = C.x; w[3] = C.y; w[4] = C.z; w[5] = C.w;
     } else {
-      t3l[i] = 1.7320508075688772 * (double)t3_fast(ra.x, ra.y, ra.z);
-      t3m[i] = 1.7320508075688772 * (double)t3_fast(ra.w, rb.x, rb.y);
+      const uint4 A = philox4x32_10_rk(gid, sweep, slot, c3, rk), B = philox4x32_10_rk(gid, sweep, slot + 1u, c3, rk);
+      w[0] = A.x; w[1] = A.y; w[2] = A.z; w[3] = A.w; w[4] = B.x; w[5] = B.y;
     }
-    uacc[i] = u32d(rb.z);
+    if (MODE == MODE_STRICT) {
+      t3l[i] = t3_strict(w[0], w[1], w[2]);
+      t3m[i] = t3_strict(w[3], w[4], w[5]);
+    } else {
+      t3l[i] = 1.7320508075688772 * (double)t3_fast(w[0], w[1], w[2]);
+      t3m[i] = 1.7320508075688772 * (double)t3_fast(w[3], w[4], w[5]);
+    }
+    uacc[i] = u32d(low_bytes(w[0], w[1], w[2], w[3]));
   }
 }
 

@@ -83,6 +83,21 @@ __device__ __forceinline__ float u32f(uint32_t a) { return fmaf((float)a, 0x1.0p
 // top 24 bits ((a >> 8) << 8), so the shift is folded into the conversion: one I2F.RZ + one FFMA.
 __device__ __forceinline__ float u24f(uint32_t a) { return fmaf(__uint2float_rz(a), 0x1.0p-32f, 0x1.0p-25f); }
 
+// the same uniform in fp64 (STRICT transforms)
+__device__ __forceinline__ double u24d(uint32_t a) { return ((double)(a >> 8) + 0.5) * 0x1.0p-24; }
+
+// ---- word layout of the Metropolis steps (sampler domain) ----------------------------------------------------------
+// A step consumes six words: (u1, angle, u3) for the log-lambda proposal and the same for log mu; each transform uses
+// the TOP 24 bits of its word.  The accept uniform is assembled from the LOW bytes of the first four of those words
+// (bits the transforms never see), so a step costs 1.5 Philox blocks instead of 2: steps 2p and 2p+1 share the three
+// blocks of slots 1+3p, 2+3p, 3+3p:
+//   step 2p   : A.x A.y A.z | A.w B.x B.y        step 2p+1 : B.z B.w C.x | C.y C.z C.w
+// Slot 0 is z/tau, slot 1+2S the eta normal (tri).
+__device__ __forceinline__ uint32_t low_bytes(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+  // three PRMT: byte 0 of w0..w3 -> bytes 0..3
+  return __byte_perm(__byte_perm(w0, w1, 0x0040), __byte_perm(w2, w3, 0x0040), 0x5410);
+}
+
 // SFU primitives without the denormal / IEEE-rounding fix-up code the default intrinsics carry
 __device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -92,7 +107,7 @@ __device__ __forceinline__ float cos_ftz(float x) { float y; asm("cos.approx.ftz
 
 // ---- Student t(3) without rejection: N0 / sqrt((N1^2 - 2 ln U3)/3) ---------------------------------
 __device__ __forceinline__ double t3_strict(uint32_t ra, uint32_t rb, uint32_t rc) {
-  double u1 = u32d(ra), u2 = u32d(rb), u3 = u32d(rc);
+  double u1 = u24d(ra), u2 = u24d(rb), u3 = u24d(rc);
   double r = sqrt(-2.0 * log(u1));
   double ang = 6.283185307179586476925286766559 * u2;
   double s, c;

@@ -72,9 +72,34 @@ def u32(a):
     return (np.asarray(a, dtype=np.float64) + 0.5) * (2.0 ** -32)
 
 
+def u24(a):
+    """24-bit uniform strictly inside (0,1) from the TOP 24 bits of a word (the level-1 proposal transforms)."""
+    return ((np.asarray(a, dtype=np.uint64) >> np.uint64(8)).astype(np.float64) + 0.5) * (2.0 ** -24)
+
+
+def low_bytes(w0, w1, w2, w3):
+    """The accept word of a Metropolis step: byte 0 of the first four words of the step -> bytes 0..3."""
+    b = [np.asarray(w, dtype=np.uint64) & np.uint64(0xFF) for w in (w0, w1, w2, w3)]
+    return b[0] | (b[1] << np.uint64(8)) | (b[2] << np.uint64(16)) | (b[3] << np.uint64(24))
+
+
+def step_words(seed, chain, gids, sweep, step):
+    """The six words Metropolis step `step` consumes (clv_rng.cuh, "word layout of the Metropolis steps"): steps 2p and
+    2p+1 share the blocks of slots 1+3p, 2+3p, 3+3p:  A.x A.y A.z | A.w B.x B.y   and   B.z B.w C.x | C.y C.z C.w."""
+    k0, k1 = chain_key(seed, chain)
+    c3 = dom_word(DOM_SAMPLER, chain)
+    slot = 1 + 3 * (step >> 1)
+    b = philox4x32_10(gids, sweep, slot + 1, c3, k0, k1)
+    if step & 1:
+        c = philox4x32_10(gids, sweep, slot + 2, c3, k0, k1)
+        return b[2], b[3], c[0], c[1], c[2], c[3]
+    a = philox4x32_10(gids, sweep, slot, c3, k0, k1)
+    return a[0], a[1], a[2], a[3], b[0], b[1]
+
+
 def t3_from_words(ra, rb, rc):
     """Student-t(3) without rejection: N0 / sqrt((N1^2 - 2 ln U3)/3)."""
-    u1, u2, u3 = u32(ra), u32(rb), u32(rc)
+    u1, u2, u3 = u24(ra), u24(rb), u24(rc)
     r = np.sqrt(-2.0 * np.log(u1))
     ang = TWO_PI * u2
     n0 = r * np.cos(ang)
@@ -111,11 +136,10 @@ def sampler_variates(seed, chain, gids, sweep, n_mh_steps, with_eta=False):
     t3_m = np.empty((S, gids.size))
     u_acc = np.empty((S, gids.size))
     for s in range(S):
-        a = philox4x32_10(gids, sweep, 1 + 2 * s, c3, k0, k1)
-        b = philox4x32_10(gids, sweep, 2 + 2 * s, c3, k0, k1)
-        t3_l[s] = t3_from_words(a[0], a[1], a[2])
-        t3_m[s] = t3_from_words(a[3], b[0], b[1])
-        u_acc[s] = u32(b[2])
+        w = step_words(seed, chain, gids, sweep, s)
+        t3_l[s] = t3_from_words(w[0], w[1], w[2])
+        t3_m[s] = t3_from_words(w[3], w[4], w[5])
+        u_acc[s] = u32(low_bytes(w[0], w[1], w[2], w[3]))
     out.update(t3_l=t3_l, t3_m=t3_m, u_acc=u_acc)
     if with_eta:
         e = philox4x32_10(gids, sweep, 1 + 2 * S, c3, k0, k1)

@@ -378,23 +378,28 @@ def test_level1_variates_fast_vs_strict_vs_oracle():
     from mcmc_clv_model_b200 import _lib as L
     from oracle import philox_np as px
     lib = L.load()
-    n, seed, sweep = 1_000_000, 777, 5
-    out = {}
-    for mode in (L.RNG_STRICT, L.RNG_FAST):
-        a, b, u = np.empty(n), np.empty(n), np.empty(n)
-        L.check(lib.clv_debug_variates(0, seed, sweep, mode, n, L.dptr(a), L.dptr(b), L.dptr(u)))
-        out[mode] = (a, b, u)
-    v = px.sampler_variates(seed, 0, np.arange(n), sweep, 1)
-    np.testing.assert_allclose(out[L.RNG_STRICT][0], v["t3_l"][0], rtol=1e-12)
-    np.testing.assert_allclose(out[L.RNG_STRICT][1], v["t3_m"][0], rtol=1e-12)
-    np.testing.assert_array_equal(out[L.RNG_STRICT][2], v["u_acc"][0])
-    np.testing.assert_array_equal(out[L.RNG_FAST][2], v["u_acc"][0])
-    for j in (0, 1):
-        s, f = out[L.RNG_STRICT][j], out[L.RNG_FAST][j]
-        err = np.abs(f - s) / (1e-3 + np.abs(s))
-        assert np.median(err) < 1e-5 and np.quantile(err, 0.999) < 1e-2, (np.median(err), np.quantile(err, 0.999))
-        assert stats.kstest(f, stats.t(3).cdf).pvalue > 1e-3
-        assert stats.kstest(s, stats.t(3).cdf).pvalue > 1e-3
+    n, seed, sweep, S = 1_000_000, 777, 5, 5
+    v = px.sampler_variates(seed, 0, np.arange(n), sweep, S)
+    for step in (0, 1, 4):           # even / odd step of a pair, and a later pair
+        out = {}
+        for mode in (L.RNG_STRICT, L.RNG_FAST):
+            a, b, u = np.empty(n), np.empty(n), np.empty(n)
+            L.check(lib.clv_debug_variates(0, seed, sweep, step, mode, n, L.dptr(a), L.dptr(b), L.dptr(u)))
+            out[mode] = (a, b, u)
+        np.testing.assert_allclose(out[L.RNG_STRICT][0], v["t3_l"][step], rtol=1e-12)
+        np.testing.assert_allclose(out[L.RNG_STRICT][1], v["t3_m"][step], rtol=1e-12)
+        np.testing.assert_array_equal(out[L.RNG_STRICT][2], v["u_acc"][step])
+        np.testing.assert_array_equal(out[L.RNG_FAST][2], v["u_acc"][step])
+        for j in (0, 1):
+            s, f = out[L.RNG_STRICT][j], out[L.RNG_FAST][j]
+            err = np.abs(f - s) / (1e-3 + np.abs(s))
+            assert np.median(err) < 1e-5 and np.quantile(err, 0.999) < 1e-2, (np.median(err), np.quantile(err, 0.999))
+            assert stats.kstest(f, stats.t(3).cdf).pvalue > 1e-3
+            assert stats.kstest(s, stats.t(3).cdf).pvalue > 1e-3
+        # the accept uniform shares its words with the proposals (low bytes vs top 24 bits): no visible dependence
+        assert stats.kstest(out[L.RNG_FAST][2], "uniform").pvalue > 1e-3
+        for j in (0, 1):
+            assert abs(np.corrcoef(out[L.RNG_FAST][2], np.abs(out[L.RNG_FAST][j]) < 1.0)[0, 1]) < 0.01
     assert abs(np.corrcoef(out[L.RNG_FAST][0], out[L.RNG_FAST][1])[0, 1]) < 0.01
 
 
