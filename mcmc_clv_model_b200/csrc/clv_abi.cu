@@ -404,9 +404,11 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   auto bail = [&](int code) { std::string m = h->err; clv_destroy(h); g_last_error = m; return code; };
 #define CKC(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { fail(h, CLV_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2)); return bail(CLV_ERR_CUDA); } } while (0)
   CKC(cudaSetDevice(cfg->device));
-  cudaDeviceProp prop;
-  CKC(cudaGetDeviceProperties(&prop, cfg->device));
-  h->sm_count = prop.multiProcessorCount;
+  const bool trace = getenv("CLV_TRACE_CREATE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+  auto t_begin = now();
+  CKC(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));   // not cudaGetDeviceProperties: that one costs milliseconds
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   t_alloc_stream = h->stream;
@@ -430,7 +432,9 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   CKC(dmalloc(&h->d_tau, C * N));
   CKC(dmalloc(&h->d_acc, C * NSTAT_MAX));
   CKC(dmalloc(&h->d_err, 1));
+  if (trace) fprintf(stderr, "[clv_create] streams/events + allocation calls %.2f ms\n", ms_since(t_begin));
   CKC(cudaStreamSynchronize(h->stream));      // pool allocations are stream ordered; the memsets below use the legacy stream
+  if (trace) fprintf(stderr, "[clv_create] ... allocations complete %.2f ms\n", ms_since(t_begin));
   CKC(cudaMemset(h->d_err, 0, sizeof(int)));
   CKC(cudaMemset(h->d_acc, 0, sizeof(unsigned long long) * C * NSTAT_MAX));
   CKC(cudaMemset(h->d_params, 0, sizeof(ChainParams) * C));
@@ -440,6 +444,7 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
     CKC(cudaMemcpyToSymbol(c_exptab, et, sizeof et));
   }
   if (upload_rk()) { h->err = g_last_error; return bail(CLV_ERR_CUDA); }
+  if (trace) fprintf(stderr, "[clv_create] ... memsets + constants %.2f ms\n", ms_since(t_begin));
   // grid: a few resident waves of 128-thread blocks, grid-stride over customer tiles
   long long ntiles = (h->N + SWEEP_THREADS - 1) / SWEEP_THREADS;
   long long want = ((long long)h->sm_count * 32 + h->chains - 1) / h->chains;
@@ -476,6 +481,7 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
       h->persist_fits = (long long)h->persist_grid_x == ntiles;
     }
   }
+  if (trace) fprintf(stderr, "[clv_create] ... attributes + occupancy %.2f ms\n", ms_since(t_begin));
 #undef CKC
   *out = h;
   return CLV_OK;
@@ -516,20 +522,28 @@ int clv_set_data(clv_sampler* h, const int32_t* x, const double* t_x, const doub
   CK(h, cudaMemcpyAsync(h->d_T, T_cal, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   if (h->D == 3) CK(h, cudaMemcpyAsync(h->d_logs, log_s, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   double* d_rows = nullptr;
+  int bad_intercept = 0;
   if (h->K > 1) {
     // row-major N x K (column 0 = intercept): one contiguous copy, then split into SoA columns on the device
     CK(h, dmalloc(&d_rows, N * (size_t)h->K));
-    cudaError_t e = cudaMemcpyAsync(d_rows, X, N * (size_t)h->K * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    cudaError_t e = cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rows, X, N * (size_t)h->K * sizeof(double), cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) {
-      k_split_columns<<<h->sm_count * 8, 256, 0, h->stream>>>(d_rows, (long long)N, h->K, h->d_Xc);
+      k_split_columns<<<h->sm_count * 8, 256, 0, h->stream>>>(d_rows, (long long)N, h->K, h->d_Xc, h->d_err);
       h->launches++;
       e = cudaGetLastError();
     }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad_intercept, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream);
     if (e != cudaSuccess) { dfree(d_rows); return fail(h, CLV_ERR_CUDA, "design-matrix upload failed: %s", cudaGetErrorString(e)); }
+  } else {
+    for (size_t i = 0; i < N; ++i)
+      if (X[i] != 1.0) { bad_intercept = 1; break; }
   }
   cudaError_t es = cudaStreamSynchronize(h->stream);
   if (d_rows) dfree(d_rows);
   if (es != cudaSuccess) return fail(h, CLV_ERR_CUDA, "clv_set_data failed: %s", cudaGetErrorString(es));
+  if (bad_intercept) return fail(h, CLV_ERR_ARG, "column 0 of X must be the intercept (all ones)");
   h->have_data = true;
   h->inited = false;
   return CLV_OK;
@@ -1051,26 +1065,31 @@ static int run_impl(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, 
   int buf = 0;
   long long chunk_base = 0;
   bool used[2] = {false, false};
-  auto flush = [&](long long filled) -> int {
-    // chunk [chunk_base, chunk_base+filled) of every chain -> host, on the copy stream
-    CK(h, cudaEventRecord(h->ev_chunk_ready[buf], h->stream));
-    CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_chunk_ready[buf], 0));
+  // A full chunk is handed to the copy stream in two steps: the "ready" event is recorded right after the segment
+  // that filled it, but its device->host copies are issued only after the NEXT segment has been enqueued.  A copy into
+  // pageable host memory blocks the calling thread, and this order lets the GPU run that segment meanwhile.
+  struct PendingChunk { bool active = false; int buf = 0; long long base = 0, filled = 0; } pend;
+  auto issue_copies = [&]() -> int {
+    if (!pend.active) return 0;
+    pend.active = false;
+    // chunk [base, base+filled) of every chain -> host, on the copy stream
+    CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_chunk_ready[pend.buf], 0));
     for (long long c = 0; c < C; ++c)
-      CK(h, cudaMemcpyAsync(level1 + ((size_t)c * n_draws + chunk_base) * N * nc, h->d_draws[buf] + (size_t)c * cap * N * nc,
-                            (size_t)filled * N * nc * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
-    CK(h, cudaEventRecord(h->ev_copy_done[buf], h->copy_stream));
-    used[buf] = true;
+      CK(h, cudaMemcpyAsync(level1 + ((size_t)c * n_draws + pend.base) * N * nc, h->d_draws[pend.buf] + (size_t)c * cap * N * nc,
+                            (size_t)pend.filled * N * nc * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(h, cudaEventRecord(h->ev_copy_done[pend.buf], h->copy_stream));
     return 0;
   };
-  // The run is cut into segments that end where the host has to act: a full draw chunk (flush), a progress
-  // callback, or the end.  A segment is one cooperative launch (persistent mode) or 2 launches per sweep.
+  // The run is cut into segments that end where the host has to act: a full draw chunk (flush), the last kept draw
+  // (so that its copy overlaps the trailing non-kept sweeps), a progress callback, or the end.  A segment is one
+  // cooperative launch (persistent mode) or 2 launches per sweep.
   long long step = 1;
   while (step <= total) {
     long long seg_end = total;
-    if (store) {
+    if (store && chunk_base < n_draws) {
       const long long last_draw = std::min(n_draws - 1, chunk_base + cap - 1);
       seg_end = std::min(seg_end, burnin + 1 + last_draw * thin);
-      if (last_draw == n_draws - 1) seg_end = total;         // trailing non-kept sweeps ride with the last chunk
+      if (!level1 && last_draw == n_draws - 1) seg_end = total;      // resident draws: nothing to copy, one segment
     }
     if (trace > 0) seg_end = std::min(seg_end, ((step + trace - 1) / trace) * trace);
     seg_end = std::min(seg_end, step + 19999);
@@ -1079,14 +1098,19 @@ static int run_impl(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, 
     rc.step0 = step; rc.draws = store ? h->d_draws[buf] : nullptr; rc.keep_any = true;
     if (int r = run_segment(h, rc, seg_end - step + 1, seg_end == total)) return r;
     step = seg_end + 1;
-    if (level1) {
+    if (int r = issue_copies()) return r;          // the previous chunk, now overlapping the segment just enqueued
+    if (level1 && chunk_base < n_draws) {
       // draws kept so far: those with burnin + 1 + d*thin <= seg_end
       const long long kept_upto = seg_end > burnin ? std::min(n_draws, (seg_end - burnin - 1) / thin + 1) : 0;
       const long long filled = kept_upto - chunk_base;
       if (filled > 0 && (filled == cap || kept_upto == n_draws)) {
-        if (int r = flush(filled)) return r;
+        CK(h, cudaEventRecord(h->ev_chunk_ready[buf], h->stream));
+        pend.active = true; pend.buf = buf; pend.base = chunk_base; pend.filled = filled;
+        used[buf] = true;
         chunk_base += filled;
         if (kept_upto != n_draws) {
+          // the other buffer is written next: wait for ITS copies (issued at the latest right after the previous
+          // segment was enqueued, so the event is recorded)
           buf ^= 1;
           if (used[buf]) CK(h, cudaStreamWaitEvent(h->stream, h->ev_copy_done[buf], 0));
         }
@@ -1097,6 +1121,7 @@ static int run_impl(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, 
       if (cb) cb(user, seg_end, total);
     }
   }
+  if (int r = issue_copies()) return r;
   if (int r = check_device_error(h)) return r;
   CK(h, cudaMemcpyAsync(level2, h->d_level2, sizeof(double) * C * n_draws * h->P, cudaMemcpyDeviceToHost, h->stream));
   std::vector<long long> ll((size_t)(C * n_draws));

@@ -590,12 +590,15 @@ __global__ void __launch_bounds__(256) k_init_state(const double* t_x, long long
   }
 }
 
-// row-major (N, K) design matrix -> SoA covariate columns [(K-1)][N] (column 0, the intercept, is implicit)
-__global__ void __launch_bounds__(256) k_split_columns(const double* X, long long N, int K, double* Xc) {
+// row-major (N, K) design matrix -> SoA covariate columns [(K-1)][N].  Column 0, the intercept, is implicit; it is
+// checked here (*bad_intercept = 1 unless it is all ones) instead of by a strided host pass over the matrix.
+__global__ void __launch_bounds__(256) k_split_columns(const double* X, long long N, int K, double* Xc, int* bad_intercept) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < N * K; t += (long long)gridDim.x * blockDim.x) {
     const long long i = t / K;
     const int k = (int)(t - i * K);
-    if (k > 0) Xc[(long long)(k - 1) * N + i] = X[t];
+    const double v = X[t];
+    if (k > 0) Xc[(long long)(k - 1) * N + i] = v;
+    else if (v != 1.0) *bad_intercept = 1;
   }
 }
 

@@ -52,8 +52,6 @@ class Sampler:
         X = np.ascontiguousarray(X, dtype=np.float64)
         if X.ndim != 2 or X.shape[0] != x.size:
             raise ValueError("X must be (N, K)")
-        if not np.all(X[:, 0] == 1.0):
-            raise ValueError("column 0 of X must be the intercept (all ones)")
         N, K = X.shape
         D = int(model_dim)
         if D == 3:
@@ -73,8 +71,13 @@ class Sampler:
                        gid_offset=int(gid_offset), seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
         L.check(self.lib.clv_create(C.byref(self.h), C.byref(cfg)))
         try:
-            L.check(self.lib.clv_set_data(self.h, x.ctypes.data_as(L.c_int32_p), L.dptr(t_x), L.dptr(T_cal),
-                                          L.dptr(X), L.dptr(log_s)), self.h)
+            try:
+                L.check(self.lib.clv_set_data(self.h, x.ctypes.data_as(L.c_int32_p), L.dptr(t_x), L.dptr(T_cal),
+                                              L.dptr(X), L.dptr(log_s)), self.h)
+            except L.ClvError as e:        # the intercept column is validated on the device during the upload
+                if "intercept" in str(e):
+                    raise ValueError("column 0 of X must be the intercept (all ones)") from None
+                raise
             hy = hyper or default_hyper(K, D)
             b0 = np.ascontiguousarray(hy["beta_0"], dtype=np.float64)
             a0 = np.ascontiguousarray(hy["A_0"], dtype=np.float64)
