@@ -447,7 +447,9 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   if (trace) fprintf(stderr, "[clv_create] ... memsets + constants %.2f ms\n", ms_since(t_begin));
   // grid: a few resident waves of 128-thread blocks, grid-stride over customer tiles
   long long ntiles = (h->N + SWEEP_THREADS - 1) / SWEEP_THREADS;
-  long long want = ((long long)h->sm_count * 32 + h->chains - 1) / h->chains;
+  long long per_sm_blocks = 32;
+  if (const char* env = getenv("CLV_SWEEP_BLOCKS_PER_SM")) per_sm_blocks = std::max(1ll, atoll(env));   // tuning knob
+  long long want = ((long long)h->sm_count * per_sm_blocks + h->chains - 1) / h->chains;
   h->grid_x = (int)std::max<long long>(1, std::min(ntiles, want));
   h->stats_smem = (size_t)(h->K * h->D + h->D * (h->D + 1) / 2 + 1) * SWEEP_THREADS * sizeof(long long);
   if (h->stats_smem > 48 * 1024) {
