@@ -377,6 +377,21 @@ def run_ours(args):
                                  "algorithmic_bytes_per_cell": 32},
                     "mean_x_star": float(fr["mean_x_star"].mean()), "mean_p_alive": float(fr["p_alive"].mean()),
                     "holdout_mean_x_star_generated": float(fc["x_star"].mean())}
+        # the API path of draw_future_transactions (SURVEY 8d, C5 ii): host (n_draws, N, 4) f64 in, host (n_draws, N)
+        # int64 out through clv_forecast -- 40 bytes per cell over PCIe, which is what bounds it
+        from mcmc_clv_model_b200.api import _forecast
+        nd_api = 64
+        l1 = np.empty((nd_api, nf, 4))
+        l1[:, :, 0] = fc["lambda_true"]; l1[:, :, 1] = fc["mu_true"]; l1[:, :, 2] = fc["tau_true"]
+        l1[:, :, 3] = (fc["tau_true"] > fc["T_cal"]).astype(np.float64)
+        _forecast(fc["T_cal"], [l1[:4]], 39.0, 42, False, 0.5, device=local)      # warm-up (streams, pool)
+        t0 = time.perf_counter()
+        xs, _ = _forecast(fc["T_cal"], [l1], 39.0, 42, False, 0.5, device=local)
+        dt = time.perf_counter() - t0
+        forecast["api_path"] = {"config": f"{nf} customers x {nd_api} draws, pageable host arrays in and out (the reference's layouts)",
+                                "cells_per_sec": nf * nd_api / dt, "seconds": dt, "pcie_GBps": nf * nd_api * 40 / dt / 1e9,
+                                "bound": "PCIe + pageable staging (40 B per cell)", "mean_x_star": float(xs.mean())}
+        del l1, xs
 
     line = {"metric": METRIC, "value": value, "unit": "customer-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
