@@ -79,6 +79,26 @@ def test_strict_philox_trajectory_vs_oracle(cdnow_abe, D, cov):
         np.testing.assert_allclose(out["loglik_sum"][0] / n, ora["log_likelihood"], rtol=RTOL)
 
 
+@pytest.mark.parametrize("S", [1, 2, 5, 7])
+def test_strict_philox_odd_step_counts_vs_oracle(cdnow_abe, S):
+    """n_mh_steps other than the default: two Metropolis steps share three Philox blocks, so odd counts end on a
+    half-used pair (and S=1 never enters the paired loop).  Both sweep paths against the oracle replay."""
+    d = cdnow_abe
+    n = 300
+    X = np.column_stack([np.ones(n), d["first_sales_scaled"][:n]])
+    cbs = ao.Cbs(x=d["x"][:n].astype(np.int64), t_x=d["t_x"][:n], T_cal=d["T_cal"][:n], X=X, log_s=d["log_s"][:n])
+    for D in (2, 3):
+        ora = ao.run_chain(cbs, ao.default_hyper(cbs.K, D), PhiloxStreams(77, 0, np.arange(n), S, D, cbs.K),
+                           mcmc=4, burnin=3, thin=1, D=D, n_mh_steps=S)
+        for mode in ("stream", "persistent"):
+            with Sampler(cbs.x, cbs.t_x, cbs.T_cal, X, cbs.log_s if D == 3 else None, model_dim=D, n_mh_steps=S, seed=77,
+                         rng="strict", sweep_mode=mode) as s:
+                out = s.run(3, 4, 1)
+            np.testing.assert_array_equal(out["level_1"][0][:, :, 3], ora["level_1"][:, :, 3])
+            np.testing.assert_allclose(out["level_1"][0], ora["level_1"], rtol=RTOL)
+            np.testing.assert_allclose(out["level_2"][0], ora["level_2"], rtol=RTOL, atol=1e-9)
+
+
 def test_chain_offset_reproduces_chain(cdnow_abe):
     """Any chain of a run can be reproduced alone (`chains=1, chain_offset=c`): the counterpart of the reference's
     `chains=1, seed=seed+ch` (bi:486) under a counter-based RNG whose chain index travels in the counter."""
