@@ -6,11 +6,14 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -251,6 +254,143 @@ double i128_scaled(__int128 t, int bits) {
     m = (double)(uint64_t)q;
   }
   return std::ldexp(neg ? -m : m, sh - bits);
+}
+
+// ---- host transfer engine -------------------------------------------------------------------------
+// A device->host (or host->device) copy whose host side is ordinary pageable memory runs at 3-5 GB/s through the
+// driver's own staging: one thread copies, and a freshly allocated destination faults its pages in on that thread.
+// Here the copy is cut into pieces that travel through a small ring of page-locked buffers (DMA at PCIe speed), and a
+// few worker threads move each piece between the ring and the caller's array in parallel (first-touch page faults
+// included).  The level-1 draws of the reference's full-data run are 12 GB; this is what bounds that run.
+class HostCopyPool {
+ public:
+  static HostCopyPool& get() { static HostCopyPool p; return p; }
+  int threads() const { return (int)workers_.size() + 1; }
+  // memcpy split over the workers and the calling thread; returns when all parts are done
+  void copy(void* dst, const void* src, size_t bytes) {
+    const int parts = bytes < (4u << 20) ? 1 : threads();
+    if (parts == 1) { memcpy(dst, src, bytes); return; }
+    const size_t per = ((bytes + parts - 1) / parts + 4095) & ~(size_t)4095;
+    {
+      std::lock_guard<std::mutex> g(m_);
+      for (int t = 1; t < parts; ++t) {
+        const size_t off = std::min(bytes, per * t), len = std::min(per, bytes - off);
+        if (len) { jobs_.push_back({(char*)dst + off, (const char*)src + off, len}); ++pending_; }
+      }
+    }
+    cv_.notify_all();
+    memcpy(dst, src, std::min(per, bytes));
+    std::unique_lock<std::mutex> g(m_);
+    done_cv_.wait(g, [&] { return pending_ == 0; });
+  }
+
+ private:
+  struct Job { char* dst; const char* src; size_t len; };
+  HostCopyPool() {
+    int n = (int)std::thread::hardware_concurrency() / 2;
+    if (const char* env = getenv("CLV_COPY_THREADS")) n = atoi(env);
+    n = std::max(1, std::min(n, 8));
+    for (int t = 1; t < n; ++t) workers_.emplace_back([this] { run(); });
+  }
+  ~HostCopyPool() {
+    { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& w : workers_) w.join();
+  }
+  void run() {
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return stop_ || !jobs_.empty(); });
+        if (jobs_.empty()) return;
+        j = jobs_.back();
+        jobs_.pop_back();
+      }
+      memcpy(j.dst, j.src, j.len);
+      {
+        std::lock_guard<std::mutex> g(m_);
+        if (--pending_ == 0) done_cv_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::vector<Job> jobs_;
+  std::mutex m_;
+  std::condition_variable cv_, done_cv_;
+  int pending_ = 0;
+  bool stop_ = false;
+};
+
+constexpr size_t STAGE_PIECE = 32u << 20;      // bytes per ring slot
+constexpr int STAGE_SLOTS = 3;
+struct StagingRing {
+  char* slot[STAGE_SLOTS] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev[STAGE_SLOTS] = {nullptr, nullptr, nullptr};
+  bool ok = false;
+};
+// one ring per calling thread (the chains-over-devices driver runs one sampler per thread); lives for the process
+StagingRing& staging_ring() {
+  static thread_local StagingRing r;
+  if (!r.ok) {
+    bool good = true;
+    for (int i = 0; i < STAGE_SLOTS && good; ++i) {
+      good = cudaHostAlloc((void**)&r.slot[i], STAGE_PIECE, cudaHostAllocDefault) == cudaSuccess &&
+             cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!good) cudaGetLastError();
+    r.ok = good;
+  }
+  return r;
+}
+size_t staging_min_bytes() {
+  const char* e = getenv("CLV_STAGING_MIN_BYTES");      // smaller copies take the driver's own pageable path
+  return e ? (size_t)atoll(e) : (size_t)(64u << 20);
+}
+
+// device -> pageable host, ordered after everything already in `stream`; returns when the data is in `dst`
+cudaError_t copy_to_host_staged(void* dst, const void* src_dev, size_t bytes, cudaStream_t stream) {
+  if (bytes < staging_min_bytes()) return cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, stream);
+  StagingRing& r = staging_ring();
+  if (!r.ok) return cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, stream);
+  HostCopyPool& pool = HostCopyPool::get();
+  const size_t n = (bytes + STAGE_PIECE - 1) / STAGE_PIECE;
+  auto issue = [&](size_t i) -> cudaError_t {
+    const size_t off = i * STAGE_PIECE, len = std::min(STAGE_PIECE, bytes - off);
+    cudaError_t e = cudaMemcpyAsync(r.slot[i % STAGE_SLOTS], (const char*)src_dev + off, len, cudaMemcpyDeviceToHost, stream);
+    return e != cudaSuccess ? e : cudaEventRecord(r.ev[i % STAGE_SLOTS], stream);
+  };
+  cudaError_t e = cudaSuccess;
+  for (size_t i = 0; i < std::min<size_t>(n, STAGE_SLOTS - 1) && e == cudaSuccess; ++i) e = issue(i);
+  for (size_t i = 0; i < n && e == cudaSuccess; ++i) {
+    if (i + STAGE_SLOTS - 1 < n) e = issue(i + STAGE_SLOTS - 1);      // its slot was emptied in iteration i - 1
+    if (e == cudaSuccess) e = cudaEventSynchronize(r.ev[i % STAGE_SLOTS]);
+    const size_t off = i * STAGE_PIECE, len = std::min(STAGE_PIECE, bytes - off);
+    if (e == cudaSuccess) pool.copy((char*)dst + off, r.slot[i % STAGE_SLOTS], len);
+  }
+  return e;
+}
+
+// pageable host -> device; returns when the last piece has been handed to the copy engine (stream ordered after that)
+cudaError_t copy_to_device_staged(void* dst_dev, const void* src, size_t bytes, cudaStream_t stream) {
+  if (bytes < staging_min_bytes()) return cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, stream);
+  StagingRing& r = staging_ring();
+  if (!r.ok) return cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, stream);
+  HostCopyPool& pool = HostCopyPool::get();
+  const size_t n = (bytes + STAGE_PIECE - 1) / STAGE_PIECE;
+  cudaError_t e = cudaSuccess;
+  for (size_t i = 0; i < n && e == cudaSuccess; ++i) {
+    const int sl = (int)(i % STAGE_SLOTS);
+    if (i >= STAGE_SLOTS) e = cudaEventSynchronize(r.ev[sl]);          // the DMA that last read this slot
+    const size_t off = i * STAGE_PIECE, len = std::min(STAGE_PIECE, bytes - off);
+    if (e == cudaSuccess) pool.copy(r.slot[sl], (const char*)src + off, len);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((char*)dst_dev + off, r.slot[sl], len, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaEventRecord(r.ev[sl], stream);
+  }
+  // the ring is reused by the next call: its slots must have been read
+  for (int sl = 0; sl < STAGE_SLOTS && e == cudaSuccess; ++sl)
+    if ((size_t)sl < n) e = cudaEventSynchronize(r.ev[sl]);
+  return e;
 }
 
 SweepArgs base_args(clv_sampler* h) {
@@ -1067,29 +1207,38 @@ static int run_impl(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, 
   int buf = 0;
   long long chunk_base = 0;
   bool used[2] = {false, false};
-  // A full chunk is handed to the copy stream in two steps: the "ready" event is recorded right after the segment
-  // that filled it, but its device->host copies are issued only after the NEXT segment has been enqueued.  A copy into
-  // pageable host memory blocks the calling thread, and this order lets the GPU run that segment meanwhile.
-  struct PendingChunk { bool active = false; int buf = 0; long long base = 0, filled = 0; } pend;
+  // Kept draws go to the host in pieces of about FLUSH_BYTES (all chains), not chunk by chunk: a piece is recorded
+  // "ready" right after the segment that completed it, and its device->host copies are issued only after the NEXT
+  // segment has been enqueued -- the copy keeps the calling thread busy (staging ring + parallel memcpy into the
+  // caller's pageable array), and this order lets the GPU sample meanwhile.  When the run does not fit one device
+  // chunk, two chunk buffers alternate; a buffer is rewritten only after the copies of its last piece.
+  const long long per_draw_bytes = C * N * nc * (long long)sizeof(double);
+  long long flush_bytes = 512ll << 20;
+  if (const char* env = getenv("CLV_FLUSH_BYTES")) flush_bytes = std::max(1ll, atoll(env));
+  const long long flush_every = std::max<long long>(1, flush_bytes / std::max<long long>(1, per_draw_bytes));
+  long long flushed = 0;                        // draws already handed to the copy path
+  struct PendingPiece { bool active = false; int buf = 0; long long first = 0, count = 0, chunk_base = 0; } pend;
   auto issue_copies = [&]() -> int {
     if (!pend.active) return 0;
     pend.active = false;
-    // chunk [base, base+filled) of every chain -> host, on the copy stream
+    // draws [first, first+count) of every chain -> host, on the copy stream
     CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_chunk_ready[pend.buf], 0));
     for (long long c = 0; c < C; ++c)
-      CK(h, cudaMemcpyAsync(level1 + ((size_t)c * n_draws + pend.base) * N * nc, h->d_draws[pend.buf] + (size_t)c * cap * N * nc,
-                            (size_t)pend.filled * N * nc * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+      CK(h, copy_to_host_staged(level1 + ((size_t)c * n_draws + pend.first) * N * nc,
+                                h->d_draws[pend.buf] + ((size_t)c * cap + (pend.first - pend.chunk_base)) * N * nc,
+                                (size_t)pend.count * N * nc * sizeof(double), h->copy_stream));
     CK(h, cudaEventRecord(h->ev_copy_done[pend.buf], h->copy_stream));
     return 0;
   };
-  // The run is cut into segments that end where the host has to act: a full draw chunk (flush), the last kept draw
-  // (so that its copy overlaps the trailing non-kept sweeps), a progress callback, or the end.  A segment is one
-  // cooperative launch (persistent mode) or 2 launches per sweep.
+  // The run is cut into segments that end where the host has to act: a piece of draws to flush, a full chunk, the
+  // last kept draw (so that its copy overlaps the trailing non-kept sweeps), a progress callback, or the end.  A
+  // segment is one cooperative launch (persistent mode) or 2 launches per sweep.
   long long step = 1;
   while (step <= total) {
     long long seg_end = total;
-    if (store && chunk_base < n_draws) {
-      const long long last_draw = std::min(n_draws - 1, chunk_base + cap - 1);
+    if (store && flushed < n_draws) {
+      long long last_draw = std::min(n_draws - 1, chunk_base + cap - 1);
+      if (level1) last_draw = std::min(last_draw, flushed + flush_every - 1);
       seg_end = std::min(seg_end, burnin + 1 + last_draw * thin);
       if (!level1 && last_draw == n_draws - 1) seg_end = total;      // resident draws: nothing to copy, one segment
     }
@@ -1100,19 +1249,20 @@ static int run_impl(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, 
     rc.step0 = step; rc.draws = store ? h->d_draws[buf] : nullptr; rc.keep_any = true;
     if (int r = run_segment(h, rc, seg_end - step + 1, seg_end == total)) return r;
     step = seg_end + 1;
-    if (int r = issue_copies()) return r;          // the previous chunk, now overlapping the segment just enqueued
-    if (level1 && chunk_base < n_draws) {
+    if (int r = issue_copies()) return r;          // the previous piece, now overlapping the segment just enqueued
+    if (level1 && flushed < n_draws) {
       // draws kept so far: those with burnin + 1 + d*thin <= seg_end
       const long long kept_upto = seg_end > burnin ? std::min(n_draws, (seg_end - burnin - 1) / thin + 1) : 0;
-      const long long filled = kept_upto - chunk_base;
-      if (filled > 0 && (filled == cap || kept_upto == n_draws)) {
+      const bool chunk_full = kept_upto - chunk_base == cap;
+      if (kept_upto > flushed && (kept_upto - flushed >= flush_every || chunk_full || kept_upto == n_draws)) {
         CK(h, cudaEventRecord(h->ev_chunk_ready[buf], h->stream));
-        pend.active = true; pend.buf = buf; pend.base = chunk_base; pend.filled = filled;
+        pend.active = true; pend.buf = buf; pend.first = flushed; pend.count = kept_upto - flushed; pend.chunk_base = chunk_base;
         used[buf] = true;
-        chunk_base += filled;
-        if (kept_upto != n_draws) {
-          // the other buffer is written next: wait for ITS copies (issued at the latest right after the previous
-          // segment was enqueued, so the event is recorded)
+        flushed = kept_upto;
+        if (chunk_full && kept_upto != n_draws) {
+          // the other buffer is written next: wait for ITS last copies (issued at the latest right after the
+          // previous segment was enqueued, so the event is recorded)
+          chunk_base = kept_upto;
           buf ^= 1;
           if (used[buf]) CK(h, cudaStreamWaitEvent(h->stream, h->ev_copy_done[buf], 0));
         }
@@ -1379,7 +1529,7 @@ static int forecast_host(const clv_forecast_config* cfg, const double* level1, c
   int b = 0;
   for (long long d0 = 0; d0 < nd; d0 += chunk, b ^= 1) {
     const long long n = std::min(chunk, nd - d0);
-    CKF(cudaMemcpyAsync(d_l1[b], level1 + (size_t)d0 * N * nc, (size_t)(n * N * nc) * 8, cudaMemcpyHostToDevice, st[b]));
+    CKF(copy_to_device_staged(d_l1[b], level1 + (size_t)d0 * N * nc, (size_t)(n * N * nc) * 8, st[b]));
     if (inject) {
       CKF(cudaMemcpyAsync(d_u[b], u + (size_t)d0 * N, (size_t)(n * N) * 8, cudaMemcpyHostToDevice, st[b]));
       if (want_spend) CKF(cudaMemcpyAsync(d_off[b], eps_offset + (size_t)d0 * N, (size_t)(n * N) * 8, cudaMemcpyHostToDevice, st[b]));
@@ -1394,8 +1544,8 @@ static int forecast_host(const clv_forecast_config* cfg, const double* level1, c
     a.x_out = d_x[b]; a.spend_out = want_spend ? d_sp[b] : nullptr;
     a.rk = round_keys(cfg->seed);
     if ((rc = launch_forecast(&c2, a, inject, st[b]))) { cleanup(); return rc; }
-    CKF(cudaMemcpyAsync(x_star + (size_t)d0 * N, d_x[b], (size_t)(n * N) * 8, cudaMemcpyDeviceToHost, st[b]));
-    if (want_spend) CKF(cudaMemcpyAsync(spend + (size_t)d0 * N, d_sp[b], (size_t)(n * N) * 8, cudaMemcpyDeviceToHost, st[b]));
+    CKF(copy_to_host_staged(x_star + (size_t)d0 * N, d_x[b], (size_t)(n * N) * 8, st[b]));
+    if (want_spend) CKF(copy_to_host_staged(spend + (size_t)d0 * N, d_sp[b], (size_t)(n * N) * 8, st[b]));
   }
   CKF(cudaStreamSynchronize(st[0]));
   CKF(cudaStreamSynchronize(st[1]));

@@ -245,6 +245,40 @@ def test_persistent_kernel_equals_stream_mode(cdnow_abe, D):
         del os.environ["CLV_DRAW_BUFFER_BYTES"]
 
 
+def test_staged_host_transfers_give_the_same_arrays():
+    """Level-1 draws and forecast arrays travel through a ring of page-locked buffers with a parallel host memcpy when
+    they are large (>= 64 MB); small ones take the driver's pageable path.  Both must deliver identical arrays, for
+    every piece size / flush granularity, with one and with two device chunk buffers."""
+    import os
+    from mcmc_clv_model_b200.synthetic import C4_BETA, C4_GAMMA, C4_SEED, C4_T_CAL, generate_cbs_arrays
+    from mcmc_clv_model_b200.api import _forecast
+    n = 150_000
+    c = generate_cbs_arrays(n, C4_BETA, C4_GAMMA, T_cal=C4_T_CAL, seed=C4_SEED, with_truth=False)
+    def run(env):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            with Sampler(c["x"], c["t_x"], c["T_cal"], c["X"], chains=2, seed=3, sweep_mode="stream") as s:
+                out = s.run(2, 21, 2)                        # 11 draws x 2 chains x 4.8 MB
+            xs, _ = _forecast(c["T_cal"], out["level_1"], 39.0, 5, False, 0.5)
+        finally:
+            for k, v in old.items():
+                if v is None: os.environ.pop(k, None)
+                else: os.environ[k] = v
+        return out, xs
+    ref, xs_ref = run({"CLV_STAGING_MIN_BYTES": str(1 << 40)})           # never staged
+    assert ref["level_1"].shape == (2, 11, n, 4)
+    per_draw = 2 * n * 4 * 8
+    for env in ({"CLV_STAGING_MIN_BYTES": "0"},                                                   # staged, one piece per chain and flush
+                {"CLV_STAGING_MIN_BYTES": "0", "CLV_FLUSH_BYTES": str(3 * per_draw)},            # 3 draws per flush
+                {"CLV_STAGING_MIN_BYTES": "0", "CLV_FLUSH_BYTES": str(2 * per_draw),
+                 "CLV_DRAW_BUFFER_BYTES": str(2 * 5 * per_draw)}):                                # two chunk buffers of 5 draws
+        out, xs = run(env)
+        for k in ("level_1", "level_2", "loglik_sum"):
+            np.testing.assert_array_equal(out[k], ref[k], err_msg=f"{env} {k}")
+        np.testing.assert_array_equal(xs, xs_ref, err_msg=str(env))
+
+
 def test_resident_forecast_equals_host_path(cdnow_abe):
     """Forecast straight from the draws left in HBM == forecast of the same draws through the host API
     (same Philox counters: global customer id, chain-major draw index), and its fused reductions are exact."""
