@@ -268,7 +268,7 @@ class HostCopyPool {
   int threads() const { return (int)workers_.size() + 1; }
   // memcpy split over the workers and the calling thread; returns when all parts are done
   void copy(void* dst, const void* src, size_t bytes) {
-    const int parts = bytes < (4u << 20) ? 1 : threads();
+    const int parts = bytes < (2u << 20) ? 1 : threads();
     if (parts == 1) { memcpy(dst, src, bytes); return; }
     const size_t per = ((bytes + parts - 1) / parts + 4095) & ~(size_t)4095;
     {
@@ -322,7 +322,8 @@ class HostCopyPool {
   bool stop_ = false;
 };
 
-constexpr size_t STAGE_PIECE = 32u << 20;      // bytes per ring slot
+// bytes per ring slot (page-locking costs ~1.5 ms per MB: keep the ring small); CLV_STAGE_PIECE_MB overrides
+static const size_t STAGE_PIECE = [] { const char* e = getenv("CLV_STAGE_PIECE_MB"); return (size_t)std::max(1, e ? atoi(e) : 16) << 20; }();
 constexpr int STAGE_SLOTS = 3;
 struct StagingRing {
   char* slot[STAGE_SLOTS] = {nullptr, nullptr, nullptr};
@@ -348,9 +349,16 @@ size_t staging_min_bytes() {
   return e ? (size_t)atoll(e) : (size_t)(64u << 20);
 }
 
+// page-locked (cudaHostAlloc / cudaHostRegister) memory goes straight to the copy engine
+bool is_page_locked(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
 // device -> pageable host, ordered after everything already in `stream`; returns when the data is in `dst`
 cudaError_t copy_to_host_staged(void* dst, const void* src_dev, size_t bytes, cudaStream_t stream) {
-  if (bytes < staging_min_bytes()) return cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, stream);
+  if (bytes < staging_min_bytes() || is_page_locked(dst)) return cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, stream);
   StagingRing& r = staging_ring();
   if (!r.ok) return cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, stream);
   HostCopyPool& pool = HostCopyPool::get();
@@ -373,7 +381,7 @@ cudaError_t copy_to_host_staged(void* dst, const void* src_dev, size_t bytes, cu
 
 // pageable host -> device; returns when the last piece has been handed to the copy engine (stream ordered after that)
 cudaError_t copy_to_device_staged(void* dst_dev, const void* src, size_t bytes, cudaStream_t stream) {
-  if (bytes < staging_min_bytes()) return cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, stream);
+  if (bytes < staging_min_bytes() || is_page_locked(src)) return cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, stream);
   StagingRing& r = staging_ring();
   if (!r.ok) return cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, stream);
   HostCopyPool& pool = HostCopyPool::get();
@@ -660,8 +668,8 @@ int clv_set_data(clv_sampler* h, const int32_t* x, const double* t_x, const doub
   CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   const size_t N = (size_t)h->N;
   CK(h, cudaMemcpyAsync(h->d_x, x, N * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaMemcpyAsync(h->d_tx, t_x, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaMemcpyAsync(h->d_T, T_cal, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(h, copy_to_device_staged(h->d_tx, t_x, N * sizeof(double), h->stream));
+  CK(h, copy_to_device_staged(h->d_T, T_cal, N * sizeof(double), h->stream));
   if (h->D == 3) CK(h, cudaMemcpyAsync(h->d_logs, log_s, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   double* d_rows = nullptr;
   int bad_intercept = 0;
@@ -669,7 +677,7 @@ int clv_set_data(clv_sampler* h, const int32_t* x, const double* t_x, const doub
     // row-major N x K (column 0 = intercept): one contiguous copy, then split into SoA columns on the device
     CK(h, dmalloc(&d_rows, N * (size_t)h->K));
     cudaError_t e = cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rows, X, N * (size_t)h->K * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = copy_to_device_staged(d_rows, X, N * (size_t)h->K * sizeof(double), h->stream);
     if (e == cudaSuccess) {
       k_split_columns<<<h->sm_count * 8, 256, 0, h->stream>>>(d_rows, (long long)N, h->K, h->d_Xc, h->d_err);
       h->launches++;
@@ -1625,7 +1633,7 @@ int clv_upload_draws(clv_sampler* h, const double* level1, int64_t n_draws) {
     if (e != cudaSuccess) return fail(h, CLV_ERR_CUDA, "cannot allocate %lld bytes for the draws: %s", bytes, cudaGetErrorString(e));
     h->draws_cap_bytes[0] = bytes;
   }
-  CK(h, cudaMemcpyAsync(h->d_draws[0], level1, (size_t)bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(h, copy_to_device_staged(h->d_draws[0], level1, (size_t)bytes, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
   h->resident_draws = n_draws;
   return CLV_OK;
