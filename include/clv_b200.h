@@ -255,6 +255,10 @@ int clv_elog2cbs(int device, int64_t n_events, const int64_t* cust, const int32_
 int clv_debug_variates(int device, uint64_t seed, uint32_t sweep, int32_t step, int rng_mode, int64_t n, double* t3_l,
                        double* t3_m, double* u_acc);
 
+/* ---- test hook: the parallel host memcpy behind the staged transfers (no device involved): copies `bytes` from src to
+ * dst on the library's copy threads, returns the number of threads that took part. */
+int clv_debug_host_copy(void* dst, const void* src, int64_t bytes);
+
 /* ---- micro-benchmarks used by bench.py for the issue-rate roofline -------------------------- */
 /* Measures, on `device`, sustained warp-instruction throughput of dependent-free loops of
  * FFMA, IMAD (32-bit), MUFU.EX2 and DFMA.  out[4] = giga thread-ops/s for each. */

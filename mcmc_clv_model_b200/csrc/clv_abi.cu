@@ -330,20 +330,44 @@ struct StagingRing {
   cudaEvent_t ev[STAGE_SLOTS] = {nullptr, nullptr, nullptr};
   bool ok = false;
 };
-// one ring per calling thread (the chains-over-devices driver runs one sampler per thread); lives for the process
-StagingRing& staging_ring() {
-  static thread_local StagingRing r;
-  if (!r.ok) {
-    bool good = true;
-    for (int i = 0; i < STAGE_SLOTS && good; ++i) {
-      good = cudaHostAlloc((void**)&r.slot[i], STAGE_PIECE, cudaHostAllocDefault) == cudaSuccess &&
-             cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming) == cudaSuccess;
+// Rings are leased for the duration of one copy and returned to a process-wide free list (the chains-over-devices
+// driver runs one sampler per short-lived thread: a ring per thread would leak page-locked memory).  At most one ring
+// per concurrently copying thread ever exists; they live until the process ends.
+class RingLease {
+ public:
+  RingLease() {
+    cudaGetDevice(&dev_);                       // the ring's events belong to the device that was current at creation
+    {
+      std::lock_guard<std::mutex> g(mutex());
+      auto& fl = free_list(dev_);
+      if (!fl.empty()) { r_ = fl.back(); fl.pop_back(); }
     }
-    if (!good) cudaGetLastError();
-    r.ok = good;
+    if (!r_) {
+      r_ = new StagingRing();
+      bool good = true;
+      for (int i = 0; i < STAGE_SLOTS && good; ++i)
+        good = cudaHostAlloc((void**)&r_->slot[i], STAGE_PIECE, cudaHostAllocPortable) == cudaSuccess &&
+               cudaEventCreateWithFlags(&r_->ev[i], cudaEventDisableTiming) == cudaSuccess;
+      if (!good) cudaGetLastError();
+      r_->ok = good;
+    }
   }
-  return r;
-}
+  ~RingLease() {
+    std::lock_guard<std::mutex> g(mutex());
+    free_list(dev_).push_back(r_);
+  }
+  StagingRing& ring() { return *r_; }
+
+ private:
+  static std::mutex& mutex() { static std::mutex m; return m; }
+  static std::vector<StagingRing*>& free_list(int dev) {          // call with mutex() held
+    static std::vector<std::vector<StagingRing*>>* v = new std::vector<std::vector<StagingRing*>>();
+    if ((int)v->size() <= dev) v->resize(dev + 1);
+    return (*v)[std::max(dev, 0)];
+  }
+  StagingRing* r_ = nullptr;
+  int dev_ = 0;
+};
 size_t staging_min_bytes() {
   const char* e = getenv("CLV_STAGING_MIN_BYTES");      // smaller copies take the driver's own pageable path
   return e ? (size_t)atoll(e) : (size_t)(64u << 20);
@@ -359,7 +383,8 @@ bool is_page_locked(const void* p) {
 // device -> pageable host, ordered after everything already in `stream`; returns when the data is in `dst`
 cudaError_t copy_to_host_staged(void* dst, const void* src_dev, size_t bytes, cudaStream_t stream) {
   if (bytes < staging_min_bytes() || is_page_locked(dst)) return cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, stream);
-  StagingRing& r = staging_ring();
+  RingLease lease;
+  StagingRing& r = lease.ring();
   if (!r.ok) return cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, stream);
   HostCopyPool& pool = HostCopyPool::get();
   const size_t n = (bytes + STAGE_PIECE - 1) / STAGE_PIECE;
@@ -382,7 +407,8 @@ cudaError_t copy_to_host_staged(void* dst, const void* src_dev, size_t bytes, cu
 // pageable host -> device; returns when the last piece has been handed to the copy engine (stream ordered after that)
 cudaError_t copy_to_device_staged(void* dst_dev, const void* src, size_t bytes, cudaStream_t stream) {
   if (bytes < staging_min_bytes() || is_page_locked(src)) return cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, stream);
-  StagingRing& r = staging_ring();
+  RingLease lease;
+  StagingRing& r = lease.ring();
   if (!r.ok) return cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, stream);
   HostCopyPool& pool = HostCopyPool::get();
   const size_t n = (bytes + STAGE_PIECE - 1) / STAGE_PIECE;
@@ -1876,6 +1902,14 @@ int clv_debug_variates(int device, uint64_t seed, uint32_t sweep, int32_t step, 
   dfree(d);
   if (e != cudaSuccess) return fail(nullptr, CLV_ERR_CUDA, "clv_debug_variates failed: %s", cudaGetErrorString(e));
   return CLV_OK;
+}
+
+// ---- test hook: parallel host memcpy ----------------------------------------------------------------
+int clv_debug_host_copy(void* dst, const void* src, int64_t bytes) {
+  if (!dst || !src || bytes < 0) return fail(nullptr, CLV_ERR_ARG, "clv_debug_host_copy: bad argument");
+  HostCopyPool& pool = HostCopyPool::get();
+  pool.copy(dst, src, (size_t)bytes);
+  return pool.threads();
 }
 
 // ---- issue-rate peaks ---------------------------------------------------------------------------

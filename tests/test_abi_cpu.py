@@ -140,3 +140,28 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 1e4 and "workload" in d["config"]
+
+
+def test_parallel_host_copy_pool():
+    """The host side of the staged transfers (a pool of copy threads splitting one memcpy) needs no device: every
+    size and alignment must arrive intact, including concurrent callers (chains-over-GPUs runs one sampler per thread)."""
+    import threading
+    lib = L.load()
+    rng = np.random.default_rng(0)
+    src = rng.integers(0, 256, 64 * 1024 * 1024 + 77, dtype=np.uint8)
+    for nbytes, so, do in ((0, 0, 0), (1, 3, 5), (4095, 1, 2), (2 << 20, 0, 0), ((2 << 20) + 1, 7, 3), (48 << 20, 13, 1),
+                           (64 << 20, 0, 64)):
+        dst = np.zeros(nbytes + do + 16, dtype=np.uint8)
+        nthr = lib.clv_debug_host_copy(dst[do:].ctypes.data, src[so:].ctypes.data, nbytes)
+        assert nthr >= 1
+        np.testing.assert_array_equal(dst[do:do + nbytes], src[so:so + nbytes])
+        assert not dst[:do].any() and not dst[do + nbytes:].any()
+    outs = [np.zeros(24 << 20, dtype=np.uint8) for _ in range(4)]
+    def work(i):
+        for _ in range(3):
+            lib.clv_debug_host_copy(outs[i].ctypes.data, src[i * 1000:].ctypes.data, outs[i].size)
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(4):
+        np.testing.assert_array_equal(outs[i], src[i * 1000:i * 1000 + outs[i].size])
