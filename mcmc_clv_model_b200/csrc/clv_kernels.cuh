@@ -132,6 +132,27 @@ __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ t
   return __hiloint2double(hi, __double2loint(v));
 }
 
+// The same with the table given as a 32-bit shared-window address held in a register: the load is [reg] instead of
+// [reg + uniform base], and the base (S2UR CgaCtaId / UMOV / UIADD3 / ULEA, which ptxas rebuilds in every loop trip)
+// disappears from the Metropolis loop.
+__device__ __forceinline__ double exp_tab(double x, uint32_t tab_addr) {
+  const double t = fma(x, c_expk[0], 6755399441055744.0);
+  const int n = __double2loint(t);
+  const double nd = t - 6755399441055744.0;
+  double r = fma(nd, c_expk[1], x);
+  r = fma(nd, c_expk[2], r);
+  double p = fma(r, c_expk[3], c_expk[4]);
+  p = fma(p, r, c_expk[5]);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = p * r;
+  double T;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(tab_addr + ((uint32_t)(n & 63) << 3)));
+  double v = fma(T, p, T);
+  const int hi = __double2hiint(v) + ((n >> 6) << 20);
+  return __hiloint2double(hi, __double2loint(v));
+}
+
 // exp for any argument: the table path where it is valid (results stay normal numbers), libm beyond
 __device__ __noinline__ double exp_slow(double x) { return exp(x); }
 __device__ __forceinline__ double exp_any(double x, const double* __restrict__ tab) {
@@ -141,8 +162,9 @@ __device__ __forceinline__ double exp_any(double x, const double* __restrict__ t
 // Level-1 target, bi:291-310, without the lm > 5 cut (the caller applies it).  Tz = z*T_cal + (1-z)*tau, omz = 1-z,
 // ll, lm in [-70, 70].  The quadratic form takes the precision pre-scaled per chain, h00 = -P00/2, h01 = -P01,
 // h11 = -P11/2, and is folded into the likelihood by Horner steps: 7 fp64 instructions instead of 10.
+template <typename Tab>
 __device__ __forceinline__ double log_post_open(double ll, double lm, double xd, double omz, double Tz, double m0,
-                                                double m1, double h00, double h01, double h11, const double* tab) {
+                                                double m1, double h00, double h01, double h11, Tab tab) {
   const double dl = ll - m0, dm = lm - m1;
   const double lik = xd * ll + omz * lm - (exp_tab(ll, tab) + exp_tab(lm, tab)) * Tz;
   return fma(dl, fma(h00, dl, h01 * dm), fma(dm, h11 * dm, lik));
@@ -308,6 +330,8 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
     const double Tz = alive ? T : tau;          // z*T_cal + (1-z)*tau, bi:298
     // ---- S Metropolis steps (bi:312-335) -------------------------------------------------------
     double cur = log_post(ll, lm, xd, omz, Tz, m0, m1, h00, h01, h11, s_tab);
+    uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(s_tab);
+    asm volatile("" : "+r"(tab_addr));                 // opaque: keeps ptxas from rebuilding it inside the loop
     // one step from its six words (ignored when the variates are injected)
     auto mh_step = [&](int s, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5) {
       double tl, tm, ua = 0.0;
@@ -335,7 +359,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
       // a proposal with log mu > 5 has target -inf and is never accepted (exp(-inf - cur) = 0, or NaN when cur is
       // -inf too); cur itself can be -inf only at the start, and then every admissible proposal is accepted (d = +inf)
       const bool admissible = !(pm > 5.0);
-      const double prop = log_post_open(pl, pm, xd, omz, Tz, m0, m1, h00, h01, h11, s_tab);
+      const double prop = log_post_open(pl, pm, xd, omz, Tz, m0, m1, h00, h01, h11, tab_addr);
       if (mh_accept<MODE == MODE_INJECT>(prop - cur, uaf, [&]() { return MODE == MODE_INJECT ? ua : u32d(ur); }) &&
           admissible) {
         ll = pl;
