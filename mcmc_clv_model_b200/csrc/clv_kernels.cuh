@@ -332,8 +332,8 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
     double cur = log_post(ll, lm, xd, omz, Tz, m0, m1, h00, h01, h11, s_tab);
     uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(s_tab);
     asm volatile("" : "+r"(tab_addr));                 // opaque: keeps ptxas from rebuilding it inside the loop
-    // one step from its six words (ignored when the variates are injected)
-    auto mh_step = [&](int s, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5) {
+    // one step from the four words of its Philox block (ignored when the variates are injected)
+    auto mh_step = [&](int s, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
       double tl, tm, ua = 0.0;
       float uaf;
       uint32_t ur = 0u;
@@ -345,11 +345,11 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
         uaf = (float)ua;
       } else {
         if (MODE == MODE_STRICT) {
-          tl = t3_strict(w0, w1, w2);
-          tm = t3_strict(w3, w4, w5);
+          tl = t3_strict(w0, w1);
+          tm = t3_strict(w2, w3);
         } else {
-          tl = (double)t3_fast(w0, w1, w2);
-          tm = (double)t3_fast(w3, w4, w5);
+          tl = (double)t3_fast(w0, w1);
+          tm = (double)t3_fast(w2, w3);
         }
         ur = low_bytes(w0, w1, w2, w3);
         uaf = u32f(ur);
@@ -367,25 +367,10 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
         cur = prop;
       }
     };
-    if (MODE == MODE_INJECT) {
-      for (int s = 0; s < S; ++s) mh_step(s, 0u, 0u, 0u, 0u, 0u, 0u);
-    } else {
-      // two steps per trip share three Philox blocks (word layout: clv_rng.cuh)
-      int s = 0;
-      uint32_t slot = 1u;
-#pragma unroll 1
-      for (; s + 1 < S; s += 2, slot += 3u) {
-        const uint4 A = philox4x32_10_rk(gid, sw.sweep, slot, c3, a.rk);
-        const uint4 B = philox4x32_10_rk(gid, sw.sweep, slot + 1u, c3, a.rk);
-        mh_step(s, A.x, A.y, A.z, A.w, B.x, B.y);
-        const uint4 C = philox4x32_10_rk(gid, sw.sweep, slot + 2u, c3, a.rk);
-        mh_step(s + 1, B.z, B.w, C.x, C.y, C.z, C.w);
-      }
-      if (s < S) {
-        const uint4 A = philox4x32_10_rk(gid, sw.sweep, slot, c3, a.rk);
-        const uint4 B = philox4x32_10_rk(gid, sw.sweep, slot + 1u, c3, a.rk);
-        mh_step(s, A.x, A.y, A.z, A.w, B.x, B.y);
-      }
+    for (int s = 0; s < S; ++s) {
+      uint4 A = make_uint4(0u, 0u, 0u, 0u);
+      if (MODE != MODE_INJECT) A = philox4x32_10_rk(gid, sw.sweep, 1u + (uint32_t)s, c3, a.rk);   // word layout: clv_rng.cuh
+      mh_step(s, A.x, A.y, A.z, A.w);
     }
     a.ll[cN + i] = ll;
     a.lm[cN + i] = lm;
@@ -502,21 +487,15 @@ template <int MODE>
 __global__ void k_debug_variates(PhiloxRoundKeys rk, uint32_t sweep, int step, long long n, double* t3l, double* t3m,
                                  double* uacc) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const uint32_t gid = (uint32_t)i, c3 = dom_word(DOM_SAMPLER, 0u), slot = 1u + 3u * (uint32_t)(step >> 1);
-    uint32_t w[6];
-    if (step & 1) {
-      const uint4 B = philox4x32_10_rk(gid, sweep, slot + 1u, c3, rk), C = philox4x32_10_rk(gid, sweep, slot + 2u, c3, rk);
-      w[0] = B.z; w[1] = B.w; w[2] = C.x; w[3] = C.y; w[4] = C.z; w[5] = C.w;
-    } else {
-      const uint4 A = philox4x32_10_rk(gid, sweep, slot, c3, rk), B = philox4x32_10_rk(gid, sweep, slot + 1u, c3, rk);
-      w[0] = A.x; w[1] = A.y; w[2] = A.z; w[3] = A.w; w[4] = B.x; w[5] = B.y;
-    }
+    const uint32_t gid = (uint32_t)i, c3 = dom_word(DOM_SAMPLER, 0u);
+    const uint4 A = philox4x32_10_rk(gid, sweep, 1u + (uint32_t)step, c3, rk);
+    const uint32_t w[4] = {A.x, A.y, A.z, A.w};
     if (MODE == MODE_STRICT) {
-      t3l[i] = t3_strict(w[0], w[1], w[2]);
-      t3m[i] = t3_strict(w[3], w[4], w[5]);
+      t3l[i] = t3_strict(w[0], w[1]);
+      t3m[i] = t3_strict(w[2], w[3]);
     } else {
-      t3l[i] = 1.7320508075688772 * (double)t3_fast(w[0], w[1], w[2]);
-      t3m[i] = 1.7320508075688772 * (double)t3_fast(w[3], w[4], w[5]);
+      t3l[i] = 1.7320508075688772 * (double)t3_fast(w[0], w[1]);
+      t3m[i] = 1.7320508075688772 * (double)t3_fast(w[2], w[3]);
     }
     uacc[i] = u32d(low_bytes(w[0], w[1], w[2], w[3]));
   }

@@ -87,12 +87,9 @@ __device__ __forceinline__ float u24f(uint32_t a) { return fmaf(__uint2float_rz(
 __device__ __forceinline__ double u24d(uint32_t a) { return ((double)(a >> 8) + 0.5) * 0x1.0p-24; }
 
 // ---- word layout of the Metropolis steps (sampler domain) ----------------------------------------------------------
-// A step consumes six words: (u1, angle, u3) for the log-lambda proposal and the same for log mu; each transform uses
-// the TOP 24 bits of its word.  The accept uniform is assembled from the LOW bytes of the first four of those words
-// (bits the transforms never see), so a step costs 1.5 Philox blocks instead of 2: steps 2p and 2p+1 share the three
-// blocks of slots 1+3p, 2+3p, 3+3p:
-//   step 2p   : A.x A.y A.z | A.w B.x B.y        step 2p+1 : B.z B.w C.x | C.y C.z C.w
-// Slot 0 is z/tau, slot 1+2S the eta normal (tri).
+// A step consumes ONE Philox block (slot 1 + step): words (x, y) = (V, angle) for the log-lambda proposal, (z, w) for
+// log mu; each transform uses the TOP 24 bits of its word.  The accept uniform is assembled from the LOW bytes of the
+// four words (bits the transforms never see).  Slot 0 is z/tau, slot 1+2S the eta normal (tri).
 __device__ __forceinline__ uint32_t low_bytes(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
   // three PRMT: byte 0 of w0..w3 -> bytes 0..3
   return __byte_perm(__byte_perm(w0, w1, 0x0040), __byte_perm(w2, w3, 0x0040), 0x5410);
@@ -105,33 +102,30 @@ __device__ __forceinline__ float sqrt_ftz(float x) { float y; asm("sqrt.approx.f
 __device__ __forceinline__ float sin_ftz(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float cos_ftz(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// ---- Student t(3) without rejection: N0 / sqrt((N1^2 - 2 ln U3)/3) ---------------------------------
-__device__ __forceinline__ double t3_strict(uint32_t ra, uint32_t rb, uint32_t rc) {
-  double u1 = u24d(ra), u2 = u24d(rb), u3 = u24d(rc);
-  double r = sqrt(-2.0 * log(u1));
-  double ang = 6.283185307179586476925286766559 * u2;
+// ---- Student t(3) without rejection, from TWO uniforms ---------------------------------------------------------------
+// t = N0 / sqrt((N1^2 + C)/3) with (N0, N1) = R (cos th, sin th) a Box-Muller pair, R^2 = 2 E1, and C = 2 E3 an
+// independent chi-square(2):  t / sqrt(3) = cos(th) / sqrt(sin^2(th) + E3 / E1).  The ratio of two independent
+// Exp(1) variables has CDF r / (1 + r), i.e. E3 / E1 = V / (1 - V) with V uniform -- no logarithm is needed, and a
+// variate costs one angle and one V:   t / sqrt(3) = cos(th) / sqrt(sin^2(th) + V / (1 - V)).
+__device__ __forceinline__ double t3_strict(uint32_t rv, uint32_t rb) {
+  const double v = u24d(rv), ang = 6.283185307179586476925286766559 * u24d(rb);
   double s, c;
   sincos(ang, &s, &c);
-  double n0 = r * c, n1 = r * s;
-  double chi2 = n1 * n1 + (-2.0 * log(u3));
-  return n0 / sqrt(chi2 / 3.0);
+  return 1.7320508075688772 * c / sqrt(s * s + v / (1.0 - v));
 }
 
-// FAST variant, returns t / sqrt(3) (the caller folds sqrt(3) into the proposal scale).  With a = lg2 u1, b = lg2 u3
-// (both <= 0) the -2 ln 2 factors of the Box-Muller radius and of the chi-square cancel:
-//   t / sqrt(3) = cos(th) / sqrt(sin^2(th) + b / a) = cos(th) |a| rsqrt((sin^2(th) a + b) a),  sin^2 = 1 - cos^2
-// which needs four SFU operations (2 lg2, cos, rsqrt) instead of six (+ sin, rcp); the SFU pipe is the second busiest
-// of the sweep kernel.  The map is odd in cos(th), so the proposal stays exactly symmetric whatever the rounding.
-__device__ __forceinline__ float t3_fast(uint32_t ra, uint32_t rb, uint32_t rc) {
-  // u1 can round to 1.0f (lg2 = +0): keep a strictly negative (>= one grid step) so that the rsqrt argument stays
-  // a normal positive number
-  const float l1 = fminf(lg2_ftz(u24f(ra)), -0x1.0p-24f), l3 = lg2_ftz(u24f(rc));
+// FAST variant (fp32, two SFU operations: cos, rsqrt), returns t / sqrt(3) (the caller folds sqrt(3) into the proposal
+// scale).  With w = 1 - V:  cos(th) / sqrt(sin^2 + V / w) = cos(th) w rsqrt((sin^2 w + V) w),  sin^2 = 1 - cos^2.
+// V is rounded toward zero so that it stays below 1 (w >= 2^-24, computed exactly); the map is odd in cos(th), so the
+// proposal stays exactly symmetric whatever the rounding.
+__device__ __forceinline__ float fma_rz(float a, float b, float c) { float y; asm("fma.rz.ftz.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c)); return y; }
+__device__ __forceinline__ float t3_fast(uint32_t rv, uint32_t rb) {
+  const float v = fma_rz(__uint2float_rz(rv), 0x1.0p-32f, 0x1.0p-25f), w = 1.0f - v;
   // angle 2 pi (k + 0.5) 2^-24 straight from the integer
   const float ang = fmaf(__uint2float_rz(rb), 6.2831853071795865f * 0x1.0p-32f, 6.2831853071795865f * 0x1.0p-25f);
   const float c = cos_ftz(ang);
   const float s2 = fmaf(-c, c, 1.0f);
-  const float w = fmaf(s2, l1, l3);
-  return (c * fabsf(l1)) * rsqrt_ftz(w * l1);
+  return (c * w) * rsqrt_ftz(fmaf(s2, w, v) * w);
 }
 
 // two standard normals from four words (53-bit uniforms, fp64): cos / sin branch

@@ -84,28 +84,19 @@ def low_bytes(w0, w1, w2, w3):
 
 
 def step_words(seed, chain, gids, sweep, step):
-    """The six words Metropolis step `step` consumes (clv_rng.cuh, "word layout of the Metropolis steps"): steps 2p and
-    2p+1 share the blocks of slots 1+3p, 2+3p, 3+3p:  A.x A.y A.z | A.w B.x B.y   and   B.z B.w C.x | C.y C.z C.w."""
+    """The four words Metropolis step `step` consumes (clv_rng.cuh, "word layout of the Metropolis steps"): the Philox
+    block of slot 1 + step; (x, y) = (V, angle) for the log-lambda proposal, (z, w) for log mu."""
     k0, k1 = chain_key(seed, chain)
     c3 = dom_word(DOM_SAMPLER, chain)
-    slot = 1 + 3 * (step >> 1)
-    b = philox4x32_10(gids, sweep, slot + 1, c3, k0, k1)
-    if step & 1:
-        c = philox4x32_10(gids, sweep, slot + 2, c3, k0, k1)
-        return b[2], b[3], c[0], c[1], c[2], c[3]
-    a = philox4x32_10(gids, sweep, slot, c3, k0, k1)
-    return a[0], a[1], a[2], a[3], b[0], b[1]
+    return philox4x32_10(gids, sweep, 1 + step, c3, k0, k1)
 
 
-def t3_from_words(ra, rb, rc):
-    """Student-t(3) without rejection: N0 / sqrt((N1^2 - 2 ln U3)/3)."""
-    u1, u2, u3 = u24(ra), u24(rb), u24(rc)
-    r = np.sqrt(-2.0 * np.log(u1))
-    ang = TWO_PI * u2
-    n0 = r * np.cos(ang)
-    n1 = r * np.sin(ang)
-    chi2 = n1 * n1 + (-2.0 * np.log(u3))
-    return n0 / np.sqrt(chi2 / 3.0)
+def t3_from_words(rv, rb):
+    """Student-t(3) without rejection from two uniforms: with a Box-Muller pair R (cos th, sin th) and an independent
+    chi-square(2) = 2 E3,  t / sqrt(3) = cos th / sqrt(sin^2 th + E3 / E1), and the ratio of two independent Exp(1)
+    variables is V / (1 - V) with V uniform."""
+    v, ang = u24(rv), TWO_PI * u24(rb)
+    return np.sqrt(3.0) * np.cos(ang) / np.sqrt(np.sin(ang) ** 2 + v / (1.0 - v))
 
 
 def normal_pair_u53(r0, r1, r2, r3):
@@ -137,8 +128,8 @@ def sampler_variates(seed, chain, gids, sweep, n_mh_steps, with_eta=False):
     u_acc = np.empty((S, gids.size))
     for s in range(S):
         w = step_words(seed, chain, gids, sweep, s)
-        t3_l[s] = t3_from_words(w[0], w[1], w[2])
-        t3_m[s] = t3_from_words(w[3], w[4], w[5])
+        t3_l[s] = t3_from_words(w[0], w[1])
+        t3_m[s] = t3_from_words(w[2], w[3])
         u_acc[s] = u32(low_bytes(w[0], w[1], w[2], w[3]))
     out.update(t3_l=t3_l, t3_m=t3_m, u_acc=u_acc)
     if with_eta:

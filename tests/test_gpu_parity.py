@@ -81,8 +81,8 @@ def test_strict_philox_trajectory_vs_oracle(cdnow_abe, D, cov):
 
 @pytest.mark.parametrize("S", [1, 2, 5, 7])
 def test_strict_philox_odd_step_counts_vs_oracle(cdnow_abe, S):
-    """n_mh_steps other than the default: two Metropolis steps share three Philox blocks, so odd counts end on a
-    half-used pair (and S=1 never enters the paired loop).  Both sweep paths against the oracle replay."""
+    """n_mh_steps other than the default (the eta slot 1 + 2S moves with it).  Both sweep paths against the oracle
+    replay."""
     d = cdnow_abe
     n = 300
     X = np.column_stack([np.ones(n), d["first_sales_scaled"][:n]])
@@ -434,7 +434,7 @@ def test_level1_variates_fast_vs_strict_vs_oracle():
     lib = L.load()
     n, seed, sweep, S = 1_000_000, 777, 5, 5
     v = px.sampler_variates(seed, 0, np.arange(n), sweep, S)
-    for step in (0, 1, 4):           # even / odd step of a pair, and a later pair
+    for step in (0, 1, 4):
         out = {}
         for mode in (L.RNG_STRICT, L.RNG_FAST):
             a, b, u = np.empty(n), np.empty(n), np.empty(n)
