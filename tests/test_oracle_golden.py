@@ -90,3 +90,34 @@ def test_poisson_inversion_matches_distribution():
         x = ao.poisson_inversion(np.full(200000, m), rng.random(200000))
         assert abs(x.mean() - m) < 5 * np.sqrt(max(m, 1e-9) / 200000) + 1e-12
         assert abs(x.var() - m) < 0.05 * max(m, 1e-9) + 1e-12
+
+
+def test_philox_contract_variates_follow_the_reference_laws():
+    """The device RNG contract restated in oracle/philox_np.py draws the Metropolis proposals from ONE Philox block per
+    step: Student-t(3) from two uniforms (t / sqrt(3) = cos th / sqrt(sin^2 th + V / (1 - V)), the ratio of the two
+    exponentials of the textbook construction being V / (1 - V)), accept uniform from the low bytes of the same words.
+    Check the laws the reference draws from (`rng.standard_t(3)`, `rng.random()`, bi:316-330) and the independence the
+    word sharing must not break."""
+    from scipy import stats
+    from oracle import philox_np as px
+    n, S = 400_000, 4
+    v = px.sampler_variates(20240229, 3, np.arange(n), 17, S, with_eta=True)
+    ref_t = np.random.default_rng(0).standard_t(3, n)
+    for s in range(S):
+        for k in ("t3_l", "t3_m"):
+            assert stats.kstest(v[k][s], stats.t(3).cdf).pvalue > 1e-3, (k, s)
+            assert stats.ks_2samp(v[k][s], ref_t).pvalue > 1e-3, (k, s)
+            # heavy tails are there (a 24-bit V reaches |t| in the thousands)
+            assert abs(np.mean(np.abs(v[k][s]) > 10) / (2 * stats.t.sf(10, 3)) - 1) < 0.15
+        assert stats.kstest(v["u_acc"][s], "uniform").pvalue > 1e-3
+        # proposals for log lambda and log mu, and the accept uniform, are mutually independent
+        assert abs(np.corrcoef(v["t3_l"][s], v["t3_m"][s])[0, 1]) < 0.01
+        assert abs(np.corrcoef(np.abs(v["t3_l"][s]) < 1, np.abs(v["t3_m"][s]) < 1)[0, 1]) < 0.01
+        for k in ("t3_l", "t3_m"):
+            assert abs(np.corrcoef(v["u_acc"][s], np.abs(v[k][s]) < 1)[0, 1]) < 0.01
+            assert abs(np.corrcoef(v["u_acc"][s], v[k][s] > 0)[0, 1]) < 0.01
+    # consecutive steps and sweeps use different counters
+    assert abs(np.corrcoef(v["t3_l"][0], v["t3_l"][1])[0, 1]) < 0.01
+    w = px.sampler_variates(20240229, 3, np.arange(n), 18, S)
+    assert abs(np.corrcoef(v["t3_l"][0], w["t3_l"][0])[0, 1]) < 0.01
+    assert stats.kstest(v["n_eta"], "norm").pvalue > 1e-3 and stats.kstest(v["u_z"], "uniform").pvalue > 1e-3
