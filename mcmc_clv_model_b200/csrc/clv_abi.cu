@@ -613,8 +613,8 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   CKC(cudaMemset(h->d_acc, 0, sizeof(unsigned long long) * C * NSTAT_MAX));
   CKC(cudaMemset(h->d_params, 0, sizeof(ChainParams) * C));
   {
-    double et[64];
-    for (int j = 0; j < 64; ++j) et[j] = (double)exp2l((long double)j / 64.0L);
+    double et[EXP_N];
+    for (int j = 0; j < EXP_N; ++j) et[j] = (double)exp2l((long double)j / (long double)EXP_N);
     CKC(cudaMemcpyToSymbol(c_exptab, et, sizeof et));
   }
   if (upload_rk()) { h->err = g_last_error; return bail(CLV_ERR_CUDA); }

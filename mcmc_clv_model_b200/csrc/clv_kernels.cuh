@@ -88,9 +88,19 @@ struct SweepArgs {
   const double *u_z, *e_tau, *u_tau, *t3_l, *t3_m, *u_acc, *n_eta;
 };
 
-__constant__ double c_exptab[64];   // 2^(j/64), uploaded by clv_create
-// exp_tab constants: 64/ln2, -ln2/64 (high, low), 1/120, 1/24, 1/6
-__constant__ double c_expk[6] = {92.332482616893656877, -0x1.62e42fefa0000p-7, -0x1.cf79abc9e3b3ap-46,
+// Table exp: 2^(j / EXP_N), j < EXP_N, in shared memory + a polynomial for the remainder.  CLV_EXP_BITS = 6 (default):
+// 64 entries, degree-5 remainder; CLV_EXP_BITS = 8: 256 entries (2 KB per block), degree 4 -- one DFMA less per exp at
+// the same <= 1 ulp (|r| <= ln2/512: r^5/120 < 4e-17).  The 8-bit build is a candidate that has not been timed yet.
+#ifndef CLV_EXP_BITS
+#define CLV_EXP_BITS 6
+#endif
+constexpr int EXP_BITS = CLV_EXP_BITS, EXP_N = 1 << EXP_BITS;
+static_assert(EXP_BITS == 6 || EXP_BITS == 8, "CLV_EXP_BITS must be 6 or 8");
+__constant__ double c_exptab[EXP_N];   // 2^(j/EXP_N), uploaded by clv_create
+// exp_tab constants: EXP_N/ln2, -ln2/EXP_N (high part with 16 zero low bits, low part), 1/120, 1/24, 1/6
+__constant__ double c_expk[6] = {EXP_BITS == 6 ? 92.332482616893656877 : 369.32993046757462751,
+                                 EXP_BITS == 6 ? -0x1.62e42fefa0000p-7 : -0x1.62e42fefa0000p-9,
+                                 EXP_BITS == 6 ? -0x1.cf79abc9e3b3ap-46 : -0x1.cf79abc9e3b3ap-48,
                                  8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01};
 
 __device__ __forceinline__ long long to_fx(double v, double scale) { return __double2ll_rn(v * scale); }
@@ -111,8 +121,8 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 }
 
 // exp(x) for |x| <= 700 (in particular the clip range +-70 of bi:323-324), ~1 ulp, branch-free:
-//   n = rint(x 64/ln2), r = x - n ln2/64 (|r| <= 0.0055), exp(x) = 2^(n>>6) * 2^((n&63)/64) * (1 + r + ... + r^5/120)
-// 2^(j/64) comes from a 64-entry shared-memory table; the degree-5 remainder is < 4e-17.
+//   n = rint(x E/ln2), r = x - n ln2/E (|r| <= ln2/2E), exp(x) = 2^(n>>B) * 2^((n&(E-1))/E) * (1 + r + ... ),  E = 2^B
+// 2^(j/E) comes from the shared-memory table; E = 64 with a degree-5 remainder (< 4e-17), or E = 256 with degree 4.
 __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
   // the fp64 constants sit in the constant bank so that DFMA reads them as c[][] operands; written as literals ptxas
   // rebuilds each one with two UMOVs on every call (26 extra issue slots per MH step)
@@ -121,14 +131,13 @@ __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ t
   const double nd = t - 6755399441055744.0;
   double r = fma(nd, c_expk[1], x);                                       // -ln2/64, high part (low 16 bits zero: n*hi exact)
   r = fma(nd, c_expk[2], r);                                              // low part
-  double p = fma(r, c_expk[3], c_expk[4]);
-  p = fma(p, r, c_expk[5]);
+  double p = (EXP_BITS == 6) ? fma(fma(r, c_expk[3], c_expk[4]), r, c_expk[5]) : fma(r, c_expk[4], c_expk[5]);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = p * r;
-  const double T = tab[n & 63];
+  const double T = tab[n & (EXP_N - 1)];
   double v = fma(T, p, T);
-  const int hi = __double2hiint(v) + ((n >> 6) << 20);
+  const int hi = __double2hiint(v) + ((n >> EXP_BITS) << 20);
   return __hiloint2double(hi, __double2loint(v));
 }
 
@@ -141,15 +150,14 @@ __device__ __forceinline__ double exp_tab(double x, uint32_t tab_addr) {
   const double nd = t - 6755399441055744.0;
   double r = fma(nd, c_expk[1], x);
   r = fma(nd, c_expk[2], r);
-  double p = fma(r, c_expk[3], c_expk[4]);
-  p = fma(p, r, c_expk[5]);
+  double p = (EXP_BITS == 6) ? fma(fma(r, c_expk[3], c_expk[4]), r, c_expk[5]) : fma(r, c_expk[4], c_expk[5]);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = p * r;
   double T;
-  asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(tab_addr + ((uint32_t)(n & 63) << 3)));
+  asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(tab_addr + ((uint32_t)(n & (EXP_N - 1)) << 3)));
   double v = fma(T, p, T);
-  const int hi = __double2hiint(v) + ((n >> 6) << 20);
+  const int hi = __double2hiint(v) + ((n >> EXP_BITS) << 20);
   return __hiloint2double(hi, __double2loint(v));
 }
 
@@ -421,7 +429,7 @@ template <int D, int MODE>
 __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArgs a) {
   extern __shared__ long long s_priv[];          // [(nstat + 1)][SWEEP_THREADS]
   __shared__ double s_beta[MAXK * MAXD];
-  __shared__ double s_tab[64];
+  __shared__ double s_tab[EXP_N];
   __shared__ unsigned long long s_acc[NSTAT_MAX + 1];
   const ModelConst& mc = *a.mc;
   const int chain = blockIdx.y;
@@ -430,7 +438,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArg
   const int nstat = K * D + D * (D + 1) / 2;
   const ChainParams& cp = a.params[chain];
   for (int t = tid; t < K * D; t += SWEEP_THREADS) s_beta[t] = cp.beta[t];
-  if (tid < 64) s_tab[tid] = c_exptab[tid];
+  for (int t = tid; t < EXP_N; t += SWEEP_THREADS) s_tab[t] = c_exptab[t];
   for (int t = tid; t < NSTAT_MAX + 1; t += SWEEP_THREADS) s_acc[t] = 0ull;
   clear_stats(s_priv, nstat);
   __syncthreads();
@@ -906,7 +914,7 @@ template <int D, int MODE>
 __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(PersistArgs pa) {
   extern __shared__ long long s_priv[];
   __shared__ double s_beta[MAXK * MAXD];
-  __shared__ double s_tab[64];
+  __shared__ double s_tab[EXP_N];
   __shared__ unsigned long long s_acc[NSTAT_MAX + 1];
   __shared__ ChainParams s_cp;
   __shared__ Level2Scratch sc;
@@ -921,7 +929,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(Per
   const uint32_t c3 = dom_word(DOM_SAMPLER, a.chain_offset + (uint32_t)chain);
   const uint32_t c3_l2 = dom_word(DOM_LEVEL2, a.chain_offset + (uint32_t)chain);
   const long long csz = (long long)gridDim.y * NSTAT_MAX;
-  if (tid < 64) s_tab[tid] = c_exptab[tid];
+  for (int t = tid; t < EXP_N; t += SWEEP_THREADS) s_tab[t] = c_exptab[t];
   clear_stats(s_priv, nstat);
   {
     const double* src = reinterpret_cast<const double*>(&pa.params[chain]);
