@@ -62,7 +62,7 @@ std::vector<CachedComm> g_comms;
 // peer mailboxes of the fused all-reduce are likewise created and connected once per (device, rank, world, chains)
 struct CachedMailbox {
   int device, rank, world, chains;
-  void* base; size_t bytes, flags_off;
+  void* base; size_t bytes;
   bool connected;
   void* peer_base[P2P_MAX_WORLD];
 };
@@ -113,11 +113,10 @@ struct clv_sampler {
   // comm
   nccl_comm_t comm = nullptr; int world = 1, rank = 0;
   // peer mailboxes (P2P all-reduce fused into k_level2)
-  void* d_mailbox = nullptr; size_t mailbox_bytes = 0, mailbox_flags_off = 0;
+  void* d_mailbox = nullptr; size_t mailbox_bytes = 0;
   bool p2p = false;
-  long long* peer_data[P2P_MAX_WORLD] = {nullptr};
-  unsigned long long* peer_flags[P2P_MAX_WORLD] = {nullptr};
-  void* peer_base[P2P_MAX_WORLD] = {nullptr};
+  unsigned long long* peer_mail[P2P_MAX_WORLD] = {nullptr};
+  bool use_pdl = true;                   // programmatic dependent launch of the two kernels of a sweep (CLV_NO_PDL=1 disables)
   unsigned long long init_epoch = 0;     // bumped by every clv_init_state: mailbox flags never repeat
   // statistics computed by clv_init_state(h, NULL)
   clv_init_stats last_stats{};
@@ -440,6 +439,7 @@ SweepArgs base_args(clv_sampler* h) {
   a.sweep = 0; a.chain_offset = (uint32_t)h->cfg.chain_offset; a.seed = h->cfg.seed;
   a.rk = round_keys(h->cfg.seed);
   a.store_zt = 0;
+  a.error_flag = h->p2p ? h->d_err : nullptr;     // only sharded runs can be told to stop by a peer
   return a;
 }
 
@@ -452,13 +452,26 @@ cudaEvent_t pool_event(clv_sampler* h) {
   return h->ev_pool[h->ev_used++];
 }
 
+// Launch with (or without) the programmatic-stream-serialization attribute: the kernel may then become resident while
+// its predecessor in the stream still runs and execute everything it has before griddepcontrol.wait.
+template <typename Arg>
+cudaError_t launch_kernel(void (*kern)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, const Arg& arg) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, arg);
+}
+
 template <int D>
-void launch_sweep_kernel(clv_sampler* h, const SweepArgs& a, int mode) {
+cudaError_t launch_sweep_kernel(clv_sampler* h, const SweepArgs& a, int mode, bool pdl) {
   dim3 grid(h->grid_x, h->chains), block(SWEEP_THREADS);
   const size_t sm = h->stats_smem;
-  if (mode == MODE_FAST) k_sweep<D, MODE_FAST><<<grid, block, sm, h->stream>>>(a);
-  else if (mode == MODE_STRICT) k_sweep<D, MODE_STRICT><<<grid, block, sm, h->stream>>>(a);
-  else k_sweep<D, MODE_INJECT><<<grid, block, sm, h->stream>>>(a);
+  if (mode == MODE_FAST) return launch_kernel(k_sweep<D, MODE_FAST>, grid, block, sm, h->stream, pdl, a);
+  if (mode == MODE_STRICT) return launch_kernel(k_sweep<D, MODE_STRICT>, grid, block, sm, h->stream, pdl, a);
+  return launch_kernel(k_sweep<D, MODE_INJECT>, grid, block, sm, h->stream, pdl, a);
 }
 
 int allreduce_acc(clv_sampler* h) {
@@ -470,20 +483,25 @@ int allreduce_acc(clv_sampler* h) {
 
 // One Gibbs sweep in the reference's block order (bi:387-399 / tri:512-536).
 int enqueue_sweep(clv_sampler* h, SweepArgs a, Level2Args l2, int mode) {
-  l2.flag_value = (h->init_epoch << 32) | (unsigned long long)l2.sweep;
+  // tag of this sweep's mailbox words: never 0, differs from the tag of sweep - 2 (same parity slot) and of earlier inits
+  l2.tag = (uint32_t)(((h->init_epoch % 255ull) + 1ull) << 24) | (l2.sweep & 0xffffffu);
+  // injected variates are uploaded between the kernels, and per-kernel timing records events there: plain launches
+  const bool pdl = h->use_pdl && mode != MODE_INJECT && !h->timing;
+  cudaError_t le = cudaSuccess;
   auto do_l2 = [&]() {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) { e0 = pool_event(h); e1 = pool_event(h); cudaEventRecord(e0, h->stream); }
-    if (h->D == 2) k_level2<2><<<h->chains, 32, 0, h->stream>>>(l2);
-    else k_level2<3><<<h->chains, 32, 0, h->stream>>>(l2);
+    cudaError_t e = (h->D == 2) ? launch_kernel(k_level2<2>, dim3(h->chains), dim3(32), 0, h->stream, pdl, l2)
+                                : launch_kernel(k_level2<3>, dim3(h->chains), dim3(32), 0, h->stream, pdl, l2);
+    if (le == cudaSuccess) le = e;
     if (h->timing) { cudaEventRecord(e1, h->stream); h->ev_l2.push_back({e0, e1}); }
     h->launches++;
   };
   auto do_sweep = [&]() {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) { e0 = pool_event(h); e1 = pool_event(h); cudaEventRecord(e0, h->stream); }
-    if (h->D == 2) launch_sweep_kernel<2>(h, a, mode);
-    else launch_sweep_kernel<3>(h, a, mode);
+    cudaError_t e = (h->D == 2) ? launch_sweep_kernel<2>(h, a, mode, pdl) : launch_sweep_kernel<3>(h, a, mode, pdl);
+    if (le == cudaSuccess) le = e;
     if (h->timing) { cudaEventRecord(e1, h->stream); h->ev_sweep.push_back({e0, e1}); }
     h->launches++;
   };
@@ -496,10 +514,21 @@ int enqueue_sweep(clv_sampler* h, SweepArgs a, Level2Args l2, int mode) {
     if (int r = allreduce_acc(h)) return r;
     do_l2();
   }
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(h, CLV_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  if (le == cudaSuccess) le = cudaGetLastError();
+  if (le != cudaSuccess) return fail(h, CLV_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(le));
   h->sweeps_done++;
   return 0;
+}
+
+// How long a rank waits for its peers' mailbox words before it gives up (CLV_ERR_COMM).  Ranks are separate processes:
+// start-up skew, a rank blocked in a pageable flush or a progress callback are all legitimate, so the default is long.
+long long p2p_timeout_ns() {
+  static const long long v = [] {
+    const char* e = getenv("CLV_P2P_TIMEOUT_S");
+    const double sec = e ? atof(e) : 120.0;
+    return (long long)(std::max(0.001, sec) * 1e9);
+  }();
+  return v;
 }
 
 Level2Args base_l2(clv_sampler* h) {
@@ -510,7 +539,9 @@ Level2Args base_l2(clv_sampler* h) {
   l.injected = 0; l.iw_norm = l.iw_chi2 = l.beta_norm = nullptr;
   l.error_flag = h->d_err;
   l.world = h->p2p ? h->world : 0; l.rank = h->rank; l.n_chains = h->chains;
-  for (int r = 0; r < P2P_MAX_WORLD; ++r) { l.peer_data[r] = h->peer_data[r]; l.peer_flags[r] = h->peer_flags[r]; }
+  l.tag = 1u;
+  l.timeout_ns = p2p_timeout_ns();
+  for (int r = 0; r < P2P_MAX_WORLD; ++r) l.peer_mail[r] = h->peer_mail[r];
   return l;
 }
 
@@ -526,7 +557,7 @@ int check_device_error(clv_sampler* h) {
   CK(h, cudaMemcpyAsync(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
   if (h->timing) collect_timing(h);
-  if (flag == 2) return fail(h, CLV_ERR_COMM, "peer mailbox all-reduce timed out (a rank stopped?) at sweep <= %lld", h->sweeps_done);
+  if (flag == 2) return fail(h, CLV_ERR_COMM, "peer mailbox all-reduce timed out after CLV_P2P_TIMEOUT_S (a rank stopped?) at sweep <= %lld; the remaining sweeps were skipped", h->sweeps_done);
   if (flag) return fail(h, CLV_ERR_NUMERIC, "level-2 scale matrix not positive definite or non-finite (sweep <= %lld)", h->sweeps_done);
   return 0;
 }
@@ -574,6 +605,7 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   clv_sampler* h = new clv_sampler();
   h->cfg = *cfg;
   h->D = cfg->model_dim; h->K = cfg->n_cov; h->S = cfg->n_mh_steps; h->chains = cfg->n_chains;
+  h->use_pdl = getenv("CLV_NO_PDL") == nullptr;
   h->N = cfg->n_local; h->ncol = h->D == 2 ? 4 : 5; h->P = h->D * h->K + h->D * (h->D + 1) / 2;
   auto bail = [&](int code) { std::string m = h->err; clv_destroy(h); g_last_error = m; return code; };
 #define CKC(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { fail(h, CLV_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2)); return bail(CLV_ERR_CUDA); } } while (0)
@@ -960,16 +992,14 @@ int clv_p2p_export(clv_sampler* h, void* handle64) {
   if (!m) {
     CachedMailbox nm{};
     nm.device = h->cfg.device; nm.chains = h->chains; nm.rank = -1; nm.world = 0; nm.connected = false;
-    const size_t data = sizeof(long long) * 2 * P2P_MAX_WORLD * (size_t)h->chains * NSTAT_MAX;
-    const size_t flags = sizeof(unsigned long long) * 2 * P2P_MAX_WORLD * (size_t)h->chains;
-    nm.flags_off = data;
-    nm.bytes = data + flags;
+    // [2 parities][P2P_MAX_WORLD senders][chains][2 * NSTAT_MAX] 64-bit words (32 bits of payload + 32-bit tag each)
+    nm.bytes = sizeof(unsigned long long) * 2 * P2P_MAX_WORLD * (size_t)h->chains * 2 * NSTAT_MAX;
     CK(h, cudaMalloc(&nm.base, nm.bytes));
     CK(h, cudaMemset(nm.base, 0, nm.bytes));
     g_mailboxes.push_back(nm);
     m = &g_mailboxes.back();
   }
-  h->d_mailbox = m->base; h->mailbox_bytes = m->bytes; h->mailbox_flags_off = m->flags_off;
+  h->d_mailbox = m->base; h->mailbox_bytes = m->bytes;
   cudaIpcMemHandle_t hd;
   CK(h, cudaIpcGetMemHandle(&hd, h->d_mailbox));
   static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -1008,13 +1038,13 @@ int clv_p2p_connect(clv_sampler* h, const void* handles, int rank, int world) {
     }
     m->rank = rank; m->world = world; m->connected = true;
   }
+  // a fresh start for this handle's tags; the caller synchronises the ranks (host barrier) between this call and the
+  // first sweep, so no peer word can arrive before the memset
+  CK(h, cudaMemset(m->base, 0, m->bytes));
+  CK(h, cudaDeviceSynchronize());
   h->rank = rank; h->world = world;
-  h->d_mailbox = m->base; h->mailbox_bytes = m->bytes; h->mailbox_flags_off = m->flags_off;
-  for (int r = 0; r < world; ++r) {
-    h->peer_base[r] = m->peer_base[r];
-    h->peer_data[r] = (long long*)m->peer_base[r];
-    h->peer_flags[r] = (unsigned long long*)((char*)m->peer_base[r] + m->flags_off);
-  }
+  h->d_mailbox = m->base; h->mailbox_bytes = m->bytes;
+  for (int r = 0; r < world; ++r) h->peer_mail[r] = (unsigned long long*)m->peer_base[r];
   h->p2p = true;
   return CLV_OK;
 }

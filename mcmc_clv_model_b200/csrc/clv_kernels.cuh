@@ -84,6 +84,7 @@ struct SweepArgs {
   uint64_t seed;
   PhiloxRoundKeys rk;          // round keys of `seed` (launch constants)
   int store_zt;                // write z/tau state arrays
+  const int* error_flag;       // device error flag (2: a peer rank stopped)
   // injected variates (MODE_INJECT)
   const double *u_z, *e_tau, *u_tau, *t3_l, *t3_m, *u_acc, *n_eta;
 };
@@ -102,6 +103,13 @@ __constant__ double c_expk[6] = {EXP_BITS == 6 ? 92.332482616893656877 : 369.329
                                  EXP_BITS == 6 ? -0x1.62e42fefa0000p-7 : -0x1.62e42fefa0000p-9,
                                  EXP_BITS == 6 ? -0x1.cf79abc9e3b3ap-46 : -0x1.cf79abc9e3b3ap-48,
                                  8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01};
+
+// Programmatic dependent launch (stream mode): a kernel launched with the programmatic-stream-serialization attribute
+// may become resident while its predecessor still runs.  pdl_launch_dependents() lets the NEXT kernel of the stream
+// start its prologue; pdl_wait() blocks until the PREVIOUS kernel has completed and its writes are visible.  Both are
+// no-ops for an ordinary launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ long long to_fx(double v, double scale) { return __double2ll_rn(v * scale); }
 
@@ -437,10 +445,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArg
   const int K = mc.K;
   const int nstat = K * D + D * (D + 1) / 2;
   const ChainParams& cp = a.params[chain];
-  for (int t = tid; t < K * D; t += SWEEP_THREADS) s_beta[t] = cp.beta[t];
+  // prologue (programmatic dependent launch): nothing here depends on the level-2 kernel that precedes this launch
+  pdl_launch_dependents();
   for (int t = tid; t < EXP_N; t += SWEEP_THREADS) s_tab[t] = c_exptab[t];
   for (int t = tid; t < NSTAT_MAX + 1; t += SWEEP_THREADS) s_acc[t] = 0ull;
   clear_stats(s_priv, nstat);
+  pdl_wait();                                   // (beta, Sigma) of this sweep and the state of the previous one are complete
+  if (a.error_flag && *(volatile const int*)a.error_flag == 2) return;   // a peer rank stopped: do not sample on partial sums
+  for (int t = tid; t < K * D; t += SWEEP_THREADS) s_beta[t] = cp.beta[t];
   __syncthreads();
   const uint32_t c3 = dom_word(DOM_SAMPLER, a.chain_offset + (uint32_t)chain);
   SweepStep sw;
@@ -616,44 +628,25 @@ __global__ void __launch_bounds__(256) k_split_columns(const double* X, long lon
 // ------------------------------------------------------------------------------------------------
 // level 2
 // ------------------------------------------------------------------------------------------------
-template <int D>
-__device__ inline bool chol_lower(const double* A, double* L) {
-  bool ok = true;
-  for (int i = 0; i < D; ++i)
-    for (int j = 0; j <= i; ++j) {
-      double s = A[i * D + j];
-      for (int m = 0; m < j; ++m) s -= L[i * D + m] * L[j * D + m];
-      if (i == j) {
-        if (!(s > 0.0) || !isfinite(s)) { ok = false; s = 1.0; }
-        L[i * D + i] = sqrt(s);
-      } else {
-        L[i * D + j] = s / L[j * D + j];
-      }
-    }
-  for (int i = 0; i < D; ++i)
-    for (int j = i + 1; j < D; ++j) L[i * D + j] = 0.0;
-  return ok;
-}
-
 // P = inv(Sigma) (entries 00, 01, 11) and the eta conjugate scalars.
 template <int D>
 __device__ inline void derive_params(ChainParams& cp, double omega2) {
   const double* S = cp.Sigma;
   if (D == 2) {
-    double det = S[0] * S[3] - S[1] * S[2];
-    cp.P00 = S[3] / det;
-    cp.P01 = -S[1] / det;
-    cp.P11 = S[0] / det;
+    const double rdet = 1.0 / (S[0] * S[3] - S[1] * S[2]);
+    cp.P00 = S[3] * rdet;
+    cp.P01 = -S[1] * rdet;
+    cp.P11 = S[0] * rdet;
     cp.eta_post_var = 0.0;
     cp.eta_sd = 0.0;
   } else {
     double c00 = S[4] * S[8] - S[5] * S[7];
     double c01 = S[5] * S[6] - S[3] * S[8];
     double c02 = S[3] * S[7] - S[4] * S[6];
-    double det = S[0] * c00 + S[1] * c01 + S[2] * c02;
-    cp.P00 = c00 / det;
-    cp.P01 = (S[2] * S[7] - S[1] * S[8]) / det;
-    cp.P11 = (S[0] * S[8] - S[2] * S[6]) / det;
+    const double rdet = 1.0 / (S[0] * c00 + S[1] * c01 + S[2] * c02);
+    cp.P00 = c00 * rdet;
+    cp.P01 = (S[2] * S[7] - S[1] * S[8]) * rdet;
+    cp.P11 = (S[0] * S[8] - S[2] * S[6]) * rdet;
     double post_precision = 1.0 / omega2 + 1.0 / S[8];      // tri:325
     cp.eta_post_var = 1.0 / post_precision;
     cp.eta_sd = sqrt(cp.eta_post_var);
@@ -685,57 +678,114 @@ struct Level2Args {
   // customer-sharded runs with peer mailboxes (NVLink/NVSwitch P2P stores): the all-reduce of the statistics is done
   // HERE, inside the level-2 kernel, instead of a separate NCCL call.  world == 0: not used.
   int world, rank, n_chains;
-  unsigned long long flag_value;             // (init epoch << 32) | sweep: never repeats over the life of a handle
-  long long* peer_data[P2P_MAX_WORLD];           // rank r's mailbox data  [2][P2P_MAX_WORLD][chains][NSTAT_MAX]
-  unsigned long long* peer_flags[P2P_MAX_WORLD]; // rank r's mailbox flags [2][P2P_MAX_WORLD][chains]
+  uint32_t tag;                                   // never 0; differs from the tag of sweep - 2 and of any earlier init
+  long long timeout_ns;                           // give up (error flag 2) when a peer's words do not arrive in time
+  unsigned long long* peer_mail[P2P_MAX_WORLD];   // rank r's mailbox [2][P2P_MAX_WORLD][chains][2 * NSTAT_MAX] words
 };
+
+// The sweep-invariant constants of the level-2 draw, staged in shared memory (they used to be re-read from global
+// memory in each of ~7 dependent phases).
+struct Level2Const {
+  double V[MAXK * MAXK], LV[MAXK * MAXK], A0B0c[MAXK * MAXD], Q0[MAXD * MAXD], center[MAXD];
+  double fx_inv, nu_n, omega2;
+  int K, compat;
+};
+
+template <int D>
+__device__ __forceinline__ void load_level2_const(const ModelConst& mc, Level2Const& lc, int tid, int nthreads) {
+  const int K = mc.K;
+  for (int t = tid; t < K * K; t += nthreads) { lc.V[t] = mc.V[t]; lc.LV[t] = mc.LV[t]; }
+  for (int t = tid; t < K * D; t += nthreads) lc.A0B0c[t] = mc.A0B0c[t];
+  for (int t = tid; t < D * D; t += nthreads) lc.Q0[t] = mc.Q0[t];
+  for (int t = tid; t < D; t += nthreads) lc.center[t] = mc.center[t];
+  if (tid == 0) { lc.fx_inv = mc.fx_inv; lc.nu_n = mc.nu_n; lc.omega2 = mc.omega2; lc.K = K; lc.compat = mc.compat; }
+}
+
+// Everything of a level-2 draw that depends only on (seed, chain, sweep) -- never on the state: the Bartlett normals
+// and chi-squares (as the inverse of the Bartlett factor A) and the beta normals (as W = chol(V) z per response).
+// Produced OFF the critical path: in stream mode by k_level2 before it waits for the sweep kernel (programmatic
+// dependent launch), in the persistent kernel by an otherwise idle warp one sweep ahead.
+struct Level2Variates {
+  double trn[3], chi[3], zb[MAXD * MAXK];
+  double W[MAXD * MAXK];        // [d*K + k]
+  double Ainv[MAXD * MAXD];     // inverse of the lower-triangular Bartlett factor (scipy: normals below, sqrt(chi2) on the diagonal)
+};
+
+template <int D>
+__device__ __forceinline__ void level2_variates(const Level2Const& lc, Level2Variates& lv, PhiloxKey key, uint32_t c3,
+                                                uint32_t sweep, int injected, const double* iw_norm, const double* iw_chi2,
+                                                const double* beta_norm, int lane) {
+  const int K = lc.K;
+  constexpr int ntril = D * (D - 1) / 2;
+  const int nb = D * K;
+  // fp64 Philox transforms are long dependent chains: one per lane
+  for (int t = lane; t < ntril + D + nb; t += 32) {
+    if (t < ntril) lv.trn[t] = injected ? iw_norm[t] : level2_normal(key, c3, sweep, (uint32_t)t);
+    else if (t < ntril + D) {
+      const int i = t - ntril;
+      lv.chi[i] = injected ? iw_chi2[i] : level2_chi2(key, c3, sweep, 16u + i, lc.nu_n - D + 1 + i);   // chi2(nu_n - D + 1 + i)
+    } else {
+      const int j = t - ntril - D;
+      lv.zb[j] = injected ? beta_norm[j] : level2_normal(key, c3, sweep, 32u + (uint32_t)j);
+    }
+  }
+  __syncwarp();
+  // W = chol(V) z (per response)
+  for (int t = lane; t < nb; t += 32) {
+    const int d = t / K, k = t - d * K;
+    double s = 0.0;
+    for (int m = 0; m <= k; ++m) s += lc.LV[k * K + m] * lv.zb[d * K + m];
+    lv.W[t] = s;
+  }
+  // A^-1: A[i][i] = sqrt(chi_i), A[i][j] = normal (row-major fill below the diagonal)
+  if (lane == 0) {
+    double inv[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) inv[i] = rsqrt(lv.chi[i]);
+#pragma unroll
+    for (int t = 0; t < D * D; ++t) lv.Ainv[t] = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) lv.Ainv[i * D + i] = inv[i];
+    if (D == 2) {
+      lv.Ainv[2] = -lv.trn[0] * inv[0] * inv[1];
+    } else {
+      const double a10 = lv.trn[0], a20 = lv.trn[1], a21 = lv.trn[2];
+      const double i10 = -a10 * inv[0] * inv[1];
+      lv.Ainv[3] = i10;
+      lv.Ainv[7] = -a21 * inv[1] * inv[2];
+      lv.Ainv[6] = -(a20 * inv[0] + a21 * i10) * inv[2];
+    }
+  }
+  __syncwarp();
+}
 
 // Shared-memory scratch of one level-2 draw (one warp).
 struct Level2Scratch {
   double st[NSTAT_MAX];            // reduced statistics: X'Yc [k*D+d], then triu(Yc'Yc)
-  double trn[3], chi[3], zb[MAXD * MAXK];
-  double R[MAXK * MAXD], Bc[MAXK * MAXD], W[MAXD * MAXK], Ef[MAXD * MAXK];
+  double R[MAXK * MAXD], Bc[MAXK * MAXD];
   double Sn[MAXD * MAXD], CA[MAXD * MAXD];
   int ok;
 };
 
 // Conjugate multivariate regression draw (bi:233-262, tri:340-380) from the reduced statistics, by ONE WARP:
-// the variates and every small matrix product are spread over the lanes; the D x D factorisations run on lane 0.
-// Works in centred responses y - c (c = prior intercept row), which leaves E and beta - B0 unchanged.
-// sc.st must be filled (and visible to the warp) on entry; cp (shared or global memory) receives beta, Sigma, P.
+// every small matrix product is spread over the lanes; the D x D factorisations run on lane 0 (three long fp64
+// operations for D = 2: rsqrt, sqrt, one reciprocal).  Works in centred responses y - c (c = prior intercept row),
+// which leaves E and beta - B0 unchanged.  sc.st must be filled (and visible to the warp) on entry, lv holds the
+// variates of this draw; cp (shared or global memory) receives beta, Sigma, P.
 template <int D>
-__device__ __forceinline__ void level2_draw(const ModelConst& mc, Level2Scratch& sc, ChainParams& cp, PhiloxKey key,
-                                            uint32_t c3, uint32_t sweep, int injected, const double* iw_norm, const double* iw_chi2,
-                                            const double* beta_norm, int lane) {
-  const int K = mc.K;
-  constexpr int ntril = D * (D - 1) / 2;
+__device__ __forceinline__ void level2_algebra(const Level2Const& lc, Level2Scratch& sc, const Level2Variates& lv, ChainParams& cp,
+                                               int lane) {
+  const int K = lc.K;
   const int nb = D * K;
-  // variates (fp64 Philox transforms are long dependent chains: one per lane)
-  for (int t = lane; t < ntril + D + nb; t += 32) {
-    if (t < ntril) sc.trn[t] = injected ? iw_norm[t] : level2_normal(key, c3, sweep, (uint32_t)t);
-    else if (t < ntril + D) {
-      const int i = t - ntril;
-      sc.chi[i] = injected ? iw_chi2[i] : level2_chi2(key, c3, sweep, 16u + i, mc.nu_n - D + 1 + i);   // chi2(nu_n - D + 1 + i)
-    } else {
-      const int j = t - ntril - D;
-      sc.zb[j] = injected ? beta_norm[j] : level2_normal(key, c3, sweep, 32u + (uint32_t)j);
-    }
-  }
   // R = X'Yc + A0 B0c                                           bi:250
-  for (int t = lane; t < nb; t += 32) sc.R[t] = sc.st[t] + mc.A0B0c[t];
+  for (int t = lane; t < nb; t += 32) sc.R[t] = sc.st[t] + lc.A0B0c[t];
   __syncwarp();
-  // Bc = V R ; W = chol(V) z (per response)
+  // Bc = V R
   for (int t = lane; t < nb; t += 32) {
     const int k = t / D, d = t - k * D;
     double s = 0.0;
-    for (int m = 0; m < K; ++m) s += mc.V[k * K + m] * sc.R[m * D + d];
+    for (int m = 0; m < K; ++m) s += lc.V[k * K + m] * sc.R[m * D + d];
     sc.Bc[t] = s;
-  }
-  for (int t = lane; t < nb; t += 32) {
-    const int d = t / K, k = t - d * K;
-    double s = 0.0;
-    for (int m = 0; m <= k; ++m) s += mc.LV[k * K + m] * sc.zb[d * K + m];
-    sc.W[t] = s;
   }
   __syncwarp();
   // S_n = S0 + E'E + C'A0C = Q0 + Yc'Yc - Bc' R                bi:253-255
@@ -748,58 +798,72 @@ __device__ __forceinline__ void level2_draw(const ModelConst& mc, Level2Scratch&
       s1 += sc.Bc[k * D + d] * sc.R[k * D + e];
       s2 += sc.Bc[k * D + e] * sc.R[k * D + d];
     }
-    sc.Sn[lane] = sc.st[t] + mc.Q0[lane] - 0.5 * (s1 + s2);        // symmetrised
+    sc.Sn[lane] = sc.st[t] + lc.Q0[lane] - 0.5 * (s1 + s2);        // symmetrised
   }
   __syncwarp();
   if (lane == 0) {
-    double C[D * D], A[D * D];
-    bool ok = chol_lower<D>(sc.Sn, C);
-    // Sigma ~ IW(nu_n, S_n): scipy's Bartlett construction (bi:258)
-    for (int t = 0; t < D * D; ++t) A[t] = 0.0;
-    int t = 0;
-    for (int i = 1; i < D; ++i)
-      for (int j = 0; j < i; ++j) A[i * D + j] = sc.trn[t++];
-    for (int i = 0; i < D; ++i) A[i * D + i] = sqrt(sc.chi[i]);
-    // CA = C A^-1 (lower triangular)  =>  Sigma = CA CA'
-    for (int r = 0; r < D; ++r)
-      for (int j = D - 1; j >= 0; --j) {
-        double s = C[r * D + j];
-        for (int m = j + 1; m < D; ++m) s -= sc.CA[r * D + m] * A[m * D + j];
-        sc.CA[r * D + j] = s / A[j * D + j];
+    // C = chol(S_n), lower; reciprocal square roots instead of sqrt + divisions
+    double C[D * D];
+    bool ok = true;
+#pragma unroll
+    for (int t = 0; t < D * D; ++t) C[t] = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double piv = sc.Sn[j * D + j];
+#pragma unroll
+      for (int m = 0; m < j; ++m) piv -= C[j * D + m] * C[j * D + m];
+      if (!(piv > 0.0) || !isfinite(piv)) { ok = false; piv = 1.0; }
+      const double r = rsqrt(piv);
+      C[j * D + j] = piv * r;
+#pragma unroll
+      for (int i = j + 1; i < D; ++i) {
+        double s = sc.Sn[i * D + j];
+#pragma unroll
+        for (int m = 0; m < j; ++m) s -= C[i * D + m] * C[j * D + m];
+        C[i * D + j] = s * r;
       }
+    }
+    // Sigma ~ IW(nu_n, S_n): scipy's Bartlett construction (bi:258): CA = C A^-1 (lower)  =>  Sigma = CA CA'
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < D; ++m)
+          if (m >= j && m <= r) s += C[r * D + m] * lv.Ainv[m * D + j];
+        sc.CA[r * D + j] = s;
+      }
+#pragma unroll
     for (int d = 0; d < D; ++d)
+#pragma unroll
       for (int e = 0; e < D; ++e) {
         double s = 0.0;
+#pragma unroll
         for (int m = 0; m < D; ++m) s += sc.CA[d * D + m] * sc.CA[e * D + m];
         cp.Sigma[d * D + e] = s;
         if (!isfinite(s)) ok = false;
       }
-    derive_params<D>(cp, mc.omega2);
+    derive_params<D>(cp, lc.omega2);
     cp.status = ok ? 0 : 1;
     sc.ok = ok ? 1 : 0;
   }
   __syncwarp();
   // beta | Sigma: noise = kron(chol Sigma, chol V) z, ordered d*K+k           bi:261
-  for (int t = lane; t < nb; t += 32) {
-    const int d = t / K, k = t - d * K;
-    double s = 0.0;
-    for (int m = 0; m <= d; ++m) s += sc.CA[d * D + m] * sc.W[m * K + k];
-    sc.Ef[t] = s;
-  }
-  __syncwarp();
   for (int j = lane; j < nb; j += 32) {
     const int k = j / D, d = j - k * D;
-    const double bh = sc.Bc[j] + (k == 0 ? mc.center[d] : 0.0);    // B_hat = Bc + e0 c'
-    const double nz = (mc.compat == 0) ? sc.Ef[j] : sc.Ef[d * K + k];  // Q1: reference adds kron-ordered noise to ravel()
-    cp.beta[j] = bh + nz;
+    const int src = (lc.compat == 0) ? j : d * K + k;                  // Q1: reference adds kron-ordered noise to ravel()
+    const int dn = src / K, kn = src - dn * K;
+    double nz = 0.0;
+    for (int m = 0; m <= dn; ++m) nz += sc.CA[dn * D + m] * lv.W[m * K + kn];
+    cp.beta[j] = sc.Bc[j] + (k == 0 ? lc.center[d] : 0.0) + nz;      // B_hat = Bc + e0 c'
   }
   __syncwarp();
 }
 
 // level_2 row: beta.T.ravel() then the upper triangle of Sigma (bi:411-412, tri:549-554)
 template <int D>
-__device__ __forceinline__ void write_level2_row(const ModelConst& mc, const ChainParams& cp, double* o, int lane) {
-  const int K = mc.K;
+__device__ __forceinline__ void write_level2_row(int K, const ChainParams& cp, double* o, int lane) {
   for (int t = lane; t < D * K; t += 32) {
     const int d = t / K, k = t - d * K;
     o[t] = cp.beta[k * D + d];
@@ -811,62 +875,119 @@ __device__ __forceinline__ void write_level2_row(const ModelConst& mc, const Cha
   }
 }
 
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long global_timer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// One-shot all-reduce of a chain's int64 statistics over peer memory, fused into the level-2 kernel (one warp).
+// Low-latency ("LL") protocol: every 64-bit word that crosses NVLink carries 32 bits of payload and a 32-bit tag, and
+// an aligned 8-byte store is single-copy atomic, so a word IS its own arrival flag -- no fence, no separate flag
+// round trip.  Every rank stores the two halves of each partial sum into every rank's mailbox (its own included) and
+// polls its own mailbox until all world x 2 nstat words carry this sweep's tag; halves are added mod 2^64 (exact
+// integers => the same totals on every rank whatever the arrival order).  Mailboxes are double-buffered by sweep
+// parity: a rank can only reach sweep s+2 after every peer sent s+1, i.e. after they consumed parity s.
+// Returns false on time-out (a rank stopped): the caller raises error flag 2.
+__device__ __forceinline__ bool ll_allreduce_stats(const Level2Args& a, int chain, int nstat, unsigned long long* s_tot, int lane) {
+  const int par = (int)(a.sweep & 1u), nw = 2 * nstat;
+  const size_t words = 2 * (size_t)NSTAT_MAX;
+  const size_t send_base = (((size_t)par * P2P_MAX_WORLD + a.rank) * a.n_chains + chain) * words;
+  const unsigned long long tag = (unsigned long long)a.tag << 32;
+  for (int t = lane; t < nstat; t += 32) s_tot[t] = 0ull;
+  for (int w = lane; w < nw; w += 32) {
+    const unsigned long long v = a.acc[chain * NSTAT_MAX + (w >> 1)];
+    const unsigned long long word = ((w & 1) ? (v >> 32) : (v & 0xffffffffull)) | tag;
+    for (int r = 0; r < a.world; ++r) st_volatile_u64(a.peer_mail[r] + send_base + w, word);
+  }
+  __syncwarp();
+  for (int t = lane; t < nstat; t += 32) a.acc[chain * NSTAT_MAX + t] = 0ull;
+  const int total = nw * a.world;
+  constexpr int BATCH = 8;
+  const unsigned long long* mine = a.peer_mail[a.rank];
+  bool ok = true;
+  long long t0 = 0;
+  for (int q0 = lane; q0 < total && ok; q0 += 32 * BATCH) {
+    unsigned long long x[BATCH];
+    const unsigned long long* p[BATCH];
+#pragma unroll
+    for (int b = 0; b < BATCH; ++b) {
+      const int q = q0 + 32 * b;
+      const int r = q / nw, w = q - r * nw;
+      p[b] = mine + (((size_t)par * P2P_MAX_WORLD + r) * a.n_chains + chain) * words + w;
+      x[b] = (q < total) ? ld_volatile_u64(p[b]) : tag;          // all loads of a batch in flight together
+    }
+#pragma unroll
+    for (int b = 0; b < BATCH; ++b) {
+      const int q = q0 + 32 * b;
+      if (q >= total) continue;
+      unsigned spins = 0;
+      while ((x[b] & 0xffffffff00000000ull) != tag) {
+        x[b] = ld_volatile_u64(p[b]);
+        if ((++spins & 1023u) == 0u) {
+          const long long now = global_timer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > a.timeout_ns) { ok = false; break; }
+        }
+      }
+      if (!ok) break;
+      const int w = q % nw;
+      atomicAdd(&s_tot[w >> 1], (w & 1) ? (x[b] << 32) : (x[b] & 0xffffffffull));
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  return ok;
+}
+
 template <int D>
 __global__ void __launch_bounds__(32) k_level2(Level2Args a) {
   __shared__ Level2Scratch sc;
+  __shared__ Level2Const lc;
+  __shared__ Level2Variates lv;
+  __shared__ unsigned long long s_tot[NSTAT_MAX];
   const ModelConst& mc = *a.mc;
   const int chain = blockIdx.x, lane = threadIdx.x;
-  const int K = mc.K;
+  constexpr int ntril = D * (D - 1) / 2;
+  // ---- prologue: needs nothing of the sweep that precedes this kernel in the stream --------------------------------
+  pdl_launch_dependents();                   // the next sweep kernel may become resident and run ITS prologue
+  load_level2_const<D>(mc, lc, lane, 32);
+  __syncwarp();
+  const int K = lc.K;
   const int nstat = K * D + D * (D + 1) / 2;
+  level2_variates<D>(lc, lv, seed_key(a.seed), dom_word(DOM_LEVEL2, a.chain_offset + (uint32_t)chain), a.sweep, a.injected,
+                     a.injected ? a.iw_norm + chain * ntril : nullptr, a.injected ? a.iw_chi2 + chain * D : nullptr,
+                     a.injected ? a.beta_norm + chain * D * K : nullptr, lane);
+  // ---- the statistics of the sweep kernel ------------------------------------------------------------------------------
+  pdl_wait();
+  if (*(volatile int*)a.error_flag == 2) return;          // a peer stopped: leave the state as it is
   if (a.world <= 1) {
     for (int t = lane; t < nstat; t += 32) {
       unsigned long long* p = &a.acc[chain * NSTAT_MAX + t];
-      sc.st[t] = (double)(long long)(*p) * mc.fx_inv;
+      sc.st[t] = (double)(long long)(*p) * lc.fx_inv;
       *p = 0ull;
     }
   } else {
-    // One-shot all-reduce over peer memory: every rank stores its partial sums into every rank's mailbox, publishes
-    // the sweep number as the flag, waits for the other ranks' flags and adds the W partials (int64: exact, so every
-    // rank gets the same totals whatever the arrival order).  Mailboxes are double-buffered by sweep parity: a rank
-    // can only reach sweep s+2 after every peer published s+1, i.e. after they finished reading parity s.
-    const int par = (int)(a.sweep & 1u);
-    const size_t slot = ((size_t)par * P2P_MAX_WORLD + a.rank) * a.n_chains + chain;
-    for (int t = lane; t < nstat; t += 32) {
-      unsigned long long* p = &a.acc[chain * NSTAT_MAX + t];
-      const long long v = (long long)(*p);
-      *p = 0ull;
-      for (int r = 0; r < a.world; ++r) __stcg(&a.peer_data[r][slot * NSTAT_MAX + t], v);
+    if (!ll_allreduce_stats(a, chain, nstat, s_tot, lane)) {
+      if (lane == 0) *a.error_flag = 2;
+      return;
     }
-    __threadfence_system();
     __syncwarp();
-    if (lane < a.world) *((volatile unsigned long long*)&a.peer_flags[lane][slot]) = a.flag_value;
-    if (lane < a.world) {
-      const size_t src = ((size_t)par * P2P_MAX_WORLD + lane) * a.n_chains + chain;
-      volatile unsigned long long* f = (volatile unsigned long long*)&a.peer_flags[a.rank][src];
-      const long long t0 = clock64();
-      while (*f != a.flag_value)
-        if (clock64() - t0 > 8000000000ll) { *a.error_flag = 2; break; }   // a peer died: give up after ~4 s
-    }
-    __threadfence_system();
-    __syncwarp();
-    for (int t = lane; t < nstat; t += 32) {
-      long long tot = 0;
-      for (int r = 0; r < a.world; ++r) {
-        const size_t src = ((size_t)par * P2P_MAX_WORLD + r) * a.n_chains + chain;
-        tot += __ldcv(&a.peer_data[a.rank][src * NSTAT_MAX + t]);
-      }
-      sc.st[t] = (double)tot * mc.fx_inv;
-    }
+    for (int t = lane; t < nstat; t += 32) sc.st[t] = (double)(long long)s_tot[t] * lc.fx_inv;
   }
   __syncwarp();
   ChainParams& cp = a.params[chain];
-  const PhiloxKey key = seed_key(a.seed);
-  constexpr int ntril = D * (D - 1) / 2;
-  level2_draw<D>(mc, sc, cp, key, dom_word(DOM_LEVEL2, a.chain_offset + (uint32_t)chain), a.sweep, a.injected, a.injected ? a.iw_norm + chain * ntril : nullptr,
-                 a.injected ? a.iw_chi2 + chain * D : nullptr, a.injected ? a.beta_norm + chain * D * K : nullptr, lane);
+  level2_algebra<D>(lc, sc, lv, cp, lane);
   if (lane == 0 && !sc.ok) *a.error_flag = 1;
   if (a.draw_index >= 0)
-    write_level2_row<D>(mc, cp, a.level2_draws + ((long long)chain * a.n_draws + a.draw_index) * (D * K + D * (D + 1) / 2), lane);
+    write_level2_row<D>(K, cp, a.level2_draws + ((long long)chain * a.n_draws + a.draw_index) * (D * K + D * (D + 1) / 2), lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -918,9 +1039,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(Per
   __shared__ unsigned long long s_acc[NSTAT_MAX + 1];
   __shared__ ChainParams s_cp;
   __shared__ Level2Scratch sc;
+  __shared__ Level2Const lc;
+  __shared__ Level2Variates lv[2];         // variates of sweep s live in lv[s & 1]; drawn one sweep ahead by warp 1
   const SweepArgs& a = pa.sw;
   const ModelConst& mc = *a.mc;
-  const int chain = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int chain = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = mc.K;
   const int nstat = K * D + D * (D + 1) / 2;
   const unsigned int nblocks = gridDim.x * gridDim.y;
@@ -931,23 +1054,29 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(Per
   const long long csz = (long long)gridDim.y * NSTAT_MAX;
   for (int t = tid; t < EXP_N; t += SWEEP_THREADS) s_tab[t] = c_exptab[t];
   clear_stats(s_priv, nstat);
+  load_level2_const<D>(mc, lc, tid, SWEEP_THREADS);
   {
     const double* src = reinterpret_cast<const double*>(&pa.params[chain]);
     double* dst = reinterpret_cast<double*>(&s_cp);
     for (int t = tid; t < (int)(sizeof(ChainParams) / sizeof(double)); t += SWEEP_THREADS) dst[t] = src[t];
   }
   __syncthreads();
+  // the variates of the first level-2 draw of this launch (they depend on (seed, chain, sweep) only)
+  if (warp == 1) level2_variates<D>(lc, lv[pa.first_sweep & 1u], key, c3_l2, pa.first_sweep, 0, nullptr, nullptr, nullptr, lane);
 
-  auto level2_phase = [&](uint32_t sweep, long long draw_index, unsigned long long* slot_read) {
-    // every block of the chain draws the same (beta, Sigma) from the same totals and the same Philox key
-    if (tid < 32) {
+  auto level2_phase = [&](uint32_t sweep, long long draw_index, unsigned long long* slot_read, bool more) {
+    // every block of the chain draws the same (beta, Sigma) from the same totals and the same Philox key: warp 0 does
+    // the algebra of this sweep while warp 1 (idle otherwise) prepares the variates of the next one
+    if (warp == 0) {
       for (int t = lane; t < nstat; t += 32)
-        sc.st[t] = (double)(long long)__ldcg(&slot_read[chain * NSTAT_MAX + t]) * mc.fx_inv;
+        sc.st[t] = (double)(long long)__ldcg(&slot_read[chain * NSTAT_MAX + t]) * lc.fx_inv;
       __syncwarp();
-      level2_draw<D>(mc, sc, s_cp, key, c3_l2, sweep, 0, nullptr, nullptr, nullptr, lane);
+      level2_algebra<D>(lc, sc, lv[sweep & 1u], s_cp, lane);
       if (lane == 0 && !sc.ok) *pa.error_flag = 1;
       if (blockIdx.x == 0 && draw_index >= 0)
-        write_level2_row<D>(mc, s_cp, pa.level2_draws + ((long long)chain * pa.n_draws + draw_index) * (D * K + D * (D + 1) / 2), lane);
+        write_level2_row<D>(K, s_cp, pa.level2_draws + ((long long)chain * pa.n_draws + draw_index) * (D * K + D * (D + 1) / 2), lane);
+    } else if (warp == 1 && more) {
+      level2_variates<D>(lc, lv[(sweep + 1u) & 1u], key, c3_l2, sweep + 1u, 0, nullptr, nullptr, nullptr, lane);
     }
     __syncthreads();
   };
@@ -957,12 +1086,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(Per
     const long long step = pa.run_step0 + it;
     const bool kept = step > pa.burnin && (step - 1 - pa.burnin) % pa.thin == 0;
     const long long draw = kept ? (step - 1 - pa.burnin) / pa.thin : -1;
+    const bool more = it + 1 < pa.n_sweeps;
     unsigned long long* slot_prev = pa.acc3 + (long long)((sweep + 2u) % 3u) * csz;   // (sweep-1) % 3
     unsigned long long* slot_cur = pa.acc3 + (long long)(sweep % 3u) * csz;
     unsigned long long* slot_next = pa.acc3 + (long long)((sweep + 1u) % 3u) * csz;
     if (D == 2) {
       grid_barrier(pa.barrier, nblocks);         // statistics of sweep-1 (or the initial state) are complete
-      level2_phase(sweep, draw, slot_prev);      // bi:393
+      level2_phase(sweep, draw, slot_prev, more);      // bi:393
     }
     if (blockIdx.x == 0)
       for (int t = tid; t < nstat; t += SWEEP_THREADS) slot_next[chain * NSTAT_MAX + t] = 0ull;
@@ -982,7 +1112,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(Per
       atomicAdd(reinterpret_cast<unsigned long long*>(&a.loglik_acc[chain * a.loglik_stride + draw]), s_acc[NSTAT_MAX]);
     if (D == 3) {
       grid_barrier(pa.barrier, nblocks);         // tri:529-536: level-2 closes the sweep
-      level2_phase(sweep, draw, slot_cur);
+      level2_phase(sweep, draw, slot_cur, more);
     }
   }
   if (blockIdx.x == 0) {

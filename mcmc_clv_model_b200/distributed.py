@@ -69,7 +69,9 @@ def connect_p2p(sampler, group=None):
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if sampler.p2p_is_cached(rank, world):        # every rank made the same calls before: the answer is the same everywhere
         sampler.p2p_connect(None, rank, world)
-        return
-    handles = [None] * world
-    dist.all_gather_object(handles, sampler.p2p_export(), group=group)
-    sampler.p2p_connect(handles, rank, world)
+    else:
+        handles = [None] * world
+        dist.all_gather_object(handles, sampler.p2p_export(), group=group)
+        sampler.p2p_connect(handles, rank, world)
+    # every rank has cleared and mapped its mailbox before any rank starts to send (clv_p2p_connect's contract)
+    dist.barrier(group=group)

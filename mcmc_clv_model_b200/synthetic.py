@@ -61,12 +61,19 @@ def elog2cbs(elog, T_cal: float):
 
 
 def generate_pareto_abe(n: int, T_cal, T_star, beta, gamma, covars: Optional[np.ndarray] = None,
-                        seed: Optional[int] = None):
+                        seed: Optional[int] = None, *, cbs_clock: str = "reference"):
     """Simulate customers under Abe (2009) -- signature and returned (cbs, elog) frames of bi:95-187.
 
     The CBS columns come from the device generator; the event log is laid out on the host from the
     generated (x, t_x, x_star, tau): first purchase at t = 0, x - 1 uniform order statistics below t_x,
     t_x itself, and the hold-out purchases uniform on (T_cal, min(tau, T_cal + max T_star)].
+
+    cbs_clock="reference" (default) reproduces the reference's CBS for cohorts with different T_cal: the event log is
+    shifted by the birth offsets T_zero = max(T_cal) - T_cal (bi:158) and summarised with ONE calibration end
+    (`elog2cbs(elog, T_cal_fix)`, bi:165), so `t_x` is on the shifted clock (T_zero for a customer without repeat
+    purchase) and the `T_cal` column is the scalar max(T_cal).  cbs_clock="customer" returns each customer's own clock
+    (t_x since the first purchase, per-customer T_cal) -- what the sampler's likelihood actually needs.  The two are
+    identical for a scalar T_cal.
     """
     import pandas as pd
     beta = np.asarray(beta, dtype=float)
@@ -103,8 +110,12 @@ def generate_pareto_abe(n: int, T_cal, T_star, beta, gamma, covars: Optional[np.
     et = et + T_zero[ec - 1]
     order = np.lexsort((et, ec))
     elog = pd.DataFrame({"cust": ec[order].astype(float), "t": et[order]})
-    cbs = pd.DataFrame({"cust": cust.astype(float), "x": x, "t_x": g["t_x"],
-                        "T_cal": T_cal})
+    if cbs_clock == "reference":
+        cbs = pd.DataFrame({"cust": cust.astype(float), "x": x, "t_x": g["t_x"] + T_zero, "T_cal": float(T_cal_fix)})
+    elif cbs_clock == "customer":
+        cbs = pd.DataFrame({"cust": cust.astype(float), "x": x, "t_x": g["t_x"], "T_cal": T_cal})
+    else:
+        raise ValueError("cbs_clock must be 'reference' or 'customer'")
     cbs["lambda_true"], cbs["mu_true"], cbs["tau_true"] = g["lambda_true"], g["mu_true"], g["tau_true"]
     cbs["alive_true"] = (T_zero + g["tau_true"]) > T_cal_fix                   # bi:169
     for t_star in T_star:                                                      # bi:172-181

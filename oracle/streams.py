@@ -119,11 +119,15 @@ class ReplayStreams(_Base):
 class PhiloxStreams(_Base):
     """Strict-f64 device contract; ``gids`` are global customer ids."""
 
-    def __init__(self, seed, chain, gids, n_mh_steps, D, K):
+    def __init__(self, seed, chain, gids, n_mh_steps, D, K, level1_variates=None):
+        """level1_variates: optional callable(sweep) -> dict(t3_l, t3_m, u_acc), each (S, N), replacing the strict-f64
+        Metropolis variates -- the hook through which a test replays the variates the device's FAST transforms
+        produced (clv_debug_variates) so that the FAST kernel's whole trajectory can be checked."""
         self.seed, self.chain = seed, chain
         self.gids = np.asarray(gids)
         self.S, self.D, self.K = n_mh_steps, D, K
         self._cache_step = None
+        self._level1_variates = level1_variates
 
     def begin_sweep(self, step):
         self.step = step
@@ -131,6 +135,8 @@ class PhiloxStreams(_Base):
         self._acc_calls = 0
         self._v = px.sampler_variates(self.seed, self.chain, self.gids, step, self.S,
                                       with_eta=(self.D == 3))
+        if self._level1_variates is not None:
+            self._v.update(self._level1_variates(step))
         self._l2 = None
 
     def u_z(self, N):

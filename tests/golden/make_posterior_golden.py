@@ -20,8 +20,9 @@ CASES = {
     "tri_k3": dict(model="tri", cov=["gender_F", "age_scaled"], chains=8, burnin=3000, mcmc=3000, seed=42),
     "bi_k4": dict(model="bi", cov=["first_sales_scaled", "age_scaled", "gender_binary"], chains=8, burnin=4000, mcmc=4000, seed=42),
     # BASELINE.json configs[1] / configs[2]: full CDNOW (23 570 customers).  Burn-in covers the degenerate start.
-    "c2_full_bi_k2": dict(model="bi", data="cdnow_full.npz", cov=["first_sales_scaled"], chains=8, burnin=3000, mcmc=1500, seed=42),
-    "c3_full_tri_k3": dict(model="tri", data="cdnow_full.npz", cov=["gender_F", "age_scaled"], chains=8, burnin=3000, mcmc=1500, seed=42),
+    # The reference drivers' real settings (run_mcmc_full.py:137-147, trivariate/run_mcmc_full.py:80-90): 10 000 + 4 000, thin 1.
+    "c2_full_bi_k2": dict(model="bi", data="cdnow_full.npz", cov=["first_sales_scaled"], chains=4, burnin=10000, mcmc=4000, seed=42),
+    "c3_full_tri_k3": dict(model="tri", data="cdnow_full.npz", cov=["gender_F", "age_scaled"], chains=4, burnin=10000, mcmc=4000, seed=42),
 }
 
 
@@ -44,7 +45,8 @@ def one_chain(args):
         out = m.mcmc_draw_parameters(cbs, covariates=cfg["cov"], mcmc=cfg["mcmc"], burnin=cfg["burnin"], thin=1, chains=1,
                                      seed=cfg["seed"] + c, trace=0)
     l1 = out["level_1"][0]
-    return out["level_2"][0], l1[::20].mean(axis=(0, 1)), out["log_likelihood"]
+    # level-1 aggregates: column means over every 20th draw, and per-customer posterior means of the first 8 customers
+    return out["level_2"][0], l1[::20].mean(axis=(0, 1)), out["log_likelihood"], l1[:, :8, :].mean(axis=0)
 
 
 def main():
@@ -62,6 +64,8 @@ def main():
                         mcse=np.array([s[j]["mcse_mean"] for j in range(l2.shape[2])]),
                         ess=np.array([s[j]["ess_geyer"] for j in range(l2.shape[2])]),
                         chain_means=l2.mean(axis=1), level1_col_means=np.mean([r[1] for r in res], axis=0),
+                        quantiles=np.percentile(l2.reshape(-1, l2.shape[2]), [2.5, 50, 97.5], axis=0),
+                        level_2=l2.astype(np.float32), customer_means8=np.mean([r[3] for r in res], axis=0),
                         loglik=np.mean([r[2] for r in res]), chains=cfg["chains"], burnin=cfg["burnin"], mcmc=cfg["mcmc"],
                         covariates=np.array(cfg["cov"]))
     print(name, "mean", np.round([s[j]["mean"] for j in range(l2.shape[2])], 3))

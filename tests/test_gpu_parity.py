@@ -584,3 +584,106 @@ def test_compat_paper_beta_draw_vs_oracle():
             out = s.sweep_injected(_sweep_arrays(g, t, D))
             np.testing.assert_allclose(out["level_2"][0], ora["level_2"][t], rtol=RTOL, atol=1e-9)
             np.testing.assert_array_equal(out["level_1"][0][:, 3], ora["level_1"][t][:, 3])
+
+
+def _device_fast_variates(seed, n, S):
+    """callable(sweep) -> the FAST-mode Metropolis variates of chain 0 exactly as k_sweep<.,FAST> consumes them
+    (clv_debug_variates runs the kernel's own t3_fast / low_bytes code)."""
+    from mcmc_clv_model_b200 import _lib as L
+    lib = L.load()
+
+    def variates(sweep):
+        out = {k: np.empty((S, n)) for k in ("t3_l", "t3_m", "u_acc")}
+        for step in range(S):
+            L.check(lib.clv_debug_variates(0, seed, sweep, step, L.RNG_FAST, n, L.dptr(out["t3_l"][step]),
+                                           L.dptr(out["t3_m"][step]), L.dptr(out["u_acc"][step])))
+        return out
+    return variates
+
+
+@pytest.mark.parametrize("mode", ["stream", "persistent"])
+@pytest.mark.parametrize("D,cov", [(2, ["first_sales_scaled"]), (3, ["gender_F", "age_scaled"])])
+def test_fast_kernel_trajectory_vs_oracle_at_full_cdnow_size(cdnow_full, D, cov, mode):
+    """The TIMED kernel (rng="fast": fp32 SFU proposal variates, fp32-screened accept) at the size of BASELINE.json
+    configs[1] / configs[2] (23 570 customers = 185 tiles; C2: K=2 bivariate, C3: K=3 trivariate): its FAST variates
+    are pulled from the device and replayed through the oracle, and the whole production trajectory (z, tau, 20
+    Metropolis steps, eta, level-2, burn-in / thinning) must match: z bit-exact, continuous 1e-6 (north_star)."""
+    d = cdnow_full
+    n = d["x"].size
+    X = np.column_stack([np.ones(n)] + [d[c].astype(float) for c in cov])
+    cbs = ao.Cbs(x=d["x"].astype(np.int64), t_x=d["t_x"], T_cal=d["T_cal"], X=X, log_s=d["log_s"] if D == 3 else None)
+    seed, burnin, mcmc, thin, S = 2025, 1, 3, 1, 20
+    ora = ao.run_chain(cbs, ao.default_hyper(cbs.K, D),
+                       PhiloxStreams(seed, 0, np.arange(n), S, D, cbs.K, level1_variates=_device_fast_variates(seed, n, S)),
+                       mcmc=mcmc, burnin=burnin, thin=thin, D=D, n_mh_steps=S)
+    with Sampler(cbs.x, cbs.t_x, cbs.T_cal, X, cbs.log_s, model_dim=D, chains=1, n_mh_steps=S, seed=seed, rng="fast",
+                 sweep_mode=mode) as s:
+        out = s.run(burnin, mcmc, thin)
+    np.testing.assert_array_equal(out["level_1"][0][:, :, 3], ora["level_1"][:, :, 3])
+    np.testing.assert_allclose(out["level_1"][0], ora["level_1"], rtol=RTOL)
+    np.testing.assert_allclose(out["level_2"][0], ora["level_2"], rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(out["loglik_sum"][0] / n, ora["log_likelihood"], rtol=RTOL)
+
+
+def test_strict_trajectory_spanning_many_tiles_and_blocks(cdnow_full):
+    """STRICT Philox at 23 570 customers with 2 chains in one handle (the chain index travels in the counter; 185 tiles
+    per chain, i.e. far more than the single tile of the injected goldens)."""
+    d = cdnow_full
+    n = d["x"].size
+    X = np.column_stack([np.ones(n), d["first_sales_scaled"]])
+    cbs = ao.Cbs(x=d["x"].astype(np.int64), t_x=d["t_x"], T_cal=d["T_cal"], X=X)
+    seed, S = 99, 20
+    with Sampler(cbs.x, cbs.t_x, cbs.T_cal, X, model_dim=2, chains=2, n_mh_steps=S, seed=seed, rng="strict", sweep_mode="stream") as s:
+        out = s.run(1, 2, 1)
+    for chain in (0, 1):
+        ora = ao.run_chain(cbs, ao.default_hyper(2, 2), PhiloxStreams(seed, chain, np.arange(n), S, 2, 2), mcmc=2, burnin=1,
+                           thin=1, D=2, n_mh_steps=S)
+        np.testing.assert_array_equal(out["level_1"][chain][:, :, 3], ora["level_1"][:, :, 3])
+        np.testing.assert_allclose(out["level_1"][chain], ora["level_1"], rtol=RTOL)
+        np.testing.assert_allclose(out["level_2"][chain], ora["level_2"], rtol=RTOL, atol=1e-9)
+
+
+def test_generator_matches_the_reference_generator_moments():
+    """`generate_pareto_abe` through the drop-in module vs golden moments of the reference's OWN generator
+    (tests/golden/make_generator_golden.py ran bi:95-187 unmodified: n = 20 000, scalar and vector T_cal).  Every
+    statistic within 4 combined standard errors; and the reference's CBS convention for cohorts (bi:158,165): t_x on
+    the shifted clock, one scalar T_cal."""
+    from mcmc_clv_model_b200.synthetic import generate_pareto_abe
+    g = load_golden("gen_ref.npz")
+    names = [str(s) for s in g["names"]]
+    n, T_star = int(g["n"]), float(g["T_star"])
+
+    def moments(cbs, T_rel, t_rel):
+        x, xs = cbs["x"].to_numpy(float), cbs["x_star"].to_numpy(float)
+        alive = cbs["alive_true"].to_numpy(float)
+        st = {"p_x0": x == 0, "p_x_ge1": x >= 1, "p_x_ge3": x >= 3, "p_x_ge10": x >= 10, "mean_sqrt_x": np.sqrt(x),
+              "mean_log1p_x": np.log1p(x), "p_xs0": xs == 0, "p_xs_ge3": xs >= 3, "mean_log1p_xs": np.log1p(xs), "alive": alive,
+              "mean_tx_over_T": t_rel / T_rel, "p_tx_late": (t_rel / T_rel) > 0.75,
+              "mean_log_lambda": np.log(cbs["lambda_true"].to_numpy()), "mean_log_mu": np.log(cbs["mu_true"].to_numpy()),
+              "corr_proxy": np.log1p(x) * alive}
+        val = np.array([np.mean(st[k].astype(float)) for k in names])
+        se = np.array([np.std(st[k].astype(float), ddof=1) / np.sqrt(len(x)) for k in names])
+        return val, se
+
+    # scalar T_cal: ten times the reference's sample, so the error is the golden's
+    big = 10 * n
+    cbs, elog = generate_pareto_abe(big, 32.0, T_star, g["beta"], g["gamma"], seed=42)
+    assert list(cbs.columns[:4]) == ["cust", "x", "t_x", "T_cal"] and np.all(cbs["T_cal"] == 32.0)
+    val, se = moments(cbs, np.full(big, 32.0), cbs["t_x"].to_numpy())
+    z = np.abs(val - g["scalar_val"]) / np.hypot(se, g["scalar_se"])
+    assert z.max() < 4.0, dict(zip(names, np.round(z, 2)))
+    # vector T_cal with the golden's covariate and T_cal inputs: law and CBS convention
+    T_vec, T_fix = g["vector_T_cal_in"], float(g["vector_T_fix"])
+    cbs2, elog2 = generate_pareto_abe(n, T_vec, T_star, g["beta"], g["gamma"], covars=g["vector_cov"], seed=43)
+    T_zero = T_fix - T_vec
+    assert np.all(cbs2["T_cal"].to_numpy() == T_fix)                                   # bi:165: one scalar T_cal
+    t_rel = cbs2["t_x"].to_numpy() - T_zero
+    assert np.all(t_rel >= 0) and np.all((cbs2["x"].to_numpy() == 0) == (t_rel == 0))   # x = 0 => t_x = T_zero (first purchase)
+    np.testing.assert_allclose(elog2.groupby("cust")["t"].min().to_numpy(), T_zero)     # event log on the shifted clock
+    val2, se2 = moments(cbs2, T_vec, t_rel)
+    z2 = np.abs(val2 - g["vector_val"]) / np.hypot(se2, g["vector_se"])
+    assert z2.max() < 4.0, dict(zip(names, np.round(z2, 2)))
+    # the customer clock is still available, and equals the reference clock for scalar T_cal
+    cbs3, _ = generate_pareto_abe(n, T_vec, T_star, g["beta"], g["gamma"], covars=g["vector_cov"], seed=43, cbs_clock="customer")
+    np.testing.assert_allclose(cbs3["t_x"].to_numpy(), t_rel, atol=1e-12)
+    np.testing.assert_array_equal(cbs3["T_cal"].to_numpy(), T_vec)
