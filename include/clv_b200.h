@@ -117,9 +117,14 @@ int clv_comm_unique_id(void* out128);
 int clv_comm_init(clv_sampler* h, const void* unique_id128, int rank, int world);
 
 /* Optional, after clv_comm_init + clv_init_state: replace the per-sweep NCCL all-reduce by a one-shot all-reduce over
- * peer memory FUSED INTO the level-2 kernel (each rank stores its int64 partial sums into every rank's mailbox over
- * NVLink/NVSwitch, publishes a flag, and adds the W partials it received).  Every rank exports its mailbox
- * (64-byte cudaIpcMemHandle), the host all-gathers the handles, every rank connects.  world <= 16, one process per GPU. */
+ * peer memory FUSED INTO the level-2 kernel.  Each rank stores the halves of its int64 partial sums into every rank's
+ * mailbox over NVLink/NVSwitch as 8-byte words of 32 payload bits + a 32-bit (init epoch, sweep) tag -- an aligned 8-byte
+ * store is atomic, so a word is its own arrival flag: no fence, no flag round trip -- and adds the words it received.
+ * Every rank exports its mailbox (64-byte cudaIpcMemHandle), the host all-gathers the handles, every rank connects.
+ * clv_p2p_connect clears the rank's own mailbox: the caller must synchronise the ranks (a host barrier) between
+ * clv_p2p_connect and the first sweep.  A rank that does not receive its peers' words within CLV_P2P_TIMEOUT_S seconds
+ * (environment, default 120) raises CLV_ERR_COMM; the remaining sweeps of the call are skipped.
+ * world <= 16, one process per GPU. */
 int clv_p2p_export(clv_sampler* h, void* handle64);
 int clv_p2p_connect(clv_sampler* h, const void* handles /* world x 64 bytes */, int rank, int world);
 /* Mailboxes and their peer mappings live for the life of the process; returns 1 when a connected set already exists for
@@ -254,6 +259,14 @@ int clv_elog2cbs(int device, int64_t n_events, const int64_t* cust, const int32_
  * 0..n-1 of chain 0 consume in sweep `sweep`, as the sweep kernel generates them in rng_mode fast / strict. */
 int clv_debug_variates(int device, uint64_t seed, uint32_t sweep, int32_t step, int rng_mode, int64_t n, double* t3_l,
                        double* t3_m, double* u_acc);
+
+/* ---- test hook: the customer-sharded path on ONE device.  `shards` are n_shards (2..16) handles on the same device holding
+ * contiguous customer ranges of one problem (same model, chains, seed, n_global; gid_offset = start of the range; initialised
+ * with the GLOBAL statistics; no communicator).  Advances all of them n_sweeps sweeps in lockstep; the per-sweep all-reduce
+ * of the level-2 statistics runs the production peer-mailbox protocol with the ranks emulated as the blocks of one
+ * cooperative launch (kernels of separate launches must not wait on each other on one GPU).  The shards' states must
+ * then equal the unsharded handle's bit for bit -- the single-GPU proof of "results do not depend on the GPU count". */
+int clv_debug_lockstep_advance(clv_sampler** shards, int n_shards, int64_t n_sweeps);
 
 /* ---- test hook: the parallel host memcpy behind the staged transfers (no device involved): copies `bytes` from src to
  * dst on the library's copy threads, returns the number of threads that took part. */

@@ -130,46 +130,69 @@ def mcmc_draw_parameters_rfm_m(cal_cbs, covariates: Sequence[str] | None = None,
 # ---------------------------------------------------------------------------------------------
 # forecast
 # ---------------------------------------------------------------------------------------------
-def _forecast(T_cal, level1_list, T_star, seed, simulate_spend, sigma_s, device=0):
+def _forecast(T_cal, level1_list, T_star, seed, simulate_spend, sigma_s, devices=None):
+    """x* (and spend) for every (draw, customer) cell, chain-major like bi:530-531.  With several devices the draws of
+    every chain are cut into contiguous ranges, one per device ("shard over customers or draws, no
+    collective"): the Philox counters carry the GLOBAL draw index (`draw_offset`), so the result does not depend on the
+    number of devices."""
     lib = L.load()
+    devices = list(devices) if devices else [0]
     T_cal = np.ascontiguousarray(T_cal, dtype=np.float64)
     N = T_cal.size
     ncol = level1_list[0].shape[2]
     seed_v = _seed_value(seed)
-    xs_parts, sp_parts = [], []
-    off = 0
+    chains = []
     for chain in level1_list:                                            # bi:530-531: chain-major
         a = np.ascontiguousarray(chain, dtype=np.float64)
         if a.shape[1] != N:
             raise ValueError("level_1 draws and cbs disagree on the number of customers")
+        chains.append(a)
+    n_total = sum(a.shape[0] for a in chains)
+    want_spend = bool(simulate_spend and ncol == 5)
+    x_future = np.empty((n_total, N), dtype=np.int64)
+    spend = np.empty((n_total, N)) if want_spend else None
+    # pieces: (device slot, chain array, first draw of the piece within the chain, count, global index of its first draw)
+    pieces = [[] for _ in devices]
+    off = 0
+    for a in chains:
         nd = a.shape[0]
-        xs = np.empty((nd, N), dtype=np.int64)
-        sp = np.empty((nd, N)) if (simulate_spend and ncol == 5) else None
-        cfg = L.ForecastConfig(device=device, ncol=ncol, n_draws_total=nd, n_customers=N, gid_offset=0,
-                               draw_offset=off, T_star=float(T_star), seed=seed_v & 0xFFFFFFFFFFFFFFFF,
-                               simulate_spend=1 if sp is not None else 0, reserved=0, sigma_s=float(sigma_s))
-        L.check(lib.clv_forecast(C.byref(cfg), L.dptr(a), L.dptr(T_cal), xs.ctypes.data_as(L.c_int64_p), L.dptr(sp)))
-        xs_parts.append(xs)
-        sp_parts.append(sp)
+        cuts = [nd * i // len(devices) for i in range(len(devices) + 1)]
+        for slot in range(len(devices)):
+            if cuts[slot + 1] > cuts[slot]:
+                pieces[slot].append((a, cuts[slot], cuts[slot + 1] - cuts[slot], off + cuts[slot]))
         off += nd
-    x_future = xs_parts[0] if len(xs_parts) == 1 else np.vstack(xs_parts)
-    if sp_parts[0] is None:
-        return x_future, None
-    return x_future, (sp_parts[0] if len(sp_parts) == 1 else np.vstack(sp_parts))
+
+    def work(slot):
+        for a, d0, cnt, g0 in pieces[slot]:
+            cfg = L.ForecastConfig(device=int(devices[slot]), ncol=ncol, n_draws_total=cnt, n_customers=N, gid_offset=0,
+                                   draw_offset=g0, T_star=float(T_star), seed=seed_v & 0xFFFFFFFFFFFFFFFF,
+                                   simulate_spend=1 if want_spend else 0, reserved=0, sigma_s=float(sigma_s))
+            L.check(lib.clv_forecast(C.byref(cfg), L.dptr(a[d0:d0 + cnt]), L.dptr(T_cal),
+                                     x_future[g0:g0 + cnt].ctypes.data_as(L.c_int64_p),
+                                     L.dptr(spend[g0:g0 + cnt]) if want_spend else None))
+
+    busy = [i for i in range(len(devices)) if pieces[i]]
+    if len(busy) <= 1:
+        for i in busy:
+            work(i)
+    else:
+        with ThreadPoolExecutor(len(busy)) as ex:
+            list(ex.map(work, busy))
+    return x_future, spend
 
 
-def draw_future_transactions(cbs, draws: Dict[str, Any], T_star: float = 39.0, seed: Optional[int] = None) -> np.ndarray:
+def draw_future_transactions(cbs, draws: Dict[str, Any], T_star: float = 39.0, seed: Optional[int] = None, *,
+                             devices=None) -> np.ndarray:
     """Simulated x* for each (draw, customer): (n_draws_total, N) int64 -- drop-in for bi:506-546."""
-    x, _ = _forecast(cbs["T_cal"].to_numpy(), draws["level_1"], T_star, seed, False, 0.5,
-                     device=_env_devices()[0])
+    x, _ = _forecast(cbs["T_cal"].to_numpy(), draws["level_1"], T_star, seed, False, 0.5, devices=devices or _env_devices())
     return x
 
 
 def draw_future_transactions_rfm_m(cbs, draws: Dict[str, Any], T_star: float = 39.0, *, simulate_spend: bool = True,
-                                   sigma_s: float = 0.50, seed: int | None = None):
+                                   sigma_s: float = 0.50, seed: int | None = None, devices=None):
     """Posterior-predictive x* (and log-normal spend) for the RFM-M model -- drop-in for tri:660-749."""
     x, sp = _forecast(cbs["T_cal"].to_numpy(float), draws["level_1"], T_star, seed, simulate_spend, sigma_s,
-                      device=_env_devices()[0])
+                      devices=devices or _env_devices())
     if not simulate_spend:
         return x
     return x, sp

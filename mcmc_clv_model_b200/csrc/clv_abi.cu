@@ -117,6 +117,7 @@ struct clv_sampler {
   bool p2p = false;
   unsigned long long* peer_mail[P2P_MAX_WORLD] = {nullptr};
   bool use_pdl = true;                   // programmatic dependent launch of the two kernels of a sweep (CLV_NO_PDL=1 disables)
+  int pdl_mode = 1;                      // CLV_PDL_MODE: 1 both kernels release their dependent at once, 2 k_level2 after its wait, 3 k_sweep after its tiles
   unsigned long long init_epoch = 0;     // bumped by every clv_init_state: mailbox flags never repeat
   // statistics computed by clv_init_state(h, NULL)
   clv_init_stats last_stats{};
@@ -440,6 +441,7 @@ SweepArgs base_args(clv_sampler* h) {
   a.rk = round_keys(h->cfg.seed);
   a.store_zt = 0;
   a.error_flag = h->p2p ? h->d_err : nullptr;     // only sharded runs can be told to stop by a peer
+  a.pdl_early = (h->pdl_mode == 3) ? 0 : 1;
   return a;
 }
 
@@ -540,6 +542,7 @@ Level2Args base_l2(clv_sampler* h) {
   l.error_flag = h->d_err;
   l.world = h->p2p ? h->world : 0; l.rank = h->rank; l.n_chains = h->chains;
   l.tag = 1u;
+  l.pdl_early = (h->pdl_mode == 2) ? 0 : 1;
   l.timeout_ns = p2p_timeout_ns();
   for (int r = 0; r < P2P_MAX_WORLD; ++r) l.peer_mail[r] = h->peer_mail[r];
   return l;
@@ -606,6 +609,7 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   h->cfg = *cfg;
   h->D = cfg->model_dim; h->K = cfg->n_cov; h->S = cfg->n_mh_steps; h->chains = cfg->n_chains;
   h->use_pdl = getenv("CLV_NO_PDL") == nullptr;
+  if (const char* e = getenv("CLV_PDL_MODE")) h->pdl_mode = atoi(e);
   h->N = cfg->n_local; h->ncol = h->D == 2 ? 4 : 5; h->P = h->D * h->K + h->D * (h->D + 1) / 2;
   auto bail = [&](int code) { std::string m = h->err; clv_destroy(h); g_last_error = m; return code; };
 #define CKC(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { fail(h, CLV_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2)); return bail(CLV_ERR_CUDA); } } while (0)
@@ -1910,6 +1914,87 @@ int clv_elog2cbs(int device, int64_t n_events, const int64_t* cust, const int32_
     ++m;
   }
   *n_customers = m;
+  return CLV_OK;
+}
+
+// ---- test hook: customer shards of one problem on ONE device, in lockstep ------------------------------------------------
+int clv_debug_lockstep_advance(clv_sampler** shards, int n_shards, int64_t n_sweeps) {
+  if (!shards || n_shards < 2 || n_shards > P2P_MAX_WORLD || n_sweeps < 0) return fail(nullptr, CLV_ERR_ARG, "clv_debug_lockstep_advance: bad argument");
+  clv_sampler* h0 = shards[0];
+  for (int r = 0; r < n_shards; ++r) {
+    clv_sampler* h = shards[r];
+    if (!h || !h->inited) return fail(h0, CLV_ERR_STATE, "lockstep: every shard must be initialised");
+    if (h->cfg.device != h0->cfg.device || h->D != h0->D || h->K != h0->K || h->S != h0->S || h->chains != h0->chains ||
+        h->cfg.seed != h0->cfg.seed || h->cfg.n_global != h0->cfg.n_global || h->sweeps_done != h0->sweeps_done ||
+        h->cfg.rng_mode == CLV_RNG_INJECTED || h->comm || h->p2p)
+      return fail(h0, CLV_ERR_ARG, "lockstep: shards must share device, model, chains, seed, n_global and sweep count, and have no communicator");
+  }
+  CK(h0, cudaSetDevice(h0->cfg.device)); t_alloc_stream = h0->stream; ensure_pool(h0->cfg.device);
+  for (int r = 0; r < n_shards; ++r) CK(h0, cudaStreamSynchronize(shards[r]->stream));
+  const size_t mail_bytes = sizeof(unsigned long long) * 2 * P2P_MAX_WORLD * (size_t)h0->chains * 2 * NSTAT_MAX;
+  std::vector<void*> mail(n_shards, nullptr);
+  Level2Args* d_ranks = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(h0->stream);
+    for (void* m : mail) if (m) cudaFree(m);
+    if (d_ranks) cudaFree(d_ranks);
+    for (int r = 0; r < n_shards; ++r) { shards[r]->p2p = false; shards[r]->world = 1; shards[r]->rank = 0; }
+  };
+#define CKL(call) do { cudaError_t e4 = (call); if (e4 != cudaSuccess) { rc = fail(h0, CLV_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e4)); cleanup(); return rc; } } while (0)
+  for (int r = 0; r < n_shards; ++r) { CKL(cudaMalloc(&mail[r], mail_bytes)); CKL(cudaMemset(mail[r], 0, mail_bytes)); }
+  CKL(cudaMalloc((void**)&d_ranks, sizeof(Level2Args) * n_shards));
+  for (int r = 0; r < n_shards; ++r) {
+    clv_sampler* h = shards[r];
+    h->p2p = true; h->world = n_shards; h->rank = r;
+    for (int q = 0; q < n_shards; ++q) h->peer_mail[q] = (unsigned long long*)mail[q];
+  }
+  std::vector<Level2Args> l2(n_shards);
+  const int mode = h0->cfg.rng_mode;
+  for (int64_t it = 0; it < n_sweeps; ++it) {
+    for (int r = 0; r < n_shards; ++r) {
+      clv_sampler* h = shards[r];
+      l2[r] = base_l2(h);
+      l2[r].sweep = (uint32_t)(h->sweeps_done + 1);
+      l2[r].tag = (uint32_t)(((h0->init_epoch % 255ull) + 1ull) << 24) | (l2[r].sweep & 0xffffffu);
+    }
+    auto do_l2 = [&]() -> cudaError_t {
+      cudaError_t e = cudaMemcpyAsync(d_ranks, l2.data(), sizeof(Level2Args) * n_shards, cudaMemcpyHostToDevice, h0->stream);
+      if (e != cudaSuccess) return e;
+      e = cudaStreamSynchronize(h0->stream);            // l2 (pageable) is rewritten next sweep
+      if (e != cudaSuccess) return e;
+      void* args[] = {&d_ranks};
+      const void* fn = h0->D == 2 ? (const void*)k_level2_ranks<2> : (const void*)k_level2_ranks<3>;
+      return cudaLaunchCooperativeKernel(fn, dim3(h0->chains, n_shards), dim3(32), args, 0, h0->stream);
+    };
+    auto do_sweeps = [&]() -> cudaError_t {
+      for (int r = 0; r < n_shards; ++r) {
+        clv_sampler* h = shards[r];
+        SweepArgs a = base_args(h);
+        a.sweep = (uint32_t)(h->sweeps_done + 1);
+        a.store_zt = (it + 1 == n_sweeps) ? 1 : 0;
+        dim3 grid(h->grid_x, h->chains), block(SWEEP_THREADS);
+        cudaError_t e = (h->D == 2)
+            ? (mode == MODE_STRICT ? launch_kernel(k_sweep<2, MODE_STRICT>, grid, block, h->stats_smem, h0->stream, false, a)
+                                   : launch_kernel(k_sweep<2, MODE_FAST>, grid, block, h->stats_smem, h0->stream, false, a))
+            : (mode == MODE_STRICT ? launch_kernel(k_sweep<3, MODE_STRICT>, grid, block, h->stats_smem, h0->stream, false, a)
+                                   : launch_kernel(k_sweep<3, MODE_FAST>, grid, block, h->stats_smem, h0->stream, false, a));
+        if (e != cudaSuccess) return e;
+        h->launches++;
+      }
+      return cudaSuccess;
+    };
+    if (h0->D == 2) { CKL(do_l2()); CKL(do_sweeps()); }
+    else { CKL(do_sweeps()); CKL(do_l2()); }
+    for (int r = 0; r < n_shards; ++r) shards[r]->sweeps_done++;
+  }
+#undef CKL
+  CK(h0, cudaStreamSynchronize(h0->stream));
+  int flag = 0;
+  for (int r = 0; r < n_shards && !flag; ++r) cudaMemcpy(&flag, shards[r]->d_err, sizeof(int), cudaMemcpyDeviceToHost);
+  cleanup();
+  if (flag == 2) return fail(h0, CLV_ERR_COMM, "lockstep: mailbox all-reduce timed out");
+  if (flag) return fail(h0, CLV_ERR_NUMERIC, "lockstep: level-2 scale matrix not positive definite or non-finite");
   return CLV_OK;
 }
 

@@ -85,15 +85,16 @@ struct SweepArgs {
   PhiloxRoundKeys rk;          // round keys of `seed` (launch constants)
   int store_zt;                // write z/tau state arrays
   const int* error_flag;       // device error flag (2: a peer rank stopped)
+  int pdl_early;               // 1: let the next kernel of the stream become resident at once, 0: once this block's tiles are done
   // injected variates (MODE_INJECT)
   const double *u_z, *e_tau, *u_tau, *t3_l, *t3_m, *u_acc, *n_eta;
 };
 
-// Table exp: 2^(j / EXP_N), j < EXP_N, in shared memory + a polynomial for the remainder.  CLV_EXP_BITS = 6 (default):
-// 64 entries, degree-5 remainder; CLV_EXP_BITS = 8: 256 entries (2 KB per block), degree 4 -- one DFMA less per exp at
-// the same <= 1 ulp (|r| <= ln2/512: r^5/120 < 4e-17).  The 8-bit build is a candidate that has not been timed yet.
+// Table exp: 2^(j / EXP_N), j < EXP_N, in shared memory + a polynomial for the remainder.  CLV_EXP_BITS = 8 (default):
+// 256 entries (2 KB per block), degree-4 remainder (|r| <= ln2/512: r^5/120 < 4e-17, <= 1 ulp); CLV_EXP_BITS = 6: 64
+// entries, degree 5 -- one DFMA more per exp (measured: 8 is 1.2 % faster on the 10 M-customer sweep, profiles/r02_kernel_ab.txt).
 #ifndef CLV_EXP_BITS
-#define CLV_EXP_BITS 6
+#define CLV_EXP_BITS 8
 #endif
 constexpr int EXP_BITS = CLV_EXP_BITS, EXP_N = 1 << EXP_BITS;
 static_assert(EXP_BITS == 6 || EXP_BITS == 8, "CLV_EXP_BITS must be 6 or 8");
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArg
   const int nstat = K * D + D * (D + 1) / 2;
   const ChainParams& cp = a.params[chain];
   // prologue (programmatic dependent launch): nothing here depends on the level-2 kernel that precedes this launch
-  pdl_launch_dependents();
+  if (a.pdl_early) pdl_launch_dependents();
   for (int t = tid; t < EXP_N; t += SWEEP_THREADS) s_tab[t] = c_exptab[t];
   for (int t = tid; t < NSTAT_MAX + 1; t += SWEEP_THREADS) s_acc[t] = 0ull;
   clear_stats(s_priv, nstat);
@@ -461,6 +462,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArg
   const long long ntiles = (mc.N + SWEEP_THREADS - 1) / SWEEP_THREADS;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
     sweep_tile<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, c3);
+  if (!a.pdl_early) pdl_launch_dependents();
   flush_stats(s_priv, s_acc, nstat, sw.keep != 0);
   __syncthreads();
   for (int t = tid; t < nstat; t += SWEEP_THREADS)
@@ -678,6 +680,7 @@ struct Level2Args {
   // customer-sharded runs with peer mailboxes (NVLink/NVSwitch P2P stores): the all-reduce of the statistics is done
   // HERE, inside the level-2 kernel, instead of a separate NCCL call.  world == 0: not used.
   int world, rank, n_chains;
+  int pdl_early;                                  // 1: the next sweep kernel may become resident at once, 0: after pdl_wait
   uint32_t tag;                                   // never 0; differs from the tag of sweep - 2 and of any earlier init
   long long timeout_ns;                           // give up (error flag 2) when a peer's words do not arrive in time
   unsigned long long* peer_mail[P2P_MAX_WORLD];   // rank r's mailbox [2][P2P_MAX_WORLD][chains][2 * NSTAT_MAX] words
@@ -947,17 +950,18 @@ __device__ __forceinline__ bool ll_allreduce_stats(const Level2Args& a, int chai
   return ok;
 }
 
+// One chain's level-2 draw by one warp (the body of k_level2): prologue that needs nothing of the preceding sweep kernel
+// (constants, variates), then the statistics (own accumulators, or the peer-mailbox all-reduce), then the algebra.
 template <int D>
-__global__ void __launch_bounds__(32) k_level2(Level2Args a) {
+__device__ __forceinline__ void level2_chain(const Level2Args& a, int chain, int lane) {
   __shared__ Level2Scratch sc;
   __shared__ Level2Const lc;
   __shared__ Level2Variates lv;
   __shared__ unsigned long long s_tot[NSTAT_MAX];
   const ModelConst& mc = *a.mc;
-  const int chain = blockIdx.x, lane = threadIdx.x;
   constexpr int ntril = D * (D - 1) / 2;
-  // ---- prologue: needs nothing of the sweep that precedes this kernel in the stream --------------------------------
-  pdl_launch_dependents();                   // the next sweep kernel may become resident and run ITS prologue
+  // ---- prologue ---------------------------------------------------------------------------------------------------
+  if (a.pdl_early) pdl_launch_dependents();  // the next sweep kernel may become resident and run ITS prologue
   load_level2_const<D>(mc, lc, lane, 32);
   __syncwarp();
   const int K = lc.K;
@@ -967,6 +971,7 @@ __global__ void __launch_bounds__(32) k_level2(Level2Args a) {
                      a.injected ? a.beta_norm + chain * D * K : nullptr, lane);
   // ---- the statistics of the sweep kernel ------------------------------------------------------------------------------
   pdl_wait();
+  if (!a.pdl_early) pdl_launch_dependents();
   if (*(volatile int*)a.error_flag == 2) return;          // a peer stopped: leave the state as it is
   if (a.world <= 1) {
     for (int t = lane; t < nstat; t += 32) {
@@ -988,6 +993,19 @@ __global__ void __launch_bounds__(32) k_level2(Level2Args a) {
   if (lane == 0 && !sc.ok) *a.error_flag = 1;
   if (a.draw_index >= 0)
     write_level2_row<D>(K, cp, a.level2_draws + ((long long)chain * a.n_draws + a.draw_index) * (D * K + D * (D + 1) / 2), lane);
+}
+
+template <int D>
+__global__ void __launch_bounds__(32) k_level2(Level2Args a) {
+  level2_chain<D>(a, blockIdx.x, threadIdx.x);
+}
+
+// Test hook (clv_debug_lockstep_advance): the level-2 kernels of G ranks as ONE cooperative launch, block (chain, r)
+// playing rank r with rank r's accumulators, mailbox and parameters.  Kernels of separate launches must not wait on
+// each other on one GPU; blocks of a cooperative launch are co-resident, so the mailbox protocol runs unchanged.
+template <int D>
+__global__ void __launch_bounds__(32) k_level2_ranks(const Level2Args* ranks) {
+  level2_chain<D>(ranks[blockIdx.y], blockIdx.x, threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------

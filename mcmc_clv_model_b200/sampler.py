@@ -183,6 +183,13 @@ class Sampler:
         L.check(self.lib.clv_advance_timed(self.h, int(n_sweeps), C.byref(ms)), self.h)
         return ms.value
 
+    @staticmethod
+    def lockstep_advance(shards, n_sweeps):
+        """Test hook (clv_debug_lockstep_advance): advance customer shards that live on ONE device in lockstep, the
+        level-2 all-reduce running the production peer-mailbox protocol with the ranks emulated inside one kernel."""
+        arr = (C.c_void_p * len(shards))(*[s.h for s in shards])
+        L.check(shards[0].lib.clv_debug_lockstep_advance(arr, len(shards), int(n_sweeps)), shards[0].h)
+
     @property
     def sweeps_done(self):
         return int(self.lib.clv_sweeps_done(self.h))

@@ -126,20 +126,34 @@ def test_missing_library_fails_loudly(monkeypatch):
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` (the CPU arm: oracle port on all host cores) prints exactly one JSON line with the
-    contract's keys."""
+    """`bench.py --impl reference` (the CPU arm: the unmodified reference from baseline/_ref when baseline/make_ref.py has
+    made that copy, else the oracle port; all host cores) prints exactly one JSON line with the contract's keys."""
     import json
     import sys
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                       capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--ref-customers-per-proc", "4000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "customer_updates_per_sec" and d["higher_is_better"] is True
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    have_ref = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "bivariate_mcmc.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 1e4 and "workload" in d["config"]
+    if have_ref:
+        assert d["cpu_port"]["kind"] == "port" and d["cpu_port"]["value"] > d["value"] * 0.5     # the port is the faster restatement
+
+
+def test_reference_copy_recipe_is_verbatim():
+    """baseline/make_ref.py copies the reference's sampler modules unmodified (sha256 recorded in the manifest)."""
+    import hashlib
+    ref = "/root/reference/src/models/bivariate/mcmc.py"
+    dst = os.path.join(ROOT, "baseline", "_ref", "bivariate_mcmc.py")
+    if not (os.path.exists(ref) and os.path.exists(dst)):
+        pytest.skip("reference tree or baseline/_ref not present")
+    assert hashlib.sha256(open(ref, "rb").read()).hexdigest() == hashlib.sha256(open(dst, "rb").read()).hexdigest()
 
 
 def test_parallel_host_copy_pool():

@@ -687,3 +687,39 @@ def test_generator_matches_the_reference_generator_moments():
     cbs3, _ = generate_pareto_abe(n, T_vec, T_star, g["beta"], g["gamma"], covars=g["vector_cov"], seed=43, cbs_clock="customer")
     np.testing.assert_allclose(cbs3["t_x"].to_numpy(), t_rel, atol=1e-12)
     np.testing.assert_array_equal(cbs3["T_cal"].to_numpy(), T_vec)
+
+
+@pytest.mark.parametrize("D,rng,G", [(2, "fast", 3), (2, "strict", 2), (3, "fast", 4)])
+def test_customer_shards_in_lockstep_equal_the_unsharded_chain(D, rng, G):
+    """The customer-sharded path on ONE GPU (the driver's test box has one): G shards of one problem -- contiguous
+    1024-aligned customer ranges, Philox counters on global ids, int64 fixed-point level-2 statistics -- advance in
+    lockstep, the per-sweep all-reduce running the production peer-mailbox (LL) protocol with the ranks emulated as the
+    blocks of one cooperative launch.  Every shard must carry exactly the unsharded chain: the property behind
+    "N-GPU == 1-GPU" (tests/test_gpu_multi.py checks the real transports on >= 2 GPUs)."""
+    from mcmc_clv_model_b200.distributed import shard_bounds
+    from mcmc_clv_model_b200.synthetic import C4_BETA, C4_GAMMA, C4_SEED, C4_T_CAL, generate_cbs_arrays
+    N, chains, sweeps = 40_003, 2, 4
+    c = generate_cbs_arrays(N, C4_BETA, C4_GAMMA, T_cal=C4_T_CAL, seed=C4_SEED, with_truth=False)
+    log_s = (0.5 * c["X"][:, 1] + 3.0 + 0.1 * np.cos(np.arange(N))) if D == 3 else None
+    with Sampler(c["x"], c["t_x"], c["T_cal"], c["X"], log_s, model_dim=D, chains=chains, seed=9, rng=rng, sweep_mode="stream") as full:
+        stats = dict(full.init_stats)
+        full.run(sweeps - 1, 1, 1, store_level1=False)          # (clv_run keeps z / tau of its last sweep; clv_advance does not)
+        ref = [full.get_state(ch) for ch in range(chains)]
+    shards = []
+    try:
+        for lo, hi in shard_bounds(N, G):
+            shards.append(Sampler(c["x"][lo:hi], c["t_x"][lo:hi], c["T_cal"][lo:hi], c["X"][lo:hi], None if log_s is None else log_s[lo:hi],
+                                  model_dim=D, chains=chains, seed=9, rng=rng, sweep_mode="stream", n_global=N, gid_offset=lo,
+                                  init_stats=stats))
+        Sampler.lockstep_advance(shards, sweeps)
+        for (lo, hi), s in zip(shard_bounds(N, G), shards):
+            assert s.sweeps_done == sweeps
+            for ch in range(chains):
+                st = s.get_state(ch)
+                np.testing.assert_array_equal(st["beta"], ref[ch]["beta"])
+                np.testing.assert_array_equal(st["Sigma"], ref[ch]["Sigma"])
+                for k in ("log_lambda", "log_mu", "z", "tau") + (("log_eta",) if D == 3 else ()):
+                    np.testing.assert_array_equal(st[k], ref[ch][k][lo:hi], err_msg=f"{k} shard [{lo},{hi}) chain {ch}")
+    finally:
+        for s in shards:
+            s.close()
