@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CLV_ABI_VERSION 1
+#define CLV_ABI_VERSION 2
 #define CLV_MAX_K 16 /* design-matrix columns incl. intercept */
 
 typedef enum {
@@ -49,8 +49,8 @@ typedef enum {
 } clv_compat;
 
 typedef enum {
-  CLV_SWEEP_AUTO = 0,      /* persistent when every 128-customer tile gets its own co-resident block, else stream */
-  CLV_SWEEP_STREAM = 1,    /* two kernels per sweep on a stream (k_sweep, k_level2) */
+  CLV_SWEEP_AUTO = 0,      /* the faster of the two for the problem; currently always stream */
+  CLV_SWEEP_STREAM = 1,    /* two kernels per sweep on a stream (k_sweep, k_level2), chained by programmatic dependent launch */
   CLV_SWEEP_RESERVED = 2,  /* treated as CLV_SWEEP_STREAM */
   CLV_SWEEP_PERSISTENT = 3 /* one cooperative kernel, grid barrier per sweep (single shard only) */
 } clv_sweep_mode;
@@ -249,11 +249,22 @@ int clv_generate(const clv_generate_config* cfg, const double* beta /*K x 2*/, c
 /* Events in any order: cust ids, day numbers (days since any fixed epoch), sales (nullable: 1 per event, :45).  Same
  * (cust, day) events are one transaction with summed sales (:62).  T_cal_day / T_tot_day: last calibration / observation
  * day; unit_days: 7 for weeks.  Outputs (any nullable) have one row per customer with a calibration purchase, ascending
- * cust id; the caller sizes them for the number of distinct customers (<= n_events); *n_customers returns the row count. */
+ * cust id; the caller sizes them for the number of distinct customers (<= n_events); *n_customers returns the row count.
+ * first_sales (nullable): the sales of the customer's first event in INPUT order -- pandas' groupby("cust")["sales"].first()
+ * of src/data_processing/2B_cdnow_elog2cbs_full.py:62-68.  Sorting, grouping, per-customer statistics and the dropping of
+ * customers without a calibration purchase all run on the device; only the kept rows are copied back. */
 int clv_elog2cbs(int device, int64_t n_events, const int64_t* cust, const int32_t* day, const double* sales,
                  int32_t T_cal_day, int32_t T_tot_day, double unit_days, int64_t* n_customers, int64_t* cust_out,
                  int32_t* x, double* t_x, double* litt, double* sales_out, double* sales_x, int32_t* first_day,
-                 double* T_cal, double* T_star, int32_t* x_star, double* sales_star);
+                 double* T_cal, double* T_star, int32_t* x_star, double* sales_star, double* first_sales);
+
+/* ---- covariate standardisation (src/data_processing/2B_cdnow_elog2cbs_full.py:70-101) ----------------------------- */
+/* out[i] = (scale * v[i] - mean) / sd with mean and sd (pandas: ddof = 1) of the scaled column: `first_sales_scaled`
+ * (scale 1e-3, :68-80) and `age_scaled` (scale 1, :84-86).  mean_out / sd_out nullable. */
+int clv_standardize(int device, int64_t n, const double* v, double scale, double* out, double* mean_out, double* sd_out);
+/* out[i] = table[codes[i]] (NaN outside the table): `gender_binary` = gender.map({"M": 1, "F": 0}) (:97-100) on the
+ * category codes. */
+int clv_recode(int device, int64_t n, const int32_t* codes, const double* table, int n_table, double* out);
 
 /* ---- test hook: the level-1 variates of MH step `step` (two Student-t3 proposals, accept uniform) that customers
  * 0..n-1 of chain 0 consume in sweep `sweep`, as the sweep kernel generates them in rng_mode fast / strict. */

@@ -98,7 +98,9 @@ SIGNATURES = {
                                c_double_p, c_int32_p, c_double_p, c_double_p, c_double_p]),
     "clv_elog2cbs": (C.c_int, [C.c_int, C.c_int64, c_int64_p, c_int32_p, c_double_p, C.c_int32, C.c_int32, C.c_double, c_int64_p,
                                c_int64_p, c_int32_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p, c_double_p,
-                               c_double_p, c_int32_p, c_double_p]),
+                               c_double_p, c_int32_p, c_double_p, c_double_p]),
+    "clv_standardize": (C.c_int, [C.c_int, C.c_int64, c_double_p, C.c_double, c_double_p, c_double_p, c_double_p]),
+    "clv_recode": (C.c_int, [C.c_int, C.c_int64, c_int32_p, c_double_p, C.c_int, c_double_p]),
     "clv_debug_host_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "clv_debug_lockstep_advance": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64]),
     "clv_debug_variates": (C.c_int, [C.c_int, C.c_uint64, C.c_uint32, C.c_int32, C.c_int, C.c_int64, c_double_p, c_double_p, c_double_p]),
@@ -119,7 +121,12 @@ def load():
             "or `make -C mcmc_clv_model_b200/csrc`.  mcmc_clv_model_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            if os.environ.get("CLV_B200_LIB"):      # an older build loaded for an A/B comparison (tools/kernel_ab.py)
+                continue
+            raise
         fn.restype = res
         fn.argtypes = args
     _lib = lib

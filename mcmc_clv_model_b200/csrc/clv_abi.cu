@@ -117,7 +117,12 @@ struct clv_sampler {
   bool p2p = false;
   unsigned long long* peer_mail[P2P_MAX_WORLD] = {nullptr};
   bool use_pdl = true;                   // programmatic dependent launch of the two kernels of a sweep (CLV_NO_PDL=1 disables)
-  int pdl_mode = 1;                      // CLV_PDL_MODE: 1 both kernels release their dependent at once, 2 k_level2 after its wait, 3 k_sweep after its tiles
+  // When a kernel lets its successor in the stream become resident (CLV_PDL_MODE overrides): 1 = both kernels at once
+  // (best when the sweep grid fills the GPU: the next sweep's blocks move in as this sweep's blocks retire); 2 = k_sweep at
+  // once, k_level2 only after its own wait (small grids: otherwise the blocks of several future sweeps pile up beside the
+  // running one and slow it down -- measured 33 vs 18 us per sweep at 23 570 customers, profiles/r02_kernel_ab.txt);
+  // 3 = k_sweep after its tiles.  0 = chosen from the grid size at create.
+  int pdl_mode = 0;
   unsigned long long init_epoch = 0;     // bumped by every clv_init_state: mailbox flags never repeat
   // statistics computed by clv_init_state(h, NULL)
   clv_init_stats last_stats{};
@@ -155,8 +160,11 @@ int fail(clv_sampler* h, int code, const char* fmt, ...) {
 // cudaMalloc: CUDA IPC needs it.)
 thread_local cudaStream_t t_alloc_stream = nullptr;   // stream the calling API function allocates / frees on
 
+std::mutex g_once_mutex;            // guards the per-device "done" flags below (handles may live on several host threads)
+
 void ensure_pool(int dev) {
   static bool done[64] = {false};
+  std::lock_guard<std::mutex> lock(g_once_mutex);
   if (dev < 0 || dev >= 64 || done[dev]) return;
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
@@ -657,10 +665,11 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   if (trace) fprintf(stderr, "[clv_create] ... memsets + constants %.2f ms\n", ms_since(t_begin));
   // grid: a few resident waves of 128-thread blocks, grid-stride over customer tiles
   long long ntiles = (h->N + SWEEP_THREADS - 1) / SWEEP_THREADS;
-  long long per_sm_blocks = 32;
+  long long per_sm_blocks = 24;       // 3 waves of 8 resident blocks (measured best at 1.25 M customers per GPU)
   if (const char* env = getenv("CLV_SWEEP_BLOCKS_PER_SM")) per_sm_blocks = std::max(1ll, atoll(env));   // tuning knob
   long long want = ((long long)h->sm_count * per_sm_blocks + h->chains - 1) / h->chains;
   h->grid_x = (int)std::max<long long>(1, std::min(ntiles, want));
+  if (h->pdl_mode == 0) h->pdl_mode = ((long long)h->grid_x * h->chains >= 8ll * h->sm_count) ? 1 : 2;
   h->stats_smem = (size_t)(h->K * h->D + h->D * (h->D + 1) / 2 + 1) * SWEEP_THREADS * sizeof(long long);
   if (h->stats_smem > 48 * 1024) {
     const int bytes = (int)h->stats_smem;
@@ -684,9 +693,13 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   {
     int coop = 0, per_sm = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
-    cudaError_t eo = (h->D == 2)
-        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<2, MODE_FAST>, SWEEP_THREADS, h->stats_smem)
-        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<3, MODE_FAST>, SWEEP_THREADS, h->stats_smem);
+    // occupancy of the instantiation this handle will launch (STRICT may need more registers than FAST)
+    const bool strict = cfg->rng_mode == CLV_RNG_PHILOX_STRICT;
+    cudaError_t eo;
+    if (h->D == 2) eo = strict ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<2, MODE_STRICT>, SWEEP_THREADS, h->stats_smem)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<2, MODE_FAST>, SWEEP_THREADS, h->stats_smem);
+    else eo = strict ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<3, MODE_STRICT>, SWEEP_THREADS, h->stats_smem)
+                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<3, MODE_FAST>, SWEEP_THREADS, h->stats_smem);
     long long maxb = (eo == cudaSuccess && coop) ? (long long)per_sm * h->sm_count : 0;
     if (maxb >= h->chains) {
       h->persist_grid_x = (int)std::min<long long>(ntiles, maxb / h->chains);
@@ -1089,8 +1102,10 @@ namespace {
 
 bool want_persistent(const clv_sampler* h) {
   if (h->comm || h->p2p || h->timing || h->persist_grid_x <= 0 || h->cfg.rng_mode == CLV_RNG_INJECTED) return false;
-  if (h->cfg.sweep_mode == CLV_SWEEP_PERSISTENT) return true;
-  return h->cfg.sweep_mode == CLV_SWEEP_AUTO && h->persist_fits;
+  // AUTO = stream: with programmatic dependent launch the two-kernel path is at least as fast as the cooperative kernel
+  // at every size measured (14.2 vs 16.4 us per sweep at 4 x 2 357 customers, 18.2 vs 20.4 at 2 x 23 570, 213 vs 261 at
+  // 1.25 M; profiles/r02_kernel_ab.txt): the grid barrier costs more than the launch boundary that PDL hides.
+  return h->cfg.sweep_mode == CLV_SWEEP_PERSISTENT;
 }
 
 struct RunCtx {                 // draw bookkeeping of the current clv_run (zeros for clv_advance)
@@ -1098,6 +1113,8 @@ struct RunCtx {                 // draw bookkeeping of the current clv_run (zero
   double* draws = nullptr;
   bool keep_any = false;
 };
+
+int run_stream_segment(clv_sampler* h, const RunCtx& rc, long long n, bool store_zt_last);
 
 // n sweeps fused in one cooperative launch (grid barrier per sweep).
 int launch_persistent(clv_sampler* h, const RunCtx& rc, long long n, bool store_zt_last) {
@@ -1131,7 +1148,15 @@ int launch_persistent(clv_sampler* h, const RunCtx& rc, long long n, bool store_
   const bool strict = h->cfg.rng_mode == CLV_RNG_PHILOX_STRICT;
   if (h->D == 2) fn = strict ? (const void*)k_persistent<2, MODE_STRICT> : (const void*)k_persistent<2, MODE_FAST>;
   else fn = strict ? (const void*)k_persistent<3, MODE_STRICT> : (const void*)k_persistent<3, MODE_FAST>;
-  CK(h, cudaLaunchCooperativeKernel(fn, grid, block, args, h->stats_smem, h->stream));
+  {
+    cudaError_t ec = cudaLaunchCooperativeKernel(fn, grid, block, args, h->stats_smem, h->stream);
+    if (ec == cudaErrorCooperativeLaunchTooLarge) {       // occupancy changed under us: the two-kernel path gives the same chain
+      cudaGetLastError();
+      h->persist_grid_x = 0;
+      return run_stream_segment(h, rc, n, store_zt_last);
+    }
+    CK(h, ec);
+  }
   h->launches++;
   if (h->D == 2)
     CK(h, cudaMemcpyAsync(h->d_acc, h->d_acc3 + (size_t)(last % 3u) * h->chains * NSTAT_MAX, slot_bytes,
@@ -1518,6 +1543,7 @@ static int check_fc(const clv_forecast_config* cfg) {
 
 static int upload_rk() {
   static bool done[64] = {false};
+  std::lock_guard<std::mutex> lock(g_once_mutex);
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && done[dev]) return 0;
@@ -1579,7 +1605,12 @@ static int forecast_host(const clv_forecast_config* cfg, const double* level1, c
     if (d_T) dfree(d_T);
     if (d_eps) dfree(d_eps);
   };
-  for (int b = 0; b < 2; ++b) cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking);
+  st[0] = st[1] = nullptr;
+  for (int b = 0; b < 2; ++b)
+    if (cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking) != cudaSuccess) {
+      if (st[0]) cudaStreamDestroy(st[0]);
+      return fail(nullptr, CLV_ERR_CUDA, "clv_forecast: cannot create a stream");
+    }
 #define CKF(call) do { cudaError_t e3 = (call); if (e3 != cudaSuccess) { rc = fail(nullptr, CLV_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e3)); cleanup(); return rc; } } while (0)
   CKF(dmalloc(&d_T, (size_t)N));
   CKF(cudaMemcpy(d_T, T_cal, (size_t)N * 8, cudaMemcpyHostToDevice));
@@ -1821,99 +1852,143 @@ int clv_generate(const clv_generate_config* cfg, const double* beta, const doubl
 int clv_elog2cbs(int device, int64_t n_events, const int64_t* cust, const int32_t* day, const double* sales,
                  int32_t T_cal_day, int32_t T_tot_day, double unit_days, int64_t* n_customers, int64_t* cust_out,
                  int32_t* x, double* t_x, double* litt, double* sales_out, double* sales_x, int32_t* first_day,
-                 double* T_cal, double* T_star, int32_t* x_star, double* sales_star) {
+                 double* T_cal, double* T_star, int32_t* x_star, double* sales_star, double* first_sales) {
   if (!cust || !day || !n_customers || n_events < 1) return fail(nullptr, CLV_ERR_ARG, "clv_elog2cbs: bad argument");
   if (n_events >= (1ll << 31)) return fail(nullptr, CLV_ERR_ARG, "clv_elog2cbs: at most 2^31 - 1 events per call");
   if (!(unit_days > 0)) return fail(nullptr, CLV_ERR_ARG, "clv_elog2cbs: unit_days must be positive");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, CLV_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
-  CK(nullptr, cudaSetDevice(device)); t_alloc_stream = nullptr; ensure_pool(device);
+  CK(nullptr, cudaSetDevice(device)); ensure_pool(device);
+  cudaStream_t st = nullptr;
+  CK(nullptr, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  t_alloc_stream = st;
   const size_t n = (size_t)n_events;
   std::vector<void*> allocs;
   auto dm = [&](size_t bytes) -> void* { void* p = nullptr; if (pool_malloc(&p, bytes) != cudaSuccess) return nullptr; allocs.push_back(p); return p; };
-  auto cleanup = [&]() { for (void* p : allocs) dfree(p); };
+  auto cleanup = [&]() { for (void* p : allocs) dfree(p); cudaStreamSynchronize(st); cudaStreamDestroy(st); t_alloc_stream = nullptr; };
   long long *k0 = (long long*)dm(n * 8), *k1 = (long long*)dm(n * 8);
-  int *d0 = (int*)dm(n * 4), *d1 = (int*)dm(n * 4), *head = (int*)dm(n * 4), *idx = (int*)dm(n * 4);
+  int *d0 = (int*)dm(n * 4), *d1 = (int*)dm(n * 4), *dtmp = (int*)dm(n * 4), *head = (int*)dm(n * 4), *idx = (int*)dm(n * 4);
   unsigned *p0 = (unsigned*)dm(n * 4), *p1 = (unsigned*)dm(n * 4);
   double *s0 = sales ? (double*)dm(n * 8) : nullptr, *s1 = sales ? (double*)dm(n * 8) : nullptr;
-  if (!k0 || !k1 || !d0 || !d1 || !head || !idx || !p0 || !p1 || (sales && (!s0 || !s1))) { cleanup(); return fail(nullptr, CLV_ERR_CUDA, "clv_elog2cbs: out of device memory"); }
-  cudaError_t e = cudaMemcpy(k0, cust, n * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d0, day, n * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && sales) e = cudaMemcpy(s0, sales, n * 8, cudaMemcpyHostToDevice);
-  // permutation-carrying stable sorts: by day, then by customer  =>  sorted by (cust, day), input order within ties
-  std::vector<unsigned> iota(n);
-  for (size_t i = 0; i < n; ++i) iota[i] = (unsigned)i;
-  if (e == cudaSuccess) e = cudaMemcpy(p0, iota.data(), n * 4, cudaMemcpyHostToDevice);
-  // day may be negative (before the epoch): bias to unsigned order
-  std::vector<unsigned> dkey(n);
-  for (size_t i = 0; i < n; ++i) dkey[i] = (unsigned)day[i] ^ 0x80000000u;
-  unsigned *dk0 = (unsigned*)dm(n * 4), *dk1 = (unsigned*)dm(n * 4);
-  if (!dk0 || !dk1) { cleanup(); return fail(nullptr, CLV_ERR_CUDA, "clv_elog2cbs: out of device memory"); }
-  if (e == cudaSuccess) e = cudaMemcpy(dk0, dkey.data(), n * 4, cudaMemcpyHostToDevice);
+  if (!k0 || !k1 || !d0 || !d1 || !dtmp || !head || !idx || !p0 || !p1 || (sales && (!s0 || !s1))) { cleanup(); return fail(nullptr, CLV_ERR_CUDA, "clv_elog2cbs: out of device memory"); }
+  const int gb = (int)std::min<size_t>((n + 255) / 256, 148 * 32);
+  cudaError_t e = cudaMemcpyAsync(k0, cust, n * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d0, day, n * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && sales) e = cudaMemcpyAsync(s0, sales, n * 8, cudaMemcpyHostToDevice, st);
+  // permutation-carrying stable sorts: by day, then by customer  =>  sorted by (cust, day), input order within ties.
+  // Keys are signed (days before the epoch, negative ids): CUB's radix sort orders signed integers.
+  if (e == cudaSuccess) { k_iota<<<gb, 256, 0, st>>>(p0, (long long)n); e = cudaGetLastError(); }
   size_t tb1 = 0, tb2 = 0, tb3 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tb1, dk0, dk1, p0, p1, (int)n);
+  cub::DeviceRadixSort::SortPairs(nullptr, tb1, d0, dtmp, p0, p1, (int)n);
   cub::DeviceRadixSort::SortPairs(nullptr, tb2, k0, k1, p0, p1, (int)n);
   cub::DeviceScan::ExclusiveSum(nullptr, tb3, head, idx, (int)n);
   void* tmp = dm(std::max(tb1, std::max(tb2, tb3)));
   if (!tmp) { cleanup(); return fail(nullptr, CLV_ERR_CUDA, "clv_elog2cbs: out of device memory"); }
   // pass 1: permutation sorted by day
-  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tb1, dk0, dk1, p0, p1, (int)n);
-  // gather customer keys in that order, pass 2: stable sort by customer (int64 with sign bias through the signed overload)
-  // (gathers are done with thrust-free tiny kernels below)
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tb1, d0, dtmp, p0, p1, (int)n, 0, 32, st);
+  // gather customer keys in that order, pass 2: stable sort by customer
   auto gather = [&](auto* dst, const auto* src, const unsigned* perm) {
     using T = std::remove_pointer_t<decltype(dst)>;
-    k_gather<T><<<(int)std::min<size_t>((n + 255) / 256, 148 * 32), 256>>>(dst, src, perm, (long long)n);
+    k_gather<T><<<gb, 256, 0, st>>>(dst, src, perm, (long long)n);
   };
   if (e == cudaSuccess) { gather(k1, k0, p1); e = cudaGetLastError(); }
-  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tb2, k1, k0, p1, p0, (int)n);   // k0 = sorted cust, p0 = final perm
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tb2, k1, k0, p1, p0, (int)n, 0, 64, st);   // k0 = sorted cust, p0 = final perm
   if (e == cudaSuccess) { gather(d1, d0, p0); if (sales) gather(s1, s0, p0); e = cudaGetLastError(); }
-  const int gb = (int)std::min<size_t>((n + 255) / 256, 148 * 32);
-  if (e == cudaSuccess) { k_cbs_heads<<<gb, 256>>>(k0, (long long)n, head); e = cudaGetLastError(); }
-  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tb3, head, idx, (int)n);
-  int last_head = 0, last_idx = 0;
-  if (e == cudaSuccess) e = cudaMemcpy(&last_head, head + n - 1, 4, cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess) e = cudaMemcpy(&last_idx, idx + n - 1, 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) { k_cbs_heads<<<gb, 256, 0, st>>>(k0, (long long)n, head); e = cudaGetLastError(); }
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tb3, head, idx, (int)n, st);
+  int last[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&last[0], head + n - 1, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&last[1], idx + n - 1, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);          // the number of distinct customers sizes the tables below
   if (e != cudaSuccess) { cleanup(); return fail(nullptr, CLV_ERR_CUDA, "clv_elog2cbs failed: %s", cudaGetErrorString(e)); }
-  const long long nc = (long long)last_idx + last_head;
+  const long long nc = (long long)last[0] + last[1];
   long long* starts = (long long*)dm((size_t)nc * 8);
-  CbsOut o{};
-  o.cust = (long long*)dm(nc * 8); o.x = (int*)dm(nc * 4); o.t_x = (double*)dm(nc * 8); o.litt = (double*)dm(nc * 8);
-  o.sales = (double*)dm(nc * 8); o.sales_x = (double*)dm(nc * 8); o.first_day = (int*)dm(nc * 4); o.T_cal = (double*)dm(nc * 8);
-  o.T_star = (double*)dm(nc * 8); o.x_star = (int*)dm(nc * 4); o.sales_star = (double*)dm(nc * 8); o.keep = (int*)dm(nc * 4);
-  if (!starts || !o.cust || !o.x || !o.t_x || !o.litt || !o.sales || !o.sales_x || !o.first_day || !o.T_cal || !o.T_star || !o.x_star || !o.sales_star || !o.keep) {
-    cleanup(); return fail(nullptr, CLV_ERR_CUDA, "clv_elog2cbs: out of device memory");
-  }
-  k_cbs_starts<<<gb, 256>>>(head, idx, (long long)n, starts);
-  k_cbs_customers<<<(int)std::min<long long>((nc + 255) / 256, 148 * 32), 256>>>(k0, d1, sales ? s1 : nullptr, starts, (long long)n, nc,
-                                                                               T_cal_day, T_tot_day, unit_days, o);
+  int* pos = (int*)dm((size_t)nc * 4);
+  auto table = [&](CbsOut& o) {
+    o.cust = (long long*)dm(nc * 8); o.x = (int*)dm(nc * 4); o.t_x = (double*)dm(nc * 8); o.litt = (double*)dm(nc * 8);
+    o.sales = (double*)dm(nc * 8); o.sales_x = (double*)dm(nc * 8); o.first_day = (int*)dm(nc * 4); o.T_cal = (double*)dm(nc * 8);
+    o.T_star = (double*)dm(nc * 8); o.x_star = (int*)dm(nc * 4); o.sales_star = (double*)dm(nc * 8); o.first_sales = (double*)dm(nc * 8);
+    o.keep = (int*)dm(nc * 4);
+    return o.cust && o.x && o.t_x && o.litt && o.sales && o.sales_x && o.first_day && o.T_cal && o.T_star && o.x_star && o.sales_star &&
+           o.first_sales && o.keep;
+  };
+  CbsOut o{}, c{};
+  size_t tb4 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb4, (int*)nullptr, (int*)nullptr, (int)nc);
+  void* tmp2 = dm(std::max<size_t>(tb4, 8));
+  if (!starts || !pos || !tmp2 || !table(o) || !table(c)) { cleanup(); return fail(nullptr, CLV_ERR_CUDA, "clv_elog2cbs: out of device memory"); }
+  const int gc = (int)std::min<long long>((nc + 255) / 256, 148 * 32);
+  k_cbs_starts<<<gb, 256, 0, st>>>(head, idx, (long long)n, starts);
+  k_cbs_customers<<<gc, 256, 0, st>>>(k0, d1, sales ? s1 : nullptr, p0, sales ? s0 : nullptr, starts, (long long)n, nc, T_cal_day, T_tot_day,
+                                      unit_days, o);
   e = cudaGetLastError();
-  // compact kept customers on the host (the table is small: one row per customer)
-  std::vector<long long> h_cust(nc);
-  std::vector<int> h_x(nc), h_first(nc), h_xs(nc), h_keep(nc);
-  std::vector<double> h_tx(nc), h_litt(nc), h_s(nc), h_sx(nc), h_T(nc), h_Ts(nc), h_ss(nc);
-  auto dl = [&](void* dst, const void* src, size_t bytes) { if (e == cudaSuccess) e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); };
-  dl(h_cust.data(), o.cust, nc * 8); dl(h_x.data(), o.x, nc * 4); dl(h_first.data(), o.first_day, nc * 4); dl(h_xs.data(), o.x_star, nc * 4);
-  dl(h_keep.data(), o.keep, nc * 4); dl(h_tx.data(), o.t_x, nc * 8); dl(h_litt.data(), o.litt, nc * 8); dl(h_s.data(), o.sales, nc * 8);
-  dl(h_sx.data(), o.sales_x, nc * 8); dl(h_T.data(), o.T_cal, nc * 8); dl(h_Ts.data(), o.T_star, nc * 8); dl(h_ss.data(), o.sales_star, nc * 8);
+  // drop customers without a calibration purchase ON THE DEVICE: scan of the keep flags, scatter of the kept rows
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp2, tb4, o.keep, pos, (int)nc, st);
+  if (e == cudaSuccess) { k_cbs_compact<<<gc, 256, 0, st>>>(o, pos, nc, c); e = cudaGetLastError(); }
+  int lastk[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&lastk[0], o.keep + nc - 1, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&lastk[1], pos + nc - 1, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  const long long m = (long long)lastk[0] + lastk[1];
+  auto dl = [&](void* dst, const void* src, size_t bytes) { if (e == cudaSuccess && dst && bytes) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st); };
+  dl(cust_out, c.cust, m * 8); dl(x, c.x, m * 4); dl(first_day, c.first_day, m * 4); dl(x_star, c.x_star, m * 4);
+  dl(t_x, c.t_x, m * 8); dl(litt, c.litt, m * 8); dl(sales_out, c.sales, m * 8); dl(sales_x, c.sales_x, m * 8);
+  dl(T_cal, c.T_cal, m * 8); dl(T_star, c.T_star, m * 8); dl(sales_star, c.sales_star, m * 8); dl(first_sales, c.first_sales, m * 8);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cleanup();
   if (e != cudaSuccess) return fail(nullptr, CLV_ERR_CUDA, "clv_elog2cbs failed: %s", cudaGetErrorString(e));
-  long long m = 0;
-  for (long long c = 0; c < nc; ++c) {
-    if (!h_keep[c]) continue;
-    if (cust_out) cust_out[m] = h_cust[c];
-    if (x) x[m] = h_x[c];
-    if (t_x) t_x[m] = h_tx[c];
-    if (litt) litt[m] = h_litt[c];
-    if (sales_out) sales_out[m] = h_s[c];
-    if (sales_x) sales_x[m] = h_sx[c];
-    if (first_day) first_day[m] = h_first[c];
-    if (T_cal) T_cal[m] = h_T[c];
-    if (T_star) T_star[m] = h_Ts[c];
-    if (x_star) x_star[m] = h_xs[c];
-    if (sales_star) sales_star[m] = h_ss[c];
-    ++m;
-  }
   *n_customers = m;
+  return CLV_OK;
+}
+
+// ---- covariate standardisation (src/data_processing/2B_cdnow_elog2cbs_full.py:70-101) ----------------------------------
+int clv_standardize(int device, int64_t n, const double* v, double scale, double* out, double* mean_out, double* sd_out) {
+  if (!v || !out || n < 2) return fail(nullptr, CLV_ERR_ARG, "clv_standardize: need n >= 2 and non-null arrays");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, CLV_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
+  CK(nullptr, cudaSetDevice(device)); t_alloc_stream = nullptr; ensure_pool(device);
+  double *d_v = nullptr, *d_o = nullptr, *d_part = nullptr, *d_ms = nullptr;
+  cudaError_t e = dmalloc(&d_v, (size_t)n);
+  if (e == cudaSuccess) e = dmalloc(&d_o, (size_t)n);
+  if (e == cudaSuccess) e = dmalloc(&d_part, (size_t)COLSUM_BLOCKS);
+  if (e == cudaSuccess) e = dmalloc(&d_ms, (size_t)2);
+  if (e == cudaSuccess) e = cudaMemcpy(d_v, v, (size_t)n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    // the column is scaled first (first_sales * 1e-3, :68): d_o = v * scale (k_zscore with mean 0, sd 1), then the mean
+    // and pandas' std (ddof = 1) of the scaled values, then the z-scores
+    const double ms01[2] = {0.0, 1.0};
+    e = cudaMemcpy(d_ms, ms01, 16, cudaMemcpyHostToDevice);
+    const int gz = (int)std::min<long long>((n + 255) / 256, 148 * 32);
+    if (e == cudaSuccess) { k_zscore<<<gz, 256>>>(d_v, n, d_ms, d_ms + 1, scale, d_o); e = cudaGetLastError(); }
+    if (e == cudaSuccess) { k_col_sum<<<COLSUM_BLOCKS, COLSUM_THREADS>>>(d_o, n, 0, d_ms, d_part); k_col_fold<<<1, COLSUM_THREADS>>>(d_part, COLSUM_BLOCKS, (double)n, 0, d_ms); }
+    if (e == cudaSuccess) { k_col_sum<<<COLSUM_BLOCKS, COLSUM_THREADS>>>(d_o, n, 1, d_ms, d_part); k_col_fold<<<1, COLSUM_THREADS>>>(d_part, COLSUM_BLOCKS, (double)(n - 1), 1, d_ms + 1); }
+    if (e == cudaSuccess) { k_zscore<<<gz, 256>>>(d_v, n, d_ms, d_ms + 1, scale, d_o); e = cudaGetLastError(); }
+  }
+  double ms[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_o, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(ms, d_ms, 16, cudaMemcpyDeviceToHost);
+  dfree(d_v); dfree(d_o); dfree(d_part); dfree(d_ms);
+  if (e != cudaSuccess) return fail(nullptr, CLV_ERR_CUDA, "clv_standardize failed: %s", cudaGetErrorString(e));
+  if (mean_out) *mean_out = ms[0];
+  if (sd_out) *sd_out = ms[1];
+  return CLV_OK;
+}
+
+int clv_recode(int device, int64_t n, const int32_t* codes, const double* table, int n_table, double* out) {
+  if (!codes || !table || !out || n < 1 || n_table < 1) return fail(nullptr, CLV_ERR_ARG, "clv_recode: bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, CLV_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
+  CK(nullptr, cudaSetDevice(device)); t_alloc_stream = nullptr; ensure_pool(device);
+  int* d_c = nullptr; double *d_t = nullptr, *d_o = nullptr;
+  cudaError_t e = dmalloc(&d_c, (size_t)n);
+  if (e == cudaSuccess) e = dmalloc(&d_t, (size_t)n_table);
+  if (e == cudaSuccess) e = dmalloc(&d_o, (size_t)n);
+  if (e == cudaSuccess) e = cudaMemcpy(d_c, codes, (size_t)n * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_t, table, (size_t)n_table * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) { k_recode<<<(int)std::min<long long>((n + 255) / 256, 148 * 32), 256>>>(d_c, n, d_t, n_table, d_o); e = cudaGetLastError(); }
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_o, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  dfree(d_c); dfree(d_t); dfree(d_o);
+  if (e != cudaSuccess) return fail(nullptr, CLV_ERR_CUDA, "clv_recode failed: %s", cudaGetErrorString(e));
   return CLV_OK;
 }
 

@@ -11,6 +11,18 @@ namespace clv {
 
 constexpr int RK_TABLE = 64;
 __constant__ double c_rk[RK_TABLE + 1];   // c_rk[k] = 1.0 / k
+// Forecast-domain Philox slots (third counter word; one counter -> one variate, ranges disjoint):
+//   0                        the Poisson uniforms of a draw pair
+//   FC_SLOT_PTRS + t         PTRS attempt t < 4096 of a cell with a large mean
+//   FC_SLOT_WEEK + w / 4     weekly-tracking uniforms, week w < 4096
+//   FC_SLOT_WEEK_PTRS + 4096 w + t   PTRS attempts of week w
+//   FC_SLOT_SPEND + j / 2    per-transaction spend normals (j < 2^31), or the single CLT normal (j = 0) for huge counts
+constexpr uint32_t FC_SLOT_PTRS = 0x00010000u, FC_SLOT_WEEK = 0x00020000u, FC_SLOT_WEEK_PTRS = 0x01000000u,
+                   FC_SLOT_SPEND = 0x80000000u;
+// Above this many transactions the total spend of a cell is drawn from the normal limit of the sum of i.i.d. log-normals
+// (mean x m1, variance x v): bounded work per cell whatever the Poisson draw (a PTRS overflow sentinel must never
+// become a loop count).
+constexpr long long SPEND_EXACT_MAX = 4096;
 constexpr int RKF_TABLE = 1032;
 __constant__ float c_rkf[RKF_TABLE];      // c_rkf[k] = 1.0f / k (fp32 screen of the Poisson inversion)
 
@@ -64,8 +76,8 @@ __device__ __forceinline__ long long poisson_inversion_screened(float mf, float 
 
 // Large means (production path only): Hoermann's transformed rejection "PTRS" (the algorithm NumPy uses for lam >= 10),
 // exact, ~1.2 attempts whatever the mean -- a customer with lambda * T_star in the hundreds must not cost hundreds of
-// dependent fp64 iterations per draw.  Attempt t takes its two uniforms from Philox block (gid, draw, 64 + t).
-__device__ __noinline__ long long poisson_ptrs(double lam, uint32_t gid, uint32_t gdraw, PhiloxKey key, uint32_t slot0 = 64u) {
+// dependent fp64 iterations per draw.  Attempt t takes its two uniforms from Philox block (gid, draw, FC_SLOT_PTRS + t).
+__device__ __noinline__ long long poisson_ptrs(double lam, uint32_t gid, uint32_t gdraw, PhiloxKey key, uint32_t slot0 = FC_SLOT_PTRS) {
   const double slam = sqrt(lam), loglam = log(lam);
   const double b = 0.931 + 2.53 * slam;
   const double a = -0.059 + 0.02483 * b;
@@ -191,15 +203,23 @@ __global__ void __launch_bounds__(256) k_forecast(ForecastArgs a) {
         if (spend) {
           // tri:730-737: sum of x* log-normal transactions, log-mean = eta column as stored (Q7)
           double tot = 0.0;
-          for (long long j = 0; j < xs; ++j) {
-            double n;
-            if (INJECT) n = a.eps[a.eps_offset[cell] + j];
-            else {
-              double nc, ns;
-              normal_pair_u53(philox4x32_10(gid, (uint32_t)gdraw, 1u + (uint32_t)(j >> 1), DOM_FORECAST, key), &nc, &ns);
-              n = (j & 1) ? ns : nc;
+          if (!INJECT && xs > SPEND_EXACT_MAX) {
+            // sum of xs i.i.d. LogNormal(eta, sigma): normal limit (relative error of the law ~ xs^-1/2 * skewness < 3 %)
+            const double s2 = a.sigma_s * a.sigma_s, m1 = exp(eta + 0.5 * s2);
+            double nc, ns;
+            normal_pair_u53(philox4x32_10(gid, (uint32_t)gdraw, FC_SLOT_SPEND, DOM_FORECAST, key), &nc, &ns);
+            tot = fmax(0.0, (double)xs * m1 + sqrt((double)xs * (exp(s2) - 1.0)) * m1 * nc);
+          } else {
+            for (long long j = 0; j < xs; ++j) {
+              double n;
+              if (INJECT) n = a.eps[a.eps_offset[cell] + j];
+              else {
+                double nc, ns;
+                normal_pair_u53(philox4x32_10(gid, (uint32_t)gdraw, FC_SLOT_SPEND + (uint32_t)(j >> 1), DOM_FORECAST, key), &nc, &ns);
+                n = (j & 1) ? ns : nc;
+              }
+              tot += exp(eta + a.sigma_s * n);
             }
-            tot += exp(eta + a.sigma_s * n);
           }
           a.spend_out[cell] = tot;
         }
@@ -208,25 +228,103 @@ __global__ void __launch_bounds__(256) k_forecast(ForecastArgs a) {
   }
 }
 
-// Fused reductions over the draws still resident in HBM (draw_offset == 0): per customer sum of x* and of z
-// (P(alive) = mean z, analysis_bi_helpers.py:98), x* optionally materialised (WRITE_X).  blockIdx.y splits the draw
-// pairs; partial sums are integers, so the atomicAdd order does not matter.  6 resident blocks per SM: the kernel is
-// latency bound and occupancy beats register comfort.
+// ---- fused reductions over the draws still resident in HBM -----------------------------------------------------------
+// Quick path of a cell: the chop-down over the first FC_QUICK_TERMS CDF values, fully unrolled and branch-free (the
+// reciprocals are immediates), from the fp32 images of the mean and the uniform.  Returns k when the uniform falls
+// below CDF(k) for some k < FC_QUICK_TERMS AND is further than the guard band from both neighbouring CDF values (then
+// k equals the fp64 inversion, see poisson_inversion_screened); -1 otherwise: the cell is DEFERRED.
+constexpr int FC_QUICK_TERMS = 8;
+__device__ __forceinline__ int poisson_quick(float mf, float uf) {
+  float p = ex2_ftz(-1.4426950408889634f * mf), cdf = p, prev = -1.0f;
+  int k = 0;
+#pragma unroll
+  for (int j = 1; j <= FC_QUICK_TERMS; ++j) {
+    const bool gt = uf > cdf;
+    prev = gt ? cdf : prev;
+    k += gt ? 1 : 0;
+    p = (p * mf) * (1.0f / (float)j);
+    cdf = gt ? cdf + p : cdf;
+  }
+  const float tol = 2e-6f * (8.0f + mf);
+  const bool ok = !(uf > cdf) && uf < cdf - tol && uf > prev + tol;
+  return ok ? k : -1;
+}
+
+// Per customer sum of x* and of z (P(alive) = mean z, analysis_bi_helpers.py:98) over the draws resident in HBM
+// (draw_offset == 0), x* optionally materialised (WRITE_X).  blockIdx.y splits the draw pairs; partial sums are
+// integers, so the atomicAdd order does not matter.
+//
+// The kernel is bound by instruction issue before it is bound by HBM (profiles/r01_forecast_ncu_summary.md: 77 % of
+// the issue slots at 17 of 32 lanes active -- the lanes of a warp wait for the one cell with a large count).  So a
+// cell gets only the unrolled quick path in lockstep; the few that need more (x* >= 8, the tie zone, means beyond the
+// fp32 screen, PTRS) are DEFERRED to a per-warp queue in shared memory and worked off 32 at a time by the whole
+// warp -- full lanes for the divergent work.  Deferred results return to the owner lane through a shared array.
+constexpr int FC_WARPS = 8, FC_QCAP = 96;
+struct FcDeferred { uint32_t gdraw, owner, ua, ub; };
+
+// one deferred cell on its own lane: the full path (screened inversion of any length, exact fp64 re-decision, PTRS).
+// Out of line: the hot loop keeps its registers.
 template <int NCOL, bool WRITE_X>
-__global__ void __launch_bounds__(256, 6) k_forecast_reduce(ForecastArgs a, double* sum_x, double* sum_z) {
+__device__ __noinline__ long long fc_deferred_cell(const ForecastArgs& a, FcDeferred e, long long ci, float T_star_f, PhiloxKey key) {
+  const double* row = a.level1 + ((long long)e.gdraw * a.N + ci) * NCOL;
+  const double Tc = a.T_cal[ci];
+  float lamf, dtf;
+  bool al;
+  load_row_f32<NCOL>(row, Tc, lamf, dtf, al);
+  const long long x = forecast_cell(row, lamf, dtf, al, Tc, a.T_star, T_star_f, e.ua, e.ub, (uint32_t)(a.gid_offset + ci), e.gdraw, key);
+  if (WRITE_X) __stcs(a.x_out + (long long)e.gdraw * a.N + ci, x);
+  return x;
+}
+
+#ifndef CLV_FC_MINBLOCKS
+#define CLV_FC_MINBLOCKS 6
+#endif
+template <int NCOL, bool WRITE_X>
+__global__ void __launch_bounds__(256, CLV_FC_MINBLOCKS) k_forecast_reduce(ForecastArgs a, double* sum_x, double* sum_z) {
+  __shared__ FcDeferred s_q[FC_WARPS][FC_QCAP];
+  __shared__ unsigned long long s_dx[FC_WARPS][32];
   const PhiloxKey key = seed_key(a.seed);
   const float T_star_f = (float)a.T_star;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int npairs = (int)((a.n_draws + 1) >> 1);
   const int per = (npairs + gridDim.y - 1) / gridDim.y;
   const int pa = blockIdx.y * per, pb = min(npairs, pa + per);
   const long long stride = a.N * NCOL;                 // doubles between consecutive draws of one customer
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.N;
-       i += (long long)gridDim.x * blockDim.x) {
-    const double T = a.T_cal[i];
-    const uint32_t gid = (uint32_t)(a.gid_offset + i);
+  FcDeferred* q = s_q[warp];
+  const long long nwt = (a.N + 31) / 32;               // warp tiles of 32 consecutive customers
+  for (long long wt = (long long)blockIdx.x * FC_WARPS + warp; wt < nwt; wt += (long long)gridDim.x * FC_WARPS) {
+    const long long i = wt * 32 + lane;
+    const bool valid = i < a.N;
+    const long long ic = valid ? i : a.N - 1;          // out-of-range lanes shadow the last customer (results dropped)
+    const double T = a.T_cal[ic];
+    const uint32_t gid = (uint32_t)(a.gid_offset + ic);
     long long sx = 0;
-    int sz = 0;
-    const double* row = a.level1 + (2ll * pa * a.N + i) * NCOL;
+    int sz = 0, qn = 0;                                // qn: queue length (warp uniform)
+    s_dx[warp][lane] = 0ull;
+    __syncwarp();
+    // the warp works off 32 deferred cells: one cell per lane, the full (screened, then exact / PTRS) path
+    auto drain = [&](int count) {
+      if (lane < count) {
+        const FcDeferred e = q[qn - count + lane];
+        const long long x = fc_deferred_cell<NCOL, WRITE_X>(a, e, wt * 32 + e.owner, T_star_f, key);
+        if (x) atomicAdd(&s_dx[warp][e.owner], (unsigned long long)x);
+      }
+      __syncwarp();
+      qn -= count;
+    };
+    auto cell = [&](float lamf, float dtf, bool alive, uint32_t ua, uint32_t ub, uint32_t gdraw, bool present) {
+      const float hf = alive ? T_star_f : fminf(fmaxf(dtf, 0.0f), T_star_f);
+      const float mf = lamf * hf;
+      int k = (mf < 24.0f) ? poisson_quick(mf, u24f(ua)) : -1;        // beyond ~24 the first 8 terms almost never decide
+      const bool defer = present && valid && k < 0;
+      if (!present || !valid) k = 0;
+      const unsigned m = __ballot_sync(0xffffffffu, defer);
+      if (defer) q[qn + __popc(m & ((1u << lane) - 1u))] = FcDeferred{gdraw, (uint32_t)lane, ua, ub};
+      qn += __popc(m);
+      if (k > 0) sx += k;
+      if (WRITE_X && present && valid && k >= 0) __stcs(a.x_out + (long long)gdraw * a.N + i, (long long)k);
+    };
+    const double* row = a.level1 + (2ll * pa * a.N + ic) * NCOL;
     for (int gp = pa; gp < pb; ++gp, row += 2 * stride) {
       const bool v1 = 2ll * gp + 1 < a.n_draws;        // only the very last pair can be half empty
       float lam0, dt0, lam1 = 0.0f, dt1 = 0.0f;
@@ -234,24 +332,24 @@ __global__ void __launch_bounds__(256, 6) k_forecast_reduce(ForecastArgs a, doub
       load_row_f32<NCOL>(row, T, lam0, dt0, al0);        // both rows in flight before the arithmetic starts
       if (v1) load_row_f32<NCOL>(row + stride, T, lam1, dt1, al1);
       const uint4 r = philox4x32_10_rk(gid, (uint32_t)gp, 0u, DOM_FORECAST, a.rk);
-      const long long x0 = forecast_cell(row, lam0, dt0, al0, T, a.T_star, T_star_f, r.x, r.y, gid, 2u * gp, key);
-      sx += x0;
-      sz += al0 ? 1 : 0;
-      if (WRITE_X) __stcs(a.x_out + (2ll * gp) * a.N + i, x0);
-      if (v1) {
-        const long long x1 = forecast_cell(row + stride, lam1, dt1, al1, T, a.T_star, T_star_f, r.z, r.w, gid, 2u * gp + 1u, key);
-        sx += x1;
-        sz += al1 ? 1 : 0;
-        if (WRITE_X) __stcs(a.x_out + (2ll * gp + 1) * a.N + i, x1);
+      sz += (al0 ? 1 : 0) + (al1 ? 1 : 0);
+      cell(lam0, dt0, al0, r.x, r.y, 2u * (uint32_t)gp, true);
+      cell(lam1, dt1, al1, r.z, r.w, 2u * (uint32_t)gp + 1u, v1);
+      __syncwarp();
+      while (qn >= 32) drain(32);
+    }
+    if (qn > 0) drain(qn);
+    sx += (long long)s_dx[warp][lane];
+    if (valid) {
+      if (gridDim.y == 1) {
+        sum_x[i] = (double)sx;
+        sum_z[i] = (double)sz;
+      } else {
+        atomicAdd(&sum_x[i], (double)sx);
+        atomicAdd(&sum_z[i], (double)sz);
       }
     }
-    if (gridDim.y == 1) {
-      sum_x[i] = (double)sx;
-      sum_z[i] = (double)sz;
-    } else {
-      atomicAdd(&sum_x[i], (double)sx);
-      atomicAdd(&sum_z[i], (double)sz);
-    }
+    __syncwarp();
   }
 }
 
@@ -342,7 +440,7 @@ __global__ void __launch_bounds__(256) k_posterior_summary(const double* level1,
 
 // Weekly tracking simulation (Figure 2; bivariate/analysis_abe.py:446-464): for every resident draw and every week t,
 // sum over customers of Poisson(lambda_i) while birth_i < t <= birth_i + tau_i.  One thread per (customer, draw);
-// uniforms: Philox (gid, draw, 256 + w/4, DOM_FORECAST), word w%4, 32-bit; totals are integers => order independent.
+// uniforms: Philox (gid, draw, FC_SLOT_WEEK + w/4, DOM_FORECAST), word w%4, 32-bit; totals are integers => order independent.
 template <int NCOL>
 __global__ void __launch_bounds__(256) k_weekly_tracking(const double* level1, long long n_tot, long long N, long long gid_offset,
                                                          const double* birth, const double* times, int n_weeks, uint64_t seed,
@@ -363,10 +461,10 @@ __global__ void __launch_bounds__(256) k_weekly_tracking(const double* level1, l
       for (int w = 0; w < n_weeks; ++w) {
         const double t = times[w];
         if (!(t > b0 && t <= b1)) continue;
-        if ((w >> 2) != have) { have = w >> 2; r = philox4x32_10(gid, (uint32_t)d, 256u + (uint32_t)have, DOM_FORECAST, key); }
+        if ((w >> 2) != have) { have = w >> 2; r = philox4x32_10(gid, (uint32_t)d, FC_SLOT_WEEK + (uint32_t)have, DOM_FORECAST, key); }
         const uint32_t word = (w & 3) == 0 ? r.x : (w & 3) == 1 ? r.y : (w & 3) == 2 ? r.z : r.w;
         long long inc;
-        if (lam >= PTRS_MIN_MEAN) inc = poisson_ptrs(lam, gid, (uint32_t)d, key, 65536u + 64u * (uint32_t)w);
+        if (lam >= PTRS_MIN_MEAN) inc = poisson_ptrs(lam, gid, (uint32_t)d, key, FC_SLOT_WEEK_PTRS + 4096u * (uint32_t)w);
         else inc = poisson_inversion_screened(lamf, u24f(word), [&]() { return poisson_inversion(lam, u32d(word)); });
         if (inc) atomicAdd(&s_week[w], (unsigned long long)inc);
       }

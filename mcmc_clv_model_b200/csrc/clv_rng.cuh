@@ -79,8 +79,9 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
 __device__ __forceinline__ double u32d(uint32_t a) { return ((double)a + 0.5) * 0x1.0p-32; }
 // fp32 image of u32d (24 significant bits), only used to screen MH decisions
 __device__ __forceinline__ float u32f(uint32_t a) { return fmaf((float)a, 0x1.0p-32f, 0x1.0p-33f); }
-// (k + 0.5) 2^-24, k = top 24 bits: exact in fp32.  Converting the whole word with round-toward-zero keeps exactly the
-// top 24 bits ((a >> 8) << 8), so the shift is folded into the conversion: one I2F.RZ + one FFMA.
+// (k + 0.5) 2^-24, k = top 24 bits: exact in fp32.  Converting the whole word with round-toward-zero keeps its top 24
+// SIGNIFICANT bits -- exactly (a >> 8) << 8 for words >= 2^24, and up to 8 further low bits for the 2^-8 of the words
+// below that (a difference < 2^-32 in the uniform) -- so the shift is folded into the conversion: one I2F.RZ + one FFMA.
 __device__ __forceinline__ float u24f(uint32_t a) { return fmaf(__uint2float_rz(a), 0x1.0p-32f, 0x1.0p-25f); }
 
 // the same uniform in fp64 (STRICT transforms)
@@ -88,8 +89,9 @@ __device__ __forceinline__ double u24d(uint32_t a) { return ((double)(a >> 8) + 
 
 // ---- word layout of the Metropolis steps (sampler domain) ----------------------------------------------------------
 // A step consumes ONE Philox block (slot 1 + step): words (x, y) = (V, angle) for the log-lambda proposal, (z, w) for
-// log mu; each transform uses the TOP 24 bits of its word.  The accept uniform is assembled from the LOW bytes of the
-// four words (bits the transforms never see).  Slot 0 is z/tau, slot 1+2S the eta normal (tri).
+// log mu; each transform uses the TOP 24 bits of its word (STRICT: exactly a >> 8; FAST: the top 24 significant bits,
+// which for a word below 2^24 -- one in 256 -- reach into the low byte and move the variate by < 2^-32).  The accept
+// uniform is assembled from the LOW bytes of the four words.  Slot 0 is z/tau, slot 1+2S the eta normal (tri).
 __device__ __forceinline__ uint32_t low_bytes(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
   // three PRMT: byte 0 of w0..w3 -> bytes 0..3
   return __byte_perm(__byte_perm(w0, w1, 0x0040), __byte_perm(w2, w3, 0x0040), 0x5410);

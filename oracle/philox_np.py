@@ -191,12 +191,14 @@ def forecast_uniform(seed, gids, draw):
 
 
 PTRS_MIN_MEAN = 60.0
+# forecast-domain slot ranges (clv_forecast.cuh): one counter -> one variate, ranges disjoint
+FC_SLOT_PTRS, FC_SLOT_WEEK, FC_SLOT_WEEK_PTRS, FC_SLOT_SPEND = 0x00010000, 0x00020000, 0x01000000, 0x80000000
 
 
 def forecast_poisson_ptrs(seed, gid, draw, lam):
     """Device contract for means >= PTRS_MIN_MEAN: Hoermann's PTRS (the algorithm NumPy's Generator.poisson uses for
     lam >= 10; numpy/random/src/distributions/distributions.c, third-party, not in the reference tree); attempt t draws
-    its two uniforms from Philox block (gid, draw, 64 + t, DOM_FORECAST)."""
+    its two uniforms from Philox block (gid, draw, FC_SLOT_PTRS + t, DOM_FORECAST)."""
     from math import lgamma, log, sqrt, floor, fabs
     k0, k1 = chain_key(seed, 0)
     slam, loglam = sqrt(lam), log(lam)
@@ -206,7 +208,7 @@ def forecast_poisson_ptrs(seed, gid, draw, lam):
     vr = 0.9277 - 3.6224 / (b - 2.0)
     t = 0
     while True:
-        r = philox4x32_10(np.asarray([gid], dtype=np.uint64), draw, 64 + t, DOM_FORECAST, k0, k1)
+        r = philox4x32_10(np.asarray([gid], dtype=np.uint64), draw, FC_SLOT_PTRS + t, DOM_FORECAST, k0, k1)
         t += 1
         U = float(u53(r[0], r[1])[0]) - 0.5
         V = float(u53(r[2], r[3])[0])
@@ -223,13 +225,13 @@ def forecast_poisson_ptrs(seed, gid, draw, lam):
 def forecast_spend_normal(seed, gid, draw, j):
     """j-th per-transaction normal of cell (draw, gid)."""
     k0, k1 = chain_key(seed, 0)
-    r = philox4x32_10(np.asarray([gid], dtype=np.uint64), draw, 1 + j // 2, DOM_FORECAST, k0, k1)
+    r = philox4x32_10(np.asarray([gid], dtype=np.uint64), draw, FC_SLOT_SPEND + j // 2, DOM_FORECAST, k0, k1)
     c, s = normal_pair_u53(r[0], r[1], r[2], r[3])
     return float(c[0] if j % 2 == 0 else s[0])
 
 
 def weekly_uniform(seed, gids, draw, w):
-    """Uniform of week index w for (customer, global draw): block (gid, draw, 256 + w//4), word w%4, 32 bits."""
+    """Uniform of week index w for (customer, global draw): block (gid, draw, FC_SLOT_WEEK + w//4), word w%4, 32 bits."""
     k0, k1 = chain_key(seed, 0)
-    r = philox4x32_10(np.asarray(gids, dtype=np.uint64), draw, 256 + w // 4, DOM_FORECAST, k0, k1)
+    r = philox4x32_10(np.asarray(gids, dtype=np.uint64), draw, FC_SLOT_WEEK + w // 4, DOM_FORECAST, k0, k1)
     return u32(r[w % 4])

@@ -297,7 +297,27 @@ def make_cbs_golden():
                             cbs_first=((cbs["first"] - pd.Timestamp("1970-01-01")) // pd.Timedelta(days=1)).to_numpy().astype(np.int32))
 
 
+
+
+def make_covariate_golden():
+    """Raw customer covariates (data/raw/cdnow_fullCovar.csv) and the standardised columns the reference's data-processing
+    script derives from them (src/data_processing/2B_cdnow_elog2cbs_full.py:62-105), as committed in
+    data/processed/cdnow_fullCBS.csv:  python tests/golden/make_golden.py covar"""
+    cov = pd.read_csv(f"{REF}/data/raw/cdnow_fullCovar.csv")
+    cbs = pd.read_csv(f"{REF}/data/processed/cdnow_fullCBS.csv")
+    m = cbs[["cust"]].merge(cov, on="cust", how="left")
+    assert (m["cust"].to_numpy() == cbs["cust"].to_numpy()).all()
+    np.savez_compressed(f"{HERE}/covar_full.npz", cust=cbs["cust"].to_numpy().astype(np.int64),
+                        age=m["age"].to_numpy(float), gender_is_M=(m["gender"] == "M").to_numpy().astype(np.int8),
+                        gender_is_F=(m["gender"] == "F").to_numpy().astype(np.int8),
+                        first_sales_scaled=cbs["first_sales_scaled"].to_numpy(float), age_scaled=cbs["age_scaled"].to_numpy(float),
+                        gender_binary=cbs["gender_binary"].to_numpy(float))
+
+
 if __name__ == "__main__":
-    if "cbs" not in sys.argv[1:]:
-        main()
-    make_cbs_golden()
+    if "covar" in sys.argv[1:]:
+        make_covariate_golden()
+    else:
+        if "cbs" not in sys.argv[1:]:
+            main()
+        make_cbs_golden()

@@ -32,7 +32,7 @@ def test_header_symbols_exported():
 def test_ctypes_mirror_is_complete():
     assert _declared() == set(L.SIGNATURES), (_declared() ^ set(L.SIGNATURES))
     lib = L.load()
-    assert lib.clv_abi_version() == 1
+    assert lib.clv_abi_version() == 2
 
 
 def test_struct_layouts():

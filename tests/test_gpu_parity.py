@@ -723,3 +723,68 @@ def test_customer_shards_in_lockstep_equal_the_unsharded_chain(D, rng, G):
     finally:
         for s in shards:
             s.close()
+
+
+def test_covariate_standardisation_vs_the_committed_full_cbs():
+    """SURVEY 8f row f-3, second half: first_sales_scaled / age_scaled / gender_binary of
+    src/data_processing/2B_cdnow_elog2cbs_full.py:62-105 computed on the device from the raw event log and customer table,
+    against the columns committed in data/processed/cdnow_fullCBS.csv (tests/golden/covar_full.npz)."""
+    import pandas as pd
+    from mcmc_clv_model_b200.cbs import add_covariates, elog2cbs, standardize
+    g, c = load_golden("elog_full.npz"), load_golden("covar_full.npz")
+    rng = np.random.default_rng(1)
+    elog = pd.DataFrame({"cust": g["cust"], "date": pd.Timestamp("1970-01-01") + pd.to_timedelta(g["day"].astype(np.int64), unit="D"),
+                         "sales": g["sales"]})
+    cbs = elog2cbs(elog, units="W", T_cal="1997-09-30", T_tot="1998-06-30", with_first_sales=True)
+    # groupby.first semantics: the first row of each customer in INPUT order
+    np.testing.assert_array_equal(cbs["first_sales"].to_numpy(), elog.groupby("cust")["sales"].first().to_numpy())
+    customers = pd.DataFrame({"cust": c["cust"], "age": c["age"], "gender": np.where(c["gender_is_M"] == 1, "M", "F"),
+                              "zone": "z", "state": "s", "age_category": "a"}).sample(frac=1.0, random_state=3)      # any row order
+    full = add_covariates(cbs, elog, customers)
+    assert not {"gender", "zone", "state", "age_category", "first_sales"} & set(full.columns)
+    np.testing.assert_array_equal(full["cust"].to_numpy(), c["cust"])
+    np.testing.assert_allclose(full["first_sales_scaled"].to_numpy(), c["first_sales_scaled"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(full["age_scaled"].to_numpy(), c["age_scaled"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_array_equal(full["gender_binary"].to_numpy(), c["gender_binary"])
+    # deterministic, and equal to pandas on a hostile column (large offset, shuffled)
+    v = rng.normal(1e6, 3.0, 200_001)
+    z1, m1, s1 = standardize(v)
+    z2, m2, s2 = standardize(v)
+    assert np.array_equal(z1, z2) and (m1, s1) == (m2, s2)
+    ser = pd.Series(v)
+    assert abs(m1 - ser.mean()) < 1e-9 and abs(s1 / ser.std() - 1) < 1e-12
+    np.testing.assert_allclose(z1, ((ser - ser.mean()) / ser.std()).to_numpy(), atol=1e-9)
+    # first row in input order is not the earliest date once the log is shuffled
+    perm = rng.permutation(len(elog))
+    sh = elog.iloc[perm].reset_index(drop=True)
+    cb2 = elog2cbs(sh, units="W", T_cal="1997-09-30", T_tot="1998-06-30", with_first_sales=True)
+    np.testing.assert_array_equal(cb2["first_sales"].to_numpy(), sh.groupby("cust")["sales"].first().to_numpy())
+
+
+def test_forecast_spend_philox_vs_restated_contract():
+    """Production trivariate forecast with spend (tri:722-741, Q7): per-transaction normals from the forecast domain's
+    spend slots (disjoint from the Poisson / PTRS / weekly-tracking slots) against the NumPy restatement, and the bounded
+    branch for huge counts (normal limit of the sum of log-normals) against its law."""
+    from oracle import philox_np as px
+    from mcmc_clv_model_b200.api import _forecast
+    g = load_golden("fc_tri.npz")
+    l1 = g["level_1"][:2].copy()
+    nd, N, _ = l1.shape
+    l1[:, :, 4] = np.clip(l1[:, :, 4], 0.5, 4.0)                 # eta is used as the log-mean (Q7): keep exp() tame
+    l1[:, 3, 0], l1[:, 3, 3] = 200.0 / 39.0, 1.0                 # one customer through the PTRS branch, > 126 transactions:
+    x, sp = _forecast(g["T_cal"], [l1], 39.0, 31, True, 0.5)     # its spend normals used to share slots with the PTRS attempts
+    ref = np.zeros((nd, N))
+    for d in range(nd):
+        for i in range(N):
+            ref[d, i] = sum(np.exp(l1[d, i, 4] + 0.5 * px.forecast_spend_normal(31, i, d, j)) for j in range(int(x[d, i])))
+    assert x[:, 3].min() > 126
+    np.testing.assert_allclose(sp, ref, rtol=1e-12, atol=1e-12)
+    # huge counts: bounded work, right mean and spread
+    M = 4000
+    big = np.zeros((2, M, 5))
+    big[:, :, 0], big[:, :, 3], big[:, :, 4] = 20000.0 / 39.0, 1.0, 1.0
+    xb, sb = _forecast(np.full(M, 30.0), [big], 39.0, 7, True, 0.5)
+    assert xb.min() > 4096
+    m1, v1 = np.exp(1.0 + 0.125), (np.exp(0.25) - 1.0) * np.exp(2.0 + 0.25)
+    zs = (sb - xb * m1) / np.sqrt(xb * v1)
+    assert abs(zs.mean()) < 5 / np.sqrt(zs.size) and abs(zs.std() - 1) < 0.05

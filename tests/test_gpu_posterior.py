@@ -1,89 +1,123 @@
-"""Statistical parity with the reference chains (re-measured from the unmodified reference):
-posterior means of beta, Gamma, E[lambda], P(alive) within 3 Monte-Carlo standard errors (north_star)."""
+"""Statistical parity with the reference chains (BASELINE.md §2 / tests/golden/post_*.npz, all produced by the
+unmodified reference): posterior means AND 2.5 / 50 / 97.5 % quantiles of every level-2 column (beta, Gamma), E[lambda],
+E[mu], P(alive), log-likelihood -- within 3 Monte-Carlo standard errors (BASELINE.json north_star), no exceptions.
+
+Our side runs 64 chains, so its own Monte-Carlo error is small next to the reference's 4 chains; the standard error of
+a pooled mean is the larger of the autocorrelation-based (Geyer) estimate and the between-chain one (these chains mix
+slowly: the within-chain estimate alone understates the error).  Quantiles: the asymptotic standard error of a
+p-quantile is sqrt(p(1-p)) / f(q) in units of sd / sqrt(ESS), i.e. 1.25 (median) and 2.7 (2.5 % / 97.5 %) times the
+standard error of the mean for a normal shape; the same 3-standard-error bar is applied with those factors."""
+import os
+
 import numpy as np
 import pytest
 
+from conftest import GOLDEN, load_golden
 from mcmc_clv_model_b200 import Sampler
 from mcmc_clv_model_b200.diagnostics import summarize
 
 pytestmark = [pytest.mark.gpu, pytest.mark.slow]
 
-# reference pooled means and MCSE(mean) over 4 x 4000 kept draws
+NSIG = 3.0                      # the bar (north_star): 3 Monte-Carlo standard errors, flat
+Q_FACTOR = np.array([2.7, 1.25, 2.7])
+CHAINS = 64
+
+# reference pooled statistics over 4 x 4000 kept draws (columns = stored level_2 order)
 REF_M1 = dict(mean=[-3.528, -3.624, 1.362, 0.226, 3.077], mcse=[0.010, 0.021, 0.013, 0.024, 0.147],
-              mean_lambda=0.0584, mean_z=0.4316, loglik=-5.4937,
+              between_sd=[0.043, 0.065, 0.056, 0.050, 0.426],
+              q=[[-3.721, -4.025, 1.078, -0.202, 1.064], [-3.532, -3.609, 1.360, 0.198, 2.941], [-3.322, -3.287, 1.657, 0.797, 5.476]],
+              mean_lambda=0.0584, mean_mu=0.1444, mean_z=0.4316, loglik=-5.4937,
               e_lambda5=[0.0457, 0.0353, 0.0770, 0.0362, 0.0346], p_alive5=[0.872, 0.259, 0.185, 0.252, 0.292])
 REF_M2 = dict(mean=[-3.564, 0.207, -3.723, 0.059, 1.386, 0.295, 2.951],
-              mcse=[0.011, 0.003, 0.026, 0.009, 0.016, 0.033, 0.133], mean_lambda=0.0587, mean_z=0.4497, loglik=-5.4769)
+              mcse=[0.011, 0.003, 0.026, 0.009, 0.016, 0.033, 0.133], between_sd=[0.022, 0.011, 0.100, 0.027, 0.059, 0.121, 0.289],
+              q=[[-3.766, 0.073, -4.298, -0.248, 1.108, -0.166, 1.365], [-3.558, 0.209, -3.700, 0.072, 1.371, 0.256, 2.768],
+                 [-3.385, 0.329, -3.359, 0.271, 1.759, 1.006, 5.526]],
+              mean_lambda=0.0587, mean_mu=0.1237, mean_z=0.4497, loglik=-5.4769)
 
 
-def _run(d, cov, rng, chains=16, seed=42):
-    X = np.column_stack([np.ones(d["x"].size)] + [d[c].astype(float) for c in cov])
-    with Sampler(d["x"], d["t_x"], d["T_cal"], X, model_dim=2, chains=chains, n_mh_steps=20, seed=seed, rng=rng) as s:
-        out = s.run(10000, 4000, 1, store_level1=False)
-        tail = s.run(0, 400, 4, store_level1=True)            # 100 level-1 draws per chain for customer-level checks
-    return out, tail
+def _run(cbs, cov, D, rng="fast", chains=CHAINS, seed=42, burnin=10000, mcmc=4000):
+    n = cbs["x"].size
+    X = np.column_stack([np.ones(n)] + [cbs[c].astype(float) for c in cov])
+    log_s = cbs["log_s"] if D == 3 else None
+    with Sampler(cbs["x"], cbs["t_x"], cbs["T_cal"], X, log_s, model_dim=D, chains=chains, n_mh_steps=20, seed=seed, rng=rng) as s:
+        out = s.run(burnin, mcmc, 1, store_level1=False)
+        tail = s.run(0, 2000, 20, store_level1=True)          # 100 level-1 draws per chain, 20 sweeps apart
+    return out, np.concatenate(list(tail["level_1"]), axis=0)
 
 
-def _check(out, tail, ref, n):
-    summ = summarize(out["level_2"])
-    for j, (m, se) in enumerate(zip(ref["mean"], ref["mcse"])):
-        ours, se_ours = summ[j]["mean"], summ[j]["mcse_mean"]
-        tol = 3.0 * np.hypot(se, se_ours)
-        assert abs(ours - m) < tol, f"level_2 column {j}: ours {ours:.4f} vs reference {m:.4f} (3 MCSE = {tol:.4f})"
-        assert summ[j]["rhat"] < 1.2
-    l1 = np.concatenate(list(tail["level_1"]), axis=0)
-    assert abs(l1[:, :, 0].mean() - ref["mean_lambda"]) < 0.004
-    assert abs(l1[:, :, 3].mean() - ref["mean_z"]) < 0.03
-    ll = (out["loglik_sum"] / n).mean()
-    assert abs(ll - ref["loglik"]) < 0.05
+def _check_level2(name, l2, ref_mean, ref_se, ref_q):
+    """Means and quantiles of every level-2 column within NSIG combined standard errors."""
+    summ = summarize(l2)
+    P = l2.shape[2]
+    cm = l2.mean(axis=1)
+    se_ours = np.maximum([summ[j]["mcse_mean"] for j in range(P)], cm.std(axis=0, ddof=1) / np.sqrt(cm.shape[0]))
+    se = np.hypot(ref_se, se_ours)
+    ours = np.array([summ[j]["mean"] for j in range(P)])
+    z = np.abs(ours - ref_mean) / se
+    assert z.max() < NSIG, f"{name}: |z| of the level_2 means = {np.round(z, 2)}; ours {np.round(ours, 4)} ref {np.round(ref_mean, 4)}"
+    q = np.percentile(l2.reshape(-1, P), [2.5, 50, 97.5], axis=0)
+    zq = np.abs(q - ref_q) / (Q_FACTOR[:, None] * se[None, :])
+    assert zq.max() < NSIG, f"{name}: |z| of the 2.5/50/97.5 % quantiles =\n{np.round(zq, 2)}\nours\n{np.round(q, 3)}\nref\n{np.round(ref_q, 3)}"
+    assert max(summ[j]["rhat"] for j in range(P)) < 1.1
+    return z.max(), zq.max()
+
+
+def _baseline_case(name, cbs, cov, ref, rng):
+    out, l1 = _run(cbs, cov, 2, rng)
+    ref_se = np.maximum(ref["mcse"], np.array(ref["between_sd"]) / 2.0)           # 4 reference chains
+    _check_level2(name, out["level_2"], np.array(ref["mean"]), ref_se, np.array(ref["q"]))
+    n = cbs["x"].size
+    assert abs(l1[:, :, 0].mean() / ref["mean_lambda"] - 1) < 0.05                 # E[lambda]
+    assert abs(l1[:, :, 1].mean() / ref["mean_mu"] - 1) < 0.15                     # E[mu]: heavy tailed (exp(Sigma_11 / 2))
+    assert abs(l1[:, :, 3].mean() - ref["mean_z"]) < 0.02                          # mean z = P(alive) over customers
+    assert abs((out["loglik_sum"] / n).mean() - ref["loglik"]) < 0.05
     return l1
 
 
 @pytest.mark.parametrize("rng", ["fast", "strict"])
 def test_c1_posterior_matches_reference(cdnow_abe, rng):
-    out, tail = _run(cdnow_abe, [], rng)
-    l1 = _check(out, tail, REF_M1, cdnow_abe["x"].size)
-    np.testing.assert_allclose(l1[:, :5, 0].mean(axis=0), REF_M1["e_lambda5"], rtol=0.3)   # 1600 correlated draws per customer
-    np.testing.assert_allclose(l1[:, :5, 3].mean(axis=0), REF_M1["p_alive5"], atol=0.06)
+    """BASELINE.json configs[0] (Abe subset, M1): Table-3 quantities and the per-customer posterior means."""
+    l1 = _baseline_case("C1/" + rng, cdnow_abe, [], REF_M1, rng)
+    np.testing.assert_allclose(l1[:, :5, 0].mean(axis=0), REF_M1["e_lambda5"], rtol=0.15)    # 6400 draws per customer
+    np.testing.assert_allclose(l1[:, :5, 3].mean(axis=0), REF_M1["p_alive5"], atol=0.04)
 
 
 def test_m2_posterior_matches_reference_including_beta_quirk(cdnow_abe):
-    out, tail = _run(cdnow_abe, ["first_sales_scaled"], "fast")
-    _check(out, tail, REF_M2, cdnow_abe["x"].size)
+    _baseline_case("M2", cdnow_abe, ["first_sales_scaled"], REF_M2, "fast")
 
 
-def _golden_case(name, cbs, D, chains=16, rng="fast"):
-    """Pooled posterior means of every level-2 column vs the reference's own chains (tests/golden/post_*.npz,
-    produced by tests/golden/make_posterior_golden.py from the unmodified reference)."""
-    from conftest import load_golden
+def _golden_case(name, cbs, D):
+    """Every level-2 column vs the reference's own chains (tests/golden/post_*.npz, made by
+    tests/golden/make_posterior_golden.py from the unmodified reference)."""
     g = load_golden(f"post_{name}.npz")
     cov = [str(c) for c in g["covariates"]]
-    X = np.column_stack([np.ones(cbs["x"].size)] + [cbs[c].astype(float) for c in cov])
-    log_s = cbs["log_s"] if D == 3 else None
-    with Sampler(cbs["x"], cbs["t_x"], cbs["T_cal"], X, log_s, model_dim=D, chains=chains, n_mh_steps=20, seed=123, rng=rng) as s:
-        out = s.run(int(g["burnin"]), int(g["mcmc"]), 1, store_level1=False)
-        tail = s.run(0, 400, 4, store_level1=True)
-    summ = summarize(out["level_2"])
-    # |ours - reference| in units of the combined Monte-Carlo standard error of the two pooled means.  The bar is 3 MCSE
-    # per parameter (north_star); with 7-15 parameters per model and MCSEs that are themselves estimates from slowly
-    # mixing chains, ONE parameter may sit between 3 and 4.5 (multiple comparisons), none beyond.
-    # MCSE of a pooled mean: the larger of the autocorrelation-based (Geyer) estimate and the between-chain one,
-    # sd(chain means) / sqrt(chains) -- these chains mix slowly (ESS of a few dozen per chain) and the within-chain
-    # estimate alone understates the error when chains have not fully overlapped.
-    cm_ours = out["level_2"].mean(axis=1)
-    se_ours = np.maximum([summ[j]["mcse_mean"] for j in range(len(g["mean"]))], cm_ours.std(axis=0, ddof=1) / np.sqrt(cm_ours.shape[0]))
-    se_ref = np.maximum(g["mcse"], g["chain_means"].std(axis=0, ddof=1) / np.sqrt(g["chain_means"].shape[0]))
-    zs = np.abs(np.array([summ[j]["mean"] for j in range(len(g["mean"]))]) - g["mean"]) / np.hypot(se_ref, se_ours)
-    worst = zs.max()
-    msg = f"{name}: |z| per level_2 column = {np.round(zs, 2)}; ours {[round(summ[j]['mean'], 4) for j in range(len(zs))]}"
-    assert (zs > 3.0).sum() <= 1 and worst < 4.5, msg
-    l1 = np.concatenate(list(tail["level_1"]), axis=0).mean(axis=(0, 1))
+    out, l1 = _run(cbs, cov, D, "fast", seed=123, burnin=int(g["burnin"]), mcmc=int(g["mcmc"]))
+    nref = g["chain_means"].shape[0]
+    ref_se = np.maximum(g["mcse"], g["chain_means"].std(axis=0, ddof=1) / np.sqrt(nref))
+    if "quantiles" in g:
+        ref_q = g["quantiles"]
+    else:                                                    # older goldens: means only
+        ref_q = None
+    if ref_q is not None:
+        _check_level2(name, out["level_2"], g["mean"], ref_se, ref_q)
+    else:
+        summ = summarize(out["level_2"])
+        cm = out["level_2"].mean(axis=1)
+        se_ours = np.maximum([summ[j]["mcse_mean"] for j in range(len(g["mean"]))], cm.std(axis=0, ddof=1) / np.sqrt(cm.shape[0]))
+        z = np.abs(np.array([summ[j]["mean"] for j in range(len(g["mean"]))]) - g["mean"]) / np.hypot(ref_se, se_ours)
+        assert z.max() < NSIG, f"{name}: |z| of the level_2 means = {np.round(z, 2)}"
+    m1 = l1.mean(axis=(0, 1))
     ref1 = g["level1_col_means"]
-    assert abs(l1[0] / ref1[0] - 1) < 0.08 and abs(l1[3] - ref1[3]) < 0.03          # E[lambda] (heavy tailed), P(alive)
+    assert abs(m1[0] / ref1[0] - 1) < 0.05 and abs(m1[3] - ref1[3]) < 0.02          # E[lambda], P(alive)
+    assert abs(m1[1] / ref1[1] - 1) < 0.15                                          # E[mu]
     if D == 3:
-        assert abs(l1[4] / ref1[4] - 1) < 0.02                                      # E[eta]
+        assert abs(m1[4] / ref1[4] - 1) < 0.02                                      # E[eta]
     assert abs((out["loglik_sum"] / cbs["x"].size).mean() - float(g["loglik"])) < 0.05
-    return worst
+    if "customer_means8" in g:                                                      # per-customer posterior means
+        c8 = g["customer_means8"]
+        ours8 = l1[:, :8, :].mean(axis=0)
+        np.testing.assert_allclose(ours8[:, 0], c8[:, 0], rtol=0.15)
+        np.testing.assert_allclose(ours8[:, 3], c8[:, 3], atol=0.04)
 
 
 def test_trivariate_k3_posterior_matches_reference(cdnow_abe):
@@ -96,19 +130,19 @@ def test_bivariate_k4_posterior_matches_reference(cdnow_abe):
     _golden_case("bi_k4", cdnow_abe, 2)
 
 
-def test_full_cdnow_c2_c3_posteriors_match_reference(cdnow_full):
-    """BASELINE.json configs[1] and configs[2] on the full CDNOW data (23 570 customers)."""
-    import os
-    from conftest import GOLDEN
-    for name, D in (("c2_full_bi_k2", 2), ("c3_full_tri_k3", 3)):
-        if not os.path.exists(os.path.join(GOLDEN, f"post_{name}.npz")):
-            pytest.skip(f"golden post_{name}.npz not generated")
-        _golden_case(name, cdnow_full, D, chains=8)
+@pytest.mark.parametrize("name,D", [("c2_full_bi_k2", 2), ("c3_full_tri_k3", 3)])
+def test_full_cdnow_posteriors_match_reference(cdnow_full, name, D):
+    """BASELINE.json configs[1] and configs[2] on the full CDNOW data (23 570 customers) at the reference drivers' real
+    settings (10 000 burn-in + 4 000 kept, thin 1: run_mcmc_full.py:137-147, trivariate/run_mcmc_full.py:80-90)."""
+    if not os.path.exists(os.path.join(GOLDEN, f"post_{name}.npz")):
+        pytest.skip(f"golden post_{name}.npz not generated")
+    _golden_case(name, cdnow_full, D)
 
 
 def test_fast_and_strict_rng_modes_sample_the_same_posterior(cdnow_abe):
     """FAST (fp32 SFU proposal variates, fp32-screened accept) and STRICT (everything fp64) target the same posterior:
-    64 chains each on C1, pooled level-2 means within 3 combined standard errors (between-chain aware)."""
+    64 chains each on the Abe subset with a covariate, pooled level-2 means within 3 combined standard errors
+    (between-chain aware) and matching quantiles."""
     d = cdnow_abe
     X = np.column_stack([np.ones(d["x"].size), d["first_sales_scaled"]])
     res = {}
@@ -118,6 +152,7 @@ def test_fast_and_strict_rng_modes_sample_the_same_posterior(cdnow_abe):
     m = {k: v.mean(axis=(0, 1)) for k, v in res.items()}
     se = {k: v.mean(axis=1).std(axis=0, ddof=1) / np.sqrt(v.shape[0]) for k, v in res.items()}
     z = np.abs(m["fast"] - m["strict"]) / np.hypot(se["fast"], se["strict"])
-    assert (z > 3.0).sum() <= 1 and z.max() < 4.5, (np.round(z, 2), m)
+    assert z.max() < NSIG, (np.round(z, 2), m)
     q = {k: np.percentile(v.reshape(-1, v.shape[2]), [2.5, 50, 97.5], axis=0) for k, v in res.items()}
-    np.testing.assert_allclose(q["fast"], q["strict"], rtol=0.08, atol=0.04)
+    zq = np.abs(q["fast"] - q["strict"]) / (Q_FACTOR[:, None] * np.hypot(se["fast"], se["strict"])[None, :])
+    assert zq.max() < NSIG, np.round(zq, 2)
