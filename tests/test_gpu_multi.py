@@ -47,3 +47,25 @@ def test_chains_across_gpus_equal_single_gpu():
             np.testing.assert_array_equal(one["level_1"][c], two["level_1"][c])
             np.testing.assert_array_equal(one["level_2"][c], two["level_2"][c])
         assert one["log_likelihood"] == two["log_likelihood"]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_forecast_sharded_over_devices_equals_single_device():
+    """draw_future_transactions with the draws cut into ranges over two GPUs (no collective; the Philox
+    counters carry the global draw index) returns exactly the single-GPU x* (and spend)."""
+    import numpy as np
+    import pandas as pd
+    from conftest import load_golden
+    from mcmc_clv_model_b200 import draw_future_transactions, draw_future_transactions_rfm_m
+    for name, fn in (("fc_bi.npz", draw_future_transactions), ("fc_tri.npz", draw_future_transactions_rfm_m)):
+        g = load_golden(name)
+        l1 = g["level_1"]
+        draws = {"level_1": [l1[:3], l1[3:]]}                      # two "chains" of unequal length
+        cbs = pd.DataFrame({"T_cal": g["T_cal"]})
+        one = fn(cbs, draws, T_star=39.0, seed=5, devices=[0])
+        two = fn(cbs, draws, T_star=39.0, seed=5, devices=[0, 1])
+        if isinstance(one, tuple):
+            np.testing.assert_array_equal(one[0], two[0])
+            np.testing.assert_array_equal(one[1], two[1])
+        else:
+            np.testing.assert_array_equal(one, two)
