@@ -210,6 +210,15 @@ int clv_forecast_injected(const clv_forecast_config* cfg, const double* level1, 
 int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t* x_star, double* mean_x_star,
                           double* p_alive, double* kernel_ms /* nullable: CUDA-event time of the kernel */);
 
+/* Fused forecast: while clv_run / clv_run_resident keeps a draw, x* of that draw (bi:535-543) is simulated inside the sweep
+ * kernel from lambda, tau, z still in registers and added to per-(chain, customer) sums -- the posterior-predictive means
+ * need no pass over the stored draws at all (level1 may even be NULL).  Same Philox counters as clv_forecast_resident /
+ * clv_forecast on the same draws (seed, global customer id, draw index chain * n_draws + draw), hence the same x*.
+ * Enable before the run; the sums restart with every run. */
+int clv_set_fused_forecast(clv_sampler* h, int enable, double T_star, uint64_t seed);
+/* mean x* and P(alive) = mean z per customer over all kept draws of all chains of the last run (host [n_local], nullable). */
+int clv_fused_forecast_result(clv_sampler* h, double* mean_x_star, double* p_alive, int64_t* n_draws_total);
+
 /* ---- analysis reductions on the resident draws (SURVEY 8f "next" rows) ---------------------- */
 /* Place host draws [chains][n_draws][n_local][4|5] (e.g. an unpickled "level_1" list, chain-major) into the handle's
  * resident buffer, so that the reductions below / clv_forecast_resident can serve draws that were not produced by this

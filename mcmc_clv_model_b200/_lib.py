@@ -76,6 +76,8 @@ SIGNATURES = {
     "clv_run_resident": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, c_double_p, c_double_p,
                                    PROGRESS_CB, C.c_void_p, C.c_int64]),
     "clv_resident_draws": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), c_int64_p]),
+    "clv_set_fused_forecast": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_uint64]),
+    "clv_fused_forecast_result": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_int64_p]),
     "clv_advance": (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),
     "clv_advance_timed": (C.c_int, [C.c_void_p, C.c_int64, c_double_p]),
     "clv_sweeps_done": (C.c_int64, [C.c_void_p]),

@@ -124,6 +124,10 @@ struct clv_sampler {
   // 3 = k_sweep after its tiles.  0 = chosen from the grid size at create.
   int pdl_mode = 0;
   unsigned long long init_epoch = 0;     // bumped by every clv_init_state: mailbox flags never repeat
+  // fused forecast of the kept draws (clv_set_fused_forecast)
+  bool fc_enabled = false; double fc_T_star = 39.0; uint64_t fc_seed = 0;
+  FusedForecast* d_fc = nullptr; unsigned long long* d_fc_sx = nullptr; unsigned int* d_fc_sz = nullptr;
+  long long fc_draws = 0;                // draws per chain accumulated by the last run
   // statistics computed by clv_init_state(h, NULL)
   clv_init_stats last_stats{};
   std::vector<double> last_xtx;
@@ -450,6 +454,7 @@ SweepArgs base_args(clv_sampler* h) {
   a.store_zt = 0;
   a.error_flag = h->p2p ? h->d_err : nullptr;     // only sharded runs can be told to stop by a peer
   a.pdl_early = (h->pdl_mode == 3) ? 0 : 1;
+  a.fc = nullptr;                                  // set by the run driver for sweeps that may keep a draw
   return a;
 }
 
@@ -479,6 +484,10 @@ template <int D>
 cudaError_t launch_sweep_kernel(clv_sampler* h, const SweepArgs& a, int mode, bool pdl) {
   dim3 grid(h->grid_x, h->chains), block(SWEEP_THREADS);
   const size_t sm = h->stats_smem;
+  if (a.fc) {      // fused forecast of the kept draws: its own instantiations
+    if (mode == MODE_STRICT) return launch_kernel(k_sweep<D, MODE_STRICT, true>, grid, block, sm, h->stream, pdl, a);
+    return launch_kernel(k_sweep<D, MODE_FAST, true>, grid, block, sm, h->stream, pdl, a);
+  }
   if (mode == MODE_FAST) return launch_kernel(k_sweep<D, MODE_FAST>, grid, block, sm, h->stream, pdl, a);
   if (mode == MODE_STRICT) return launch_kernel(k_sweep<D, MODE_STRICT>, grid, block, sm, h->stream, pdl, a);
   return launch_kernel(k_sweep<D, MODE_INJECT>, grid, block, sm, h->stream, pdl, a);
@@ -679,6 +688,10 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
     cudaFuncSetAttribute(k_sweep<3, MODE_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_sweep<3, MODE_STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_sweep<3, MODE_INJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_sweep<2, MODE_FAST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_sweep<2, MODE_STRICT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_sweep<3, MODE_FAST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_sweep<3, MODE_STRICT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_stats_only<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_persistent<2, MODE_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_persistent<2, MODE_STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -720,6 +733,9 @@ void clv_destroy(clv_sampler* h) {
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   if (h->d_acc3) dfree(h->d_acc3);
   if (h->d_barrier) dfree(h->d_barrier);
+  if (h->d_fc) dfree(h->d_fc);
+  if (h->d_fc_sx) dfree(h->d_fc_sx);
+  if (h->d_fc_sz) dfree(h->d_fc_sz);
   void* ptrs[] = {h->d_mc, h->d_params, h->d_x, h->d_tx, h->d_T, h->d_Xc, h->d_logs, h->d_ll, h->d_lm, h->d_le,
                   h->d_z, h->d_tau, h->d_acc, h->d_err, h->d_loglik, h->d_level2, h->d_draws[0], h->d_draws[1], h->d_inj};
   for (void* p : ptrs) if (p) dfree(p);
@@ -1101,7 +1117,7 @@ int clv_kernel_time_ms(clv_sampler* h, double* sweep_ms, double* l2_ms, int64_t*
 namespace {
 
 bool want_persistent(const clv_sampler* h) {
-  if (h->comm || h->p2p || h->timing || h->persist_grid_x <= 0 || h->cfg.rng_mode == CLV_RNG_INJECTED) return false;
+  if (h->comm || h->p2p || h->timing || h->fc_enabled || h->persist_grid_x <= 0 || h->cfg.rng_mode == CLV_RNG_INJECTED) return false;
   // AUTO = stream: with programmatic dependent launch the two-kernel path is at least as fast as the cooperative kernel
   // at every size measured (14.2 vs 16.4 us per sweep at 4 x 2 357 customers, 18.2 vs 20.4 at 2 x 23 570, 213 vs 261 at
   // 1.25 M; profiles/r02_kernel_ab.txt): the grid barrier costs more than the launch boundary that PDL hides.
@@ -1176,6 +1192,7 @@ int run_stream_segment(clv_sampler* h, const RunCtx& rc, long long n, bool store
     a.sweep = l2.sweep = (uint32_t)(h->sweeps_done + 1);
     l2.n_draws = rc.n_draws;
     a.loglik_stride = rc.n_draws;
+    a.fc = (rc.keep_any && h->fc_enabled) ? h->d_fc : nullptr;
     const bool kept = rc.keep_any && step > rc.burnin && (step - 1 - rc.burnin) % rc.thin == 0;      // bi:402
     if (kept) {
       const long long draw = (step - 1 - rc.burnin) / rc.thin;
@@ -1296,6 +1313,11 @@ static int run_impl(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, 
   if (int r = ensure_run_buffers(h, n_draws, store, &cap)) return r;
   if (resident_only && cap < n_draws)
     return fail(h, CLV_ERR_ARG, "clv_run_resident: %lld draws do not fit the device draw buffer (%lld fit)", n_draws, cap);
+  if (h->fc_enabled) {        // fused forecast: fresh per-(chain, customer) sums for this run
+    CK(h, cudaMemsetAsync(h->d_fc_sx, 0, sizeof(unsigned long long) * C * N, h->stream));
+    CK(h, cudaMemsetAsync(h->d_fc_sz, 0, sizeof(unsigned int) * C * N, h->stream));
+    h->fc_draws = n_draws;
+  }
   const long long total = burnin + mcmc;
   int buf = 0;
   long long chunk_base = 0;
@@ -1387,6 +1409,46 @@ int clv_run(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* 
 int clv_run_resident(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* level2, double* loglik,
                      clv_progress_cb cb, void* user, int64_t trace) {
   return run_impl(h, burnin, mcmc, thin, nullptr, true, level2, loglik, cb, user, trace);
+}
+
+int clv_set_fused_forecast(clv_sampler* h, int enable, double T_star, uint64_t seed) {
+  if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
+  if (int r = upload_rk()) return r;
+  h->fc_enabled = enable != 0;
+  h->fc_draws = 0;
+  if (!h->fc_enabled) return CLV_OK;
+  if (!(T_star >= 0.0)) return fail(h, CLV_ERR_ARG, "clv_set_fused_forecast: T_star must be >= 0");
+  const size_t cn = (size_t)h->chains * (size_t)h->N;
+  if (!h->d_fc) { CK(h, dmalloc(&h->d_fc, 1)); CK(h, dmalloc(&h->d_fc_sx, cn)); CK(h, dmalloc(&h->d_fc_sz, cn)); }
+  h->fc_T_star = T_star; h->fc_seed = seed;
+  FusedForecast f{};
+  f.sum_x = h->d_fc_sx; f.sum_z = h->d_fc_sz; f.T_star = T_star; f.seed = seed; f.rk = round_keys(seed);
+  CK(h, cudaMemcpyAsync(h->d_fc, &f, sizeof f, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemsetAsync(h->d_fc_sx, 0, sizeof(unsigned long long) * cn, h->stream));
+  CK(h, cudaMemsetAsync(h->d_fc_sz, 0, sizeof(unsigned int) * cn, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));          // `f` is on this function's stack
+  return CLV_OK;
+}
+
+int clv_fused_forecast_result(clv_sampler* h, double* mean_x_star, double* p_alive, int64_t* n_draws_total) {
+  if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
+  if (!h->fc_enabled || h->fc_draws <= 0) return fail(h, CLV_ERR_STATE, "no fused forecast: call clv_set_fused_forecast, then clv_run / clv_run_resident");
+  CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
+  const long long C = h->chains, N = h->N;
+  double *d_mx = nullptr, *d_pa = nullptr;
+  CK(h, dmalloc(&d_mx, (size_t)N));
+  CK(h, dmalloc(&d_pa, (size_t)N));
+  k_fused_forecast_fold<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_fc_sx, h->d_fc_sz, N, (int)C, 1.0 / (double)(C * h->fc_draws), d_mx, d_pa);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && mean_x_star) e = cudaMemcpyAsync(mean_x_star, d_mx, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && p_alive) e = cudaMemcpyAsync(p_alive, d_pa, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  dfree(d_mx); dfree(d_pa);
+  if (e != cudaSuccess) return fail(h, CLV_ERR_CUDA, "clv_fused_forecast_result failed: %s", cudaGetErrorString(e));
+  if (n_draws_total) *n_draws_total = C * h->fc_draws;
+  return CLV_OK;
 }
 
 int clv_resident_draws(clv_sampler* h, const double** level1_dev, int64_t* n_draws) {

@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "clv_rng.cuh"
+#include "clv_forecast.cuh"
 
 namespace clv {
 
@@ -55,6 +56,42 @@ struct ModelConst {
   double omega2;             // tri:494
 };
 
+// Fused forecast (SURVEY 8a a8 on the sampler's own kept draws): when a draw is kept, lambda, tau and z of the cell are in
+// registers -- x* is simulated there and added to per-(chain, customer) sums, so the posterior-predictive means need no
+// second pass over the draws at all (zero re-read; the draws need not even be stored).  Same Philox counters as
+// clv_forecast_resident on the stored draws (global draw index = chain * n_draws + draw), hence the same x*.
+struct FusedForecast {
+  unsigned long long* sum_x;   // [chains][N]
+  unsigned int* sum_z;         // [chains][N]
+  double T_star;
+  uint64_t seed;
+  PhiloxRoundKeys rk;          // round keys of `seed`
+};
+
+__device__ __noinline__ void fused_forecast_cell(const FusedForecast* f, uint32_t gid, long long gdraw, double lam, double tau,
+                                                 double zf, double T, long long idx) {
+  const uint4 r = philox4x32_10_rk(gid, (uint32_t)(gdraw >> 1), 0u, DOM_FORECAST, f->rk);
+  const uint32_t ua = (gdraw & 1) ? r.z : r.x, ub = (gdraw & 1) ? r.w : r.y;
+  const double m = lam * future_horizon(T, tau, zf, f->T_star);
+  long long x;
+  if (m >= PTRS_MIN_MEAN) x = poisson_ptrs(m, gid, (uint32_t)gdraw, seed_key(f->seed));
+  else x = poisson_inversion_screened((float)m, u24f(ua), [&]() { return poisson_inversion(m, u53(ua, ub)); });
+  if (x) f->sum_x[idx] += (unsigned long long)x;
+  if (zf > 0.5) f->sum_z[idx] += 1u;
+}
+
+// per customer: sums over the chains, scaled to means
+__global__ void k_fused_forecast_fold(const unsigned long long* sx, const unsigned int* sz, long long N, int chains, double inv,
+                                      double* mean_x, double* p_alive) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long tx = 0;
+    unsigned long long tz = 0;
+    for (int c = 0; c < chains; ++c) { tx += sx[(long long)c * N + i]; tz += sz[(long long)c * N + i]; }
+    mean_x[i] = (double)tx * inv;
+    p_alive[i] = (double)tz * inv;
+  }
+}
+
 struct SweepArgs {
   const ModelConst* mc;
   const ChainParams* params;   // [chains]
@@ -84,6 +121,7 @@ struct SweepArgs {
   uint64_t seed;
   PhiloxRoundKeys rk;          // round keys of `seed` (launch constants)
   int store_zt;                // write z/tau state arrays
+  const FusedForecast* fc;     // nullable: simulate x* of every kept draw from the registers (clv_set_fused_forecast)
   const int* error_flag;       // device error flag (2: a peer rank stopped)
   int pdl_early;               // 1: let the next kernel of the stream become resident at once, 0: once this block's tiles are done
   // injected variates (MODE_INJECT)
@@ -275,12 +313,13 @@ struct SweepStep {
   int store_zt;          // write z / tau state arrays
   long long slot;        // slot inside the draw chunk
   long long chunk_cap;
+  long long draw_index;  // index of the kept draw within the run
   double* draws;         // nullable
 };
 
 // One tile of 128 customers of one chain through one Gibbs sweep (blocks a1-a3, a5 of SURVEY 8a) plus its share of
 // the level-2 statistics.  cp / s_beta / s_tab / s_acc live in shared memory.
-template <int D, int MODE>
+template <int D, int MODE, bool FUSE_FC = false>
 __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst& mc, const ChainParams& cp,
                                            const double* s_beta, const double* s_tab, long long* s_priv,
                                            const SweepStep& sw, int chain, long long tile, uint32_t c3) {
@@ -423,6 +462,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
           o[0] = lam_n; o[1] = mu_n; o[2] = tau; o[3] = zf; o[4] = exp(le);
         }
       }
+      if (FUSE_FC && a.fc) fused_forecast_cell(a.fc, gid, (long long)chain * a.loglik_stride + sw.draw_index, lam_n, tau, zf, T, cN + i);
       lik = xd * ll + omz * lm - (lam_n + mu_n) * Tz;         // bi:423-427
       lik = fmin(fmax(lik, -1048576.0), 1048576.0);
     }
@@ -434,7 +474,10 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
   if (keep && valid) s_priv[(K * D + D * (D + 1) / 2) * SWEEP_THREADS + tid] += to_fx(lik, mc.ll_scale);
 }
 
-template <int D, int MODE>
+// FUSE_FC: the instantiation that also simulates x* of a kept draw (clv_set_fused_forecast).  A separate instantiation, so
+// that the out-of-line call in the keep branch costs the ordinary sweep kernel no register (it put a spill reload into
+// the Metropolis loop when it was a run-time option).
+template <int D, int MODE, bool FUSE_FC = false>
 __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArgs a) {
   extern __shared__ long long s_priv[];          // [(nstat + 1)][SWEEP_THREADS]
   __shared__ double s_beta[MAXK * MAXD];
@@ -458,10 +501,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArg
   const uint32_t c3 = dom_word(DOM_SAMPLER, a.chain_offset + (uint32_t)chain);
   SweepStep sw;
   sw.sweep = a.sweep; sw.keep = a.slot >= 0; sw.store_zt = a.store_zt; sw.slot = a.slot; sw.chunk_cap = a.chunk_cap;
-  sw.draws = a.draws;
+  sw.draws = a.draws; sw.draw_index = a.draw_index;
   const long long ntiles = (mc.N + SWEEP_THREADS - 1) / SWEEP_THREADS;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-    sweep_tile<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, c3);
+    sweep_tile<D, MODE, FUSE_FC>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, c3);
   if (!a.pdl_early) pdl_launch_dependents();
   flush_stats(s_priv, s_acc, nstat, sw.keep != 0);
   __syncthreads();
@@ -1119,7 +1162,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(Per
     __syncthreads();
     SweepStep sw;
     sw.sweep = sweep; sw.keep = kept; sw.store_zt = (pa.store_zt_last && it + 1 == pa.n_sweeps);
-    sw.slot = kept ? draw - pa.chunk_base : 0; sw.chunk_cap = a.chunk_cap; sw.draws = a.draws;
+    sw.slot = kept ? draw - pa.chunk_base : 0; sw.chunk_cap = a.chunk_cap; sw.draws = a.draws; sw.draw_index = draw;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
       sweep_tile<D, MODE>(a, mc, s_cp, s_beta, s_tab, s_priv, sw, chain, tile, c3);
     flush_stats(s_priv, s_acc, nstat, kept);

@@ -257,6 +257,19 @@ class Sampler:
                 self.h)
         return dict(level_1=lvl1, level_2=lvl2, loglik_sum=ll)
 
+    # ---- fused forecast --------------------------------------------------------------------------
+    def set_fused_forecast(self, T_star=39.0, seed=0, enable=True):
+        """Simulate x* of every kept draw inside the sweep kernel (lambda, tau, z still in registers) during the next
+        run()/run_resident(): no pass over stored draws, which need not even be kept (store_level1=False)."""
+        L.check(self.lib.clv_set_fused_forecast(self.h, 1 if enable else 0, float(T_star), int(seed) & 0xFFFFFFFFFFFFFFFF), self.h)
+
+    def fused_forecast_result(self):
+        """Per-customer mean x* and P(alive) over all kept draws of all chains of the last run (same values as
+        forecast_resident() on the same draws and seed)."""
+        mx, pa, n = np.empty(self.N), np.empty(self.N), C.c_int64()
+        L.check(self.lib.clv_fused_forecast_result(self.h, L.dptr(mx), L.dptr(pa), C.byref(n)), self.h)
+        return dict(mean_x_star=mx, p_alive=pa, n_draws_total=int(n.value))
+
     # ---- resident forecast ---------------------------------------------------------------------
     def forecast_resident(self, T_star=39.0, seed=0, want_x_star=False):
         """x* / P(alive) from the draws still in HBM after run()/run_resident(): per-customer mean x* and mean z,

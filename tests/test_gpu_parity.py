@@ -788,3 +788,33 @@ def test_forecast_spend_philox_vs_restated_contract():
     m1, v1 = np.exp(1.0 + 0.125), (np.exp(0.25) - 1.0) * np.exp(2.0 + 0.25)
     zs = (sb - xb * m1) / np.sqrt(xb * v1)
     assert abs(zs.mean()) < 5 / np.sqrt(zs.size) and abs(zs.std() - 1) < 0.05
+
+
+@pytest.mark.parametrize("D", [2, 3])
+def test_fused_forecast_equals_forecast_of_the_stored_draws(cdnow_abe, D):
+    """x* drawn inside the sweep kernel when a draw is kept (lambda, tau, z in registers: zero re-read) == the forecast
+    of the same stored draws with the same seed (clv_forecast_resident, and the host-path clv_forecast): same Philox
+    counters (global customer id, draw index chain * n_draws + draw).  Includes a customer in the PTRS regime."""
+    from mcmc_clv_model_b200.api import _forecast
+    d = cdnow_abe
+    n = 1500
+    x = d["x"][:n].copy()
+    x[7] = 900                                                       # lambda * T_star well beyond the PTRS switch
+    t_x = d["t_x"][:n].copy()
+    t_x[7] = d["T_cal"][7] - 0.01
+    X = np.column_stack([np.ones(n), d["first_sales_scaled"][:n]])
+    with Sampler(x, t_x, d["T_cal"][:n], X, d["log_s"][:n] if D == 3 else None, model_dim=D, chains=3, seed=21) as s:
+        s.set_fused_forecast(T_star=39.0, seed=77)
+        out = s.run(40, 30, 3)                                        # 10 kept draws per chain, draws stored as well
+        fused = s.fused_forecast_result()
+        res = s.forecast_resident(T_star=39.0, seed=77, want_x_star=True)
+        s.set_fused_forecast(T_star=39.0, seed=78)
+        s.run(0, 12, 4, store_level1=False)                           # draws not stored at all
+        fused2 = s.fused_forecast_result()
+        s.set_fused_forecast(enable=False)
+    assert fused["n_draws_total"] == 30 and fused2["n_draws_total"] == 9
+    np.testing.assert_array_equal(fused["mean_x_star"], res["mean_x_star"])
+    np.testing.assert_array_equal(fused["p_alive"], res["p_alive"])
+    xs, _ = _forecast(d["T_cal"][:n], list(out["level_1"]), 39.0, 77, False, 0.5)
+    np.testing.assert_allclose(fused["mean_x_star"], xs.mean(axis=0), rtol=1e-13)
+    assert res["x_star"][:, 7].min() > 60 and np.isfinite(fused2["mean_x_star"]).all()
