@@ -414,16 +414,18 @@ def run_ours(args):
     sw = make()                     # untimed warm-up of the same call sequence (first-use costs of the draw buffers / copy path)
     sw.run(0, max(args.warmup, 1), max(args.warmup, 1), store_level1=True)
     sw.close()
-    e2e_s, small = e2e_once(None)
+    e2e_runs = [e2e_once(None) for _ in range(2)]
+    e2e_s, small = min(e2e_runs)
     h2d = n_loc * (4 + 8 + 8 + 8 * K_COV)
     d2h = n_loc * 32 + small
     e2e = {"value": n_tot * args.steps / e2e_s, "unit": "customer-updates/s", "h2d_bytes_per_step": h2d / args.steps,
-           "d2h_bytes_per_step": d2h / args.steps, "seconds": e2e_s,
-           "what": "clv_create + clv_set_data (page-locked host CBS -> device) + clv_init_state + clv_run(K sweeps, 1 kept "
+           "d2h_bytes_per_step": d2h / args.steps, "seconds": e2e_s, "seconds_all_runs": [r[0] for r in e2e_runs],
+           "what": "best of two timed runs of: clv_create + clv_set_data (page-locked host CBS -> device) + clv_init_state + clv_run(K sweeps, 1 kept "
                    "level-1 draw -> host) + clv_destroy, i.e. everything mcmc_draw_parameters does after the DataFrame is unpacked"}
     pageable = {k: np.array(cols[k], copy=True) for k in ("x", "t_x", "T_cal", "X")}     # ordinary NumPy arrays, as the API receives them
-    e2e_p, _ = e2e_once(pageable)
-    e2e_pageable = {"value": n_tot * args.steps / e2e_p, "unit": "customer-updates/s", "seconds": e2e_p,
+    e2e_p_runs = [e2e_once(pageable)[0] for _ in range(2)]
+    e2e_p = min(e2e_p_runs)
+    e2e_pageable = {"value": n_tot * args.steps / e2e_p, "unit": "customer-updates/s", "seconds": e2e_p, "seconds_all_runs": e2e_p_runs,
                     "what": "the same call sequence from ordinary (pageable) NumPy columns, as mcmc_draw_parameters receives them"}
     del pageable
 

@@ -128,6 +128,7 @@ struct clv_sampler {
   bool fc_enabled = false; double fc_T_star = 39.0; uint64_t fc_seed = 0;
   FusedForecast* d_fc = nullptr; unsigned long long* d_fc_sx = nullptr; unsigned int* d_fc_sz = nullptr;
   long long fc_draws = 0;                // draws per chain accumulated by the last run
+  unsigned long long fc_deferred_last = 0;   // cells the last resident forecast handed to its second pass
   // statistics computed by clv_init_state(h, NULL)
   clv_init_stats last_stats{};
   std::vector<double> last_xtx;
@@ -1749,7 +1750,49 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, h->stream);
   if (gy > 1) { cudaMemsetAsync(d_mx, 0, sizeof(double) * N, h->stream); cudaMemsetAsync(d_pa, 0, sizeof(double) * N, h->stream); }
-  if (h->ncol == 4) {
+  // bivariate rows (32 bytes: every bulk copy is 16-byte aligned): the TMA-fed kernel; CLV_FC_KERNEL=reg selects the
+  // register-fed one (always used for the 40-byte trivariate rows)
+  static const bool use_tma = [] { const char* e = getenv("CLV_FC_KERNEL"); return !(e && std::string(e) == "reg"); }();
+  bool tma_done = false;
+  if (h->ncol == 4 && use_tma) {
+    const size_t smem = (size_t)FC_STAGES * 2 * FC_TILE * 32 + (size_t)FC_WARPS * 96 * sizeof(FcQueued) + 2 * FC_STAGES * 8 + sizeof(FcCursor);
+    const long long ntiles = (N + FC_TILE - 1) / FC_TILE;
+    const int tx = (int)std::min<long long>(ntiles, 65535);
+    const int ty = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(npairs, 64), (long long)h->sm_count * 4 * 4 / std::max(1, tx)));
+    // list of deferred cells (x* >= 8, tie zone, large means): ~3 % of the cells; capacity 1/8 of them + slack
+    const unsigned long long cap = (unsigned long long)(C * nd * N) / 8 + 65536;
+    FcQueued* d_list = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    if (dmalloc(&d_list, (size_t)cap) == cudaSuccess && dmalloc(&d_cnt, 1) == cudaSuccess) {
+      cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), h->stream);
+      if (ty > 1 && gy <= 1) { cudaMemsetAsync(d_mx, 0, sizeof(double) * N, h->stream); cudaMemsetAsync(d_pa, 0, sizeof(double) * N, h->stream); }
+      const int gd = h->sm_count * 8;
+      if (d_x) {
+        cudaFuncSetAttribute(k_forecast_tma<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_forecast_tma<4, true><<<dim3(tx, ty), FC_TILE, smem, h->stream>>>(a, d_mx, d_pa, d_list, d_cnt, cap);
+        k_forecast_deferred<4, true><<<gd, 256, 0, h->stream>>>(a, d_list, d_cnt, cap, d_mx);
+      } else {
+        cudaFuncSetAttribute(k_forecast_tma<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_forecast_tma<4, false><<<dim3(tx, ty), FC_TILE, smem, h->stream>>>(a, d_mx, d_pa, d_list, d_cnt, cap);
+        k_forecast_deferred<4, false><<<gd, 256, 0, h->stream>>>(a, d_list, d_cnt, cap, d_mx);
+      }
+      h->launches++;
+      unsigned long long listed = 0;
+      cudaMemcpyAsync(&listed, d_cnt, sizeof listed, cudaMemcpyDeviceToHost, h->stream);
+      cudaStreamSynchronize(h->stream);
+      tma_done = cudaGetLastError() == cudaSuccess && listed <= cap;      // else: rerun below with the register-fed kernel
+      h->fc_deferred_last = listed;
+    } else {
+      cudaGetLastError();
+    }
+    if (d_list) dfree(d_list);
+    if (d_cnt) dfree(d_cnt);
+    // list overflow: rerun with the register-fed kernel (plain stores when gy == 1, atomics onto zeroed sums otherwise)
+    if (!tma_done && gy > 1) { cudaMemsetAsync(d_mx, 0, sizeof(double) * N, h->stream); cudaMemsetAsync(d_pa, 0, sizeof(double) * N, h->stream); }
+  }
+  if (tma_done) {
+    // done
+  } else if (h->ncol == 4) {
     if (d_x) k_forecast_reduce<4, true><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa);
     else k_forecast_reduce<4, false><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa);
   } else {

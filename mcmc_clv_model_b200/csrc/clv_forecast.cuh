@@ -263,16 +263,17 @@ constexpr int FC_WARPS = 8, FC_QCAP = 96;
 struct FcDeferred { uint32_t gdraw, owner, ua, ub; };
 
 // one deferred cell on its own lane: the full path (screened inversion of any length, exact fp64 re-decision, PTRS).
-// Out of line: the hot loop keeps its registers.
+// Out of line (the hot loop keeps its registers), arguments by value (no local copy of the kernel's parameter struct).
 template <int NCOL, bool WRITE_X>
-__device__ __noinline__ long long fc_deferred_cell(const ForecastArgs& a, FcDeferred e, long long ci, float T_star_f, PhiloxKey key) {
-  const double* row = a.level1 + ((long long)e.gdraw * a.N + ci) * NCOL;
-  const double Tc = a.T_cal[ci];
+__device__ __noinline__ long long fc_deferred_cell(const double* level1, const double* T_cal, long long N, long long gid_offset,
+                                                   double T_star, long long* x_out, FcDeferred e, long long ci, PhiloxKey key) {
+  const double* row = level1 + ((long long)e.gdraw * N + ci) * NCOL;
+  const double Tc = T_cal[ci];
   float lamf, dtf;
   bool al;
   load_row_f32<NCOL>(row, Tc, lamf, dtf, al);
-  const long long x = forecast_cell(row, lamf, dtf, al, Tc, a.T_star, T_star_f, e.ua, e.ub, (uint32_t)(a.gid_offset + ci), e.gdraw, key);
-  if (WRITE_X) __stcs(a.x_out + (long long)e.gdraw * a.N + ci, x);
+  const long long x = forecast_cell(row, lamf, dtf, al, Tc, T_star, (float)T_star, e.ua, e.ub, (uint32_t)(gid_offset + ci), e.gdraw, key);
+  if (WRITE_X) __stcs(x_out + (long long)e.gdraw * N + ci, x);
   return x;
 }
 
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(256, CLV_FC_MINBLOCKS) k_forecast_reduce(Forec
     auto drain = [&](int count) {
       if (lane < count) {
         const FcDeferred e = q[qn - count + lane];
-        const long long x = fc_deferred_cell<NCOL, WRITE_X>(a, e, wt * 32 + e.owner, T_star_f, key);
+        const long long x = fc_deferred_cell<NCOL, WRITE_X>(a.level1, a.T_cal, a.N, a.gid_offset, a.T_star, a.x_out, e, wt * 32 + e.owner, key);
         if (x) atomicAdd(&s_dx[warp][e.owner], (unsigned long long)x);
       }
       __syncwarp();
@@ -350,6 +351,213 @@ __global__ void __launch_bounds__(256, CLV_FC_MINBLOCKS) k_forecast_reduce(Forec
       }
     }
     __syncwarp();
+  }
+}
+
+// ---- the same reduction fed by the TMA engine ----------------------------------------------------------------------
+// k_forecast_reduce above keeps two level-1 rows per thread in flight in REGISTERS: at the 40 registers that six
+// resident blocks allow, the rows plus the Philox state spill (51 local-memory instructions per draw pair), and the loads
+// are only in flight while their warp waits for them.  Here the rows never pass through registers on their way in: for
+// a tile of 256 consecutive customers one draw is a contiguous 8 KB (10 KB for the trivariate layout) of the resident
+// array [draw][customer][col], which ONE thread fetches with a bulk asynchronous copy (cp.async.bulk, the TMA engine;
+// UBLKCP in SASS) into a ring of FC_STAGES shared-memory stages of one draw pair each, completion signalled on an
+// mbarrier.  Every thread then reads its own 32-byte row from shared memory when it needs it; a warp that has taken its
+// rows arrives on the stage's "empty" barrier and the producer refills the stage FC_STAGES pairs ahead.  HBM always has
+// (FC_STAGES - 1) x 16 KB per block in flight whatever the warps are doing, and the kernel needs no register for data in
+// flight.  Cells: quick path in lockstep + deferred queue, exactly as above (same x*).
+constexpr int FC_TILE = 256, FC_STAGES = 3;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (bytes: multiple of 16, both addresses 16-byte aligned), completion on `bar`
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct FcQueued { uint32_t gdraw, owner; };
+
+// Producer-side cursor over the loads of a block: tiles blockIdx.x, blockIdx.x + gridDim.x, ..., pairs pa .. pb-1 of each, in
+// consumption order; load number n goes to stage n % FC_STAGES.  It lives in SHARED memory and only thread 0 touches it:
+// the hot loop carries none of it in registers.
+struct FcCursor {
+  long long left;         // loads still to issue
+  int tile, gp, st;       // tile, draw pair and stage of the next load
+};
+
+template <int NCOL>
+__device__ __forceinline__ void fc_issue(FcCursor* c, const ForecastArgs& a, unsigned char* s_rows, uint64_t* s_full, int pa, int pb) {
+  constexpr int ROW = NCOL * 8, DRAW_BYTES = FC_TILE * ROW, STAGE_BYTES = 2 * DRAW_BYTES;
+  const int st = c->st, gp = c->gp;
+  const long long i0 = (long long)c->tile * FC_TILE;
+  const uint32_t bytes = (uint32_t)min((long long)FC_TILE, a.N - i0) * ROW;
+  const bool v1 = 2ll * gp + 1 < a.n_draws;
+  mbar_expect_tx(&s_full[st], v1 ? 2u * bytes : bytes);
+  const double* src = a.level1 + ((2ll * gp) * a.N + i0) * NCOL;
+  bulk_load(s_rows + (size_t)st * STAGE_BYTES, src, bytes, &s_full[st]);
+  if (v1) bulk_load(s_rows + (size_t)st * STAGE_BYTES + DRAW_BYTES, src + a.N * NCOL, bytes, &s_full[st]);
+  c->left -= 1;
+  if (gp + 1 == pb) { c->gp = pa; c->tile += (int)gridDim.x; } else c->gp = gp + 1;
+  c->st = (st + 1 == FC_STAGES) ? 0 : st + 1;
+}
+
+// quick path of one cell; a cell that needs more is queued (qn and the queue belong to the warp)
+template <bool WRITE_X>
+__device__ __forceinline__ void fc_quick_cell(double lam, double tau, double zf, double T, float T_star_f, uint32_t ua, uint32_t gdraw,
+                                              uint32_t cust, bool live, int lane, FcQueued* q, int& qn, int& sx, int& sz, long long* x_cell) {
+  const bool alive = zf > 0.5;
+  const float hf = alive ? T_star_f : fminf(fmaxf((float)(tau - T), 0.0f), T_star_f);
+  const float mf = (float)lam * hf;
+  const int k = (mf < 24.0f) ? poisson_quick(mf, u24f(ua)) : -1;
+  const bool defer = live && k < 0;
+  const unsigned m = __ballot_sync(0xffffffffu, defer);
+  if (defer) q[qn + __popc(m & ((1u << lane) - 1u))] = FcQueued{gdraw, cust};
+  qn += __popc(m);
+  if (live && k > 0) sx += k;
+  if (live && alive) ++sz;
+  if (WRITE_X && live && k >= 0) __stcs(x_cell, (long long)k);
+}
+
+// The warp moves q[first .. last) to the global list of deferred cells: one atomicAdd per batch, coalesced 8-byte stores.
+// Entries beyond the list's capacity are dropped and counted: the host then reruns the forecast with the register-fed kernel.
+__device__ __forceinline__ void fc_flush(const FcQueued* q, int first, int last, FcQueued* g_list, unsigned long long* g_count,
+                                         unsigned long long cap, int lane) {
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(g_count, (unsigned long long)(last - first));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (int b = first + lane; b < last; b += 32) {
+    const unsigned long long pos = base + (unsigned long long)(b - first);
+    if (pos < cap) g_list[pos] = q[b];
+  }
+  __syncwarp();
+}
+
+// Main pass: every cell's quick path; cells that need more are listed in global memory for k_forecast_deferred.
+// No function call in this kernel: it keeps its registers for the loop (64 at 4 blocks per SM, no spill).
+template <int NCOL, bool WRITE_X>
+__global__ void __launch_bounds__(FC_TILE, NCOL == 4 ? 4 : 3) k_forecast_tma(ForecastArgs a, double* sum_x, double* sum_z,
+                                                                              FcQueued* g_list, unsigned long long* g_count,
+                                                                              unsigned long long g_cap) {
+  extern __shared__ __align__(128) unsigned char fc_smem[];
+  constexpr int ROW = NCOL * 8, DRAW_BYTES = FC_TILE * ROW, STAGE_BYTES = 2 * DRAW_BYTES;
+  constexpr int QCAP = 96;
+  unsigned char* s_rows = fc_smem;                                                   // [FC_STAGES][2][FC_TILE][ROW]
+  FcQueued* s_q = reinterpret_cast<FcQueued*>(fc_smem + FC_STAGES * STAGE_BYTES);    // [FC_WARPS][QCAP]
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_q + FC_WARPS * QCAP);             // [FC_STAGES]
+  uint64_t* s_empty = s_full + FC_STAGES;                                            // [FC_STAGES]
+  FcCursor* s_cur = reinterpret_cast<FcCursor*>(s_empty + FC_STAGES);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int npairs = (int)((a.n_draws + 1) >> 1);
+  const int per = (npairs + gridDim.y - 1) / gridDim.y;
+  const int pa = blockIdx.y * per, pb = min(npairs, pa + per);
+  const int ntiles = (int)((a.N + FC_TILE - 1) / FC_TILE);
+  if (pb <= pa || (int)blockIdx.x >= ntiles) return;
+  if (tid == 0) {
+    for (int s = 0; s < FC_STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], FC_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_cur->left = (long long)((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * (pb - pa);
+    s_cur->tile = (int)blockIdx.x; s_cur->gp = pa; s_cur->st = 0;
+    for (int s = 0; s < FC_STAGES && s_cur->left > 0; ++s) fc_issue<NCOL>(s_cur, a, s_rows, s_full, pa, pb);
+  }
+  __syncthreads();
+  FcQueued* q = s_q + (tid >> 5) * QCAP;
+  const float T_star_f = (float)a.T_star;
+  int st = 0;                               // stage of this consumption
+  uint32_t par = 0;                         // parity of the stage's current use
+  bool first = true;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const bool valid = (long long)tile * FC_TILE + tid < a.N;
+    const long long ic = valid ? (long long)tile * FC_TILE + tid : a.N - 1;
+    const double T = a.T_cal[ic];
+    const uint32_t gid = (uint32_t)(a.gid_offset + ic);
+    int sx = 0, sz = 0, qn = 0;             // quick-path counts are < 8 per cell: 32 bits hold 2^28 draws
+    for (int gp = pa; gp < pb; ++gp) {
+      const bool v1 = 2ll * gp + 1 < a.n_draws;
+      const uint4 r = philox4x32_10_rk(gid, (uint32_t)gp, 0u, DOM_FORECAST, a.rk);   // independent of the data: before the wait
+      mbar_wait(&s_full[st], par);
+      const unsigned char* rows = s_rows + (size_t)st * STAGE_BYTES + (size_t)tid * ROW;
+      // copy out what the cells need (lambda, tau, z), then hand the stage back: the refill does not wait for the arithmetic
+      const double lam0 = *reinterpret_cast<const double*>(rows);
+      const double2 tz0 = *reinterpret_cast<const double2*>(rows + 16);
+      double lam1 = 0.0;
+      double2 tz1 = make_double2(0.0, 0.0);
+      if (v1) {
+        lam1 = *reinterpret_cast<const double*>(rows + DRAW_BYTES);
+        tz1 = *reinterpret_cast<const double2*>(rows + DRAW_BYTES + 16);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+      // the producer refills the stage consumed one iteration ago (its readers have long moved on)
+      if (tid == 0 && !first && s_cur->left > 0) {
+        mbar_wait(&s_empty[st == 0 ? FC_STAGES - 1 : st - 1], st == 0 ? par ^ 1u : par);
+        fc_issue<NCOL>(s_cur, a, s_rows, s_full, pa, pb);
+      }
+      first = false;
+      if (++st == FC_STAGES) { st = 0; par ^= 1u; }
+      long long* xc = WRITE_X ? a.x_out + (2ll * gp) * a.N + ic : nullptr;
+      fc_quick_cell<WRITE_X>(lam0, tz0.x, tz0.y, T, T_star_f, r.x, 2u * (uint32_t)gp, (uint32_t)ic, valid, lane, q, qn, sx, sz, xc);
+      fc_quick_cell<WRITE_X>(lam1, tz1.x, tz1.y, T, T_star_f, r.z, 2u * (uint32_t)gp + 1u, (uint32_t)ic, valid && v1, lane, q, qn, sx, sz,
+                             WRITE_X ? xc + a.N : nullptr);
+      if (qn >= 32) {                        // full batches only: the remainder stays queued
+        __syncwarp();
+        const int rem = qn & 31;
+        fc_flush(q, rem, qn, g_list, g_count, g_cap, lane);
+        qn = rem;
+      }
+    }
+    __syncwarp();
+    if (qn > 0) fc_flush(q, 0, qn, g_list, g_count, g_cap, lane);
+    if (valid) {
+      if (gridDim.y == 1) {
+        sum_x[ic] = (double)sx;
+        sum_z[ic] = (double)sz;
+      } else {
+        atomicAdd(&sum_x[ic], (double)sx);
+        atomicAdd(&sum_z[ic], (double)sz);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Second pass: one thread per listed cell, the full path (screened inversion of any length, exact fp64 re-decision, PTRS)
+// on full warps.  Its x* is added to the customer's sum (integers in doubles: exact, order independent).
+template <int NCOL, bool WRITE_X>
+__global__ void __launch_bounds__(256) k_forecast_deferred(ForecastArgs a, const FcQueued* g_list, const unsigned long long* g_count,
+                                                           unsigned long long g_cap, double* sum_x) {
+  const unsigned long long n = min(*g_count, g_cap);
+  const PhiloxKey key = seed_key(a.seed);
+  for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (unsigned long long)gridDim.x * blockDim.x) {
+    const FcQueued c = g_list[e];
+    const long long ci = c.owner;
+    const double* row = a.level1 + ((long long)c.gdraw * a.N + ci) * NCOL;
+    const double Tc = a.T_cal[ci];
+    const uint32_t gid = (uint32_t)(a.gid_offset + ci);
+    const uint4 r = philox4x32_10_rk(gid, c.gdraw >> 1, 0u, DOM_FORECAST, a.rk);
+    float lamf, dtf;
+    bool al;
+    load_row_f32<NCOL>(row, Tc, lamf, dtf, al);
+    const long long x = forecast_cell(row, lamf, dtf, al, Tc, a.T_star, (float)a.T_star, (c.gdraw & 1u) ? r.z : r.x,
+                                      (c.gdraw & 1u) ? r.w : r.y, gid, c.gdraw, key);
+    if (WRITE_X) __stcs(a.x_out + (long long)c.gdraw * a.N + ci, x);
+    if (x) atomicAdd(&sum_x[ci], (double)x);
   }
 }
 
