@@ -1749,55 +1749,66 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, h->stream);
-  if (gy > 1) { cudaMemsetAsync(d_mx, 0, sizeof(double) * N, h->stream); cudaMemsetAsync(d_pa, 0, sizeof(double) * N, h->stream); }
-  // bivariate rows (32 bytes: every bulk copy is 16-byte aligned): the TMA-fed kernel; CLV_FC_KERNEL=reg selects the
-  // register-fed one (always used for the 40-byte trivariate rows)
-  static const bool use_tma = [] { const char* e = getenv("CLV_FC_KERNEL"); return !(e && std::string(e) == "reg"); }();
-  bool tma_done = false;
-  if (h->ncol == 4 && use_tma) {
-    const size_t smem = (size_t)FC_STAGES * 2 * FC_TILE * 32 + (size_t)FC_WARPS * 96 * sizeof(FcQueued) + 2 * FC_STAGES * 8 + sizeof(FcCursor);
-    const long long ntiles = (N + FC_TILE - 1) / FC_TILE;
-    const int tx = (int)std::min<long long>(ntiles, 65535);
-    const int ty = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(npairs, 64), (long long)h->sm_count * 4 * 4 / std::max(1, tx)));
-    // list of deferred cells (x* >= 8, tie zone, large means): ~3 % of the cells; capacity 1/8 of them + slack
-    const unsigned long long cap = (unsigned long long)(C * nd * N) / 8 + 65536;
+  // Two passes: the main pass takes every cell through the quick path and lists the cells that need more (x* >= 8, the tie
+  // zone, large means: ~3 %) in global memory; k_forecast_deferred works the list off on full warps.  Main pass: register-fed
+  // (default: measured faster, profiles/r02_kernel_ab.txt) or TMA-fed (CLV_FC_KERNEL=tma; bivariate 32-byte rows only:
+  // every bulk copy must be 16-byte aligned).  The list holds 1/8 of the cells; if that is ever too small the pass is
+  // repeated with a list sized for the count.
+  static const bool use_tma = [] { const char* e = getenv("CLV_FC_KERNEL"); return e && std::string(e) == "tma"; }();
+  unsigned long long cap = (unsigned long long)(C * nd * N) / 8 + 65536;
+  cudaError_t fe = cudaSuccess;
+  for (int attempt = 0; attempt < 2 && fe == cudaSuccess; ++attempt) {
     FcQueued* d_list = nullptr;
     unsigned long long* d_cnt = nullptr;
-    if (dmalloc(&d_list, (size_t)cap) == cudaSuccess && dmalloc(&d_cnt, 1) == cudaSuccess) {
-      cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), h->stream);
-      if (ty > 1 && gy <= 1) { cudaMemsetAsync(d_mx, 0, sizeof(double) * N, h->stream); cudaMemsetAsync(d_pa, 0, sizeof(double) * N, h->stream); }
-      const int gd = h->sm_count * 8;
+    fe = dmalloc(&d_list, (size_t)cap);
+    if (fe == cudaSuccess) fe = dmalloc(&d_cnt, 1);
+    if (fe != cudaSuccess) { if (d_list) dfree(d_list); break; }
+    cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), h->stream);
+    const int gd = h->sm_count * 8;
+    if (h->ncol == 4 && use_tma) {
+      const size_t smem = (size_t)FC_STAGES * 2 * FC_TILE * 32 + (size_t)FC_WARPS * 96 * sizeof(FcQueued) + 2 * FC_STAGES * 8 + sizeof(FcCursor);
+      const long long ntiles = (N + FC_TILE - 1) / FC_TILE;
+      const int tx = (int)std::min<long long>(ntiles, 65535);
+      const int ty = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(npairs, 64), (long long)h->sm_count * 4 * 4 / std::max(1, tx)));
+      if (ty > 1 || attempt > 0) { cudaMemsetAsync(d_mx, 0, sizeof(double) * N, h->stream); cudaMemsetAsync(d_pa, 0, sizeof(double) * N, h->stream); }
       if (d_x) {
         cudaFuncSetAttribute(k_forecast_tma<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_forecast_tma<4, true><<<dim3(tx, ty), FC_TILE, smem, h->stream>>>(a, d_mx, d_pa, d_list, d_cnt, cap);
-        k_forecast_deferred<4, true><<<gd, 256, 0, h->stream>>>(a, d_list, d_cnt, cap, d_mx);
       } else {
         cudaFuncSetAttribute(k_forecast_tma<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_forecast_tma<4, false><<<dim3(tx, ty), FC_TILE, smem, h->stream>>>(a, d_mx, d_pa, d_list, d_cnt, cap);
-        k_forecast_deferred<4, false><<<gd, 256, 0, h->stream>>>(a, d_list, d_cnt, cap, d_mx);
       }
-      h->launches++;
-      unsigned long long listed = 0;
-      cudaMemcpyAsync(&listed, d_cnt, sizeof listed, cudaMemcpyDeviceToHost, h->stream);
-      cudaStreamSynchronize(h->stream);
-      tma_done = cudaGetLastError() == cudaSuccess && listed <= cap;      // else: rerun below with the register-fed kernel
-      h->fc_deferred_last = listed;
     } else {
-      cudaGetLastError();
+      if (gy > 1 || attempt > 0) { cudaMemsetAsync(d_mx, 0, sizeof(double) * N, h->stream); cudaMemsetAsync(d_pa, 0, sizeof(double) * N, h->stream); }
+      if (h->ncol == 4) {
+        if (d_x) k_forecast_reduce<4, true><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa, d_list, d_cnt, cap);
+        else k_forecast_reduce<4, false><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa, d_list, d_cnt, cap);
+      } else {
+        if (d_x) k_forecast_reduce<5, true><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa, d_list, d_cnt, cap);
+        else k_forecast_reduce<5, false><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa, d_list, d_cnt, cap);
+      }
     }
-    if (d_list) dfree(d_list);
-    if (d_cnt) dfree(d_cnt);
-    // list overflow: rerun with the register-fed kernel (plain stores when gy == 1, atomics onto zeroed sums otherwise)
-    if (!tma_done && gy > 1) { cudaMemsetAsync(d_mx, 0, sizeof(double) * N, h->stream); cudaMemsetAsync(d_pa, 0, sizeof(double) * N, h->stream); }
+    if (h->ncol == 4) {
+      if (d_x) k_forecast_deferred<4, true><<<gd, 256, 0, h->stream>>>(a, d_list, d_cnt, cap, d_mx);
+      else k_forecast_deferred<4, false><<<gd, 256, 0, h->stream>>>(a, d_list, d_cnt, cap, d_mx);
+    } else {
+      if (d_x) k_forecast_deferred<5, true><<<gd, 256, 0, h->stream>>>(a, d_list, d_cnt, cap, d_mx);
+      else k_forecast_deferred<5, false><<<gd, 256, 0, h->stream>>>(a, d_list, d_cnt, cap, d_mx);
+    }
+    h->launches += 2;
+    unsigned long long listed = 0;
+    fe = cudaMemcpyAsync(&listed, d_cnt, sizeof listed, cudaMemcpyDeviceToHost, h->stream);
+    if (fe == cudaSuccess) fe = cudaStreamSynchronize(h->stream);
+    dfree(d_list); dfree(d_cnt);
+    h->fc_deferred_last = listed;
+    if (listed <= cap) break;
+    cap = listed + 65536;                         // the list was too small: once more, sized for the count
   }
-  if (tma_done) {
-    // done
-  } else if (h->ncol == 4) {
-    if (d_x) k_forecast_reduce<4, true><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa);
-    else k_forecast_reduce<4, false><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa);
-  } else {
-    if (d_x) k_forecast_reduce<5, true><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa);
-    else k_forecast_reduce<5, false><<<dim3(gx, gy), 256, 0, h->stream>>>(a, d_mx, d_pa);
+  if (fe != cudaSuccess) {
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    dfree(d_mx); dfree(d_pa);
+    if (d_x) dfree(d_x);
+    return fail(h, CLV_ERR_CUDA, "clv_forecast_resident failed: %s", cudaGetErrorString(fe));
   }
   k_scale<<<h->sm_count * 4, 256, 0, h->stream>>>(d_mx, d_pa, N, 1.0 / (double)(C * nd));
   h->launches++;

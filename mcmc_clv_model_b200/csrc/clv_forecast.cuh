@@ -260,38 +260,54 @@ __device__ __forceinline__ int poisson_quick(float mf, float uf) {
 // fp32 screen, PTRS) are DEFERRED to a per-warp queue in shared memory and worked off 32 at a time by the whole
 // warp -- full lanes for the divergent work.  Deferred results return to the owner lane through a shared array.
 constexpr int FC_WARPS = 8, FC_QCAP = 96;
-struct FcDeferred { uint32_t gdraw, owner, ua, ub; };
+struct FcQueued { uint32_t gdraw, owner; };      // a deferred cell: global draw index, customer (index within the shard)
 
-// one deferred cell on its own lane: the full path (screened inversion of any length, exact fp64 re-decision, PTRS).
-// Out of line (the hot loop keeps its registers), arguments by value (no local copy of the kernel's parameter struct).
-template <int NCOL, bool WRITE_X>
-__device__ __noinline__ long long fc_deferred_cell(const double* level1, const double* T_cal, long long N, long long gid_offset,
-                                                   double T_star, long long* x_out, FcDeferred e, long long ci, PhiloxKey key) {
-  const double* row = level1 + ((long long)e.gdraw * N + ci) * NCOL;
-  const double Tc = T_cal[ci];
-  float lamf, dtf;
-  bool al;
-  load_row_f32<NCOL>(row, Tc, lamf, dtf, al);
-  const long long x = forecast_cell(row, lamf, dtf, al, Tc, T_star, (float)T_star, e.ua, e.ub, (uint32_t)(gid_offset + ci), e.gdraw, key);
-  if (WRITE_X) __stcs(x_out + (long long)e.gdraw * N + ci, x);
-  return x;
+// quick path of one cell; a cell that needs more is queued (qn and the queue belong to the warp)
+template <bool WRITE_X>
+__device__ __forceinline__ void fc_quick_cell(float lamf, float dtf, bool alive, float T_star_f, uint32_t ua, uint32_t gdraw,
+                                              uint32_t cust, bool live, int lane, FcQueued* q, int& qn, int& sx, int& sz, long long* x_cell) {
+  const float hf = alive ? T_star_f : fminf(fmaxf(dtf, 0.0f), T_star_f);
+  const float mf = lamf * hf;
+  const int k = (mf < 24.0f) ? poisson_quick(mf, u24f(ua)) : -1;       // beyond ~24 the first 8 terms almost never decide
+  const bool defer = live && k < 0;
+  const unsigned m = __ballot_sync(0xffffffffu, defer);
+  if (defer) q[qn + __popc(m & ((1u << lane) - 1u))] = FcQueued{gdraw, cust};
+  qn += __popc(m);
+  if (live && k > 0) sx += k;
+  if (live && alive) ++sz;
+  if (WRITE_X && live && k >= 0) __stcs(x_cell, (long long)k);
+}
+
+// The warp moves q[first .. last) to the global list of deferred cells: one atomicAdd per batch, coalesced 8-byte stores.
+// Entries beyond the list's capacity are dropped and counted: the host then sizes the list for the count and reruns.
+__device__ __forceinline__ void fc_flush(const FcQueued* q, int first, int last, FcQueued* g_list, unsigned long long* g_count,
+                                         unsigned long long cap, int lane) {
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(g_count, (unsigned long long)(last - first));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (int b = first + lane; b < last; b += 32) {
+    const unsigned long long pos = base + (unsigned long long)(b - first);
+    if (pos < cap) g_list[pos] = q[b];
+  }
+  __syncwarp();
 }
 
 #ifndef CLV_FC_MINBLOCKS
 #define CLV_FC_MINBLOCKS 6
 #endif
+// Register-fed main pass: one thread per customer, the two rows of a draw pair in flight in registers.  No function
+// call in the kernel (cells that need more than the quick path go to the global list for k_forecast_deferred).
 template <int NCOL, bool WRITE_X>
-__global__ void __launch_bounds__(256, CLV_FC_MINBLOCKS) k_forecast_reduce(ForecastArgs a, double* sum_x, double* sum_z) {
-  __shared__ FcDeferred s_q[FC_WARPS][FC_QCAP];
-  __shared__ unsigned long long s_dx[FC_WARPS][32];
-  const PhiloxKey key = seed_key(a.seed);
+__global__ void __launch_bounds__(256, CLV_FC_MINBLOCKS) k_forecast_reduce(ForecastArgs a, double* sum_x, double* sum_z, FcQueued* g_list,
+                                                                          unsigned long long* g_count, unsigned long long g_cap) {
+  __shared__ FcQueued s_q[FC_WARPS][FC_QCAP];
   const float T_star_f = (float)a.T_star;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int npairs = (int)((a.n_draws + 1) >> 1);
   const int per = (npairs + gridDim.y - 1) / gridDim.y;
   const int pa = blockIdx.y * per, pb = min(npairs, pa + per);
   const long long stride = a.N * NCOL;                 // doubles between consecutive draws of one customer
-  FcDeferred* q = s_q[warp];
+  FcQueued* q = s_q[warp];
   const long long nwt = (a.N + 31) / 32;               // warp tiles of 32 consecutive customers
   for (long long wt = (long long)blockIdx.x * FC_WARPS + warp; wt < nwt; wt += (long long)gridDim.x * FC_WARPS) {
     const long long i = wt * 32 + lane;
@@ -299,32 +315,7 @@ __global__ void __launch_bounds__(256, CLV_FC_MINBLOCKS) k_forecast_reduce(Forec
     const long long ic = valid ? i : a.N - 1;          // out-of-range lanes shadow the last customer (results dropped)
     const double T = a.T_cal[ic];
     const uint32_t gid = (uint32_t)(a.gid_offset + ic);
-    long long sx = 0;
-    int sz = 0, qn = 0;                                // qn: queue length (warp uniform)
-    s_dx[warp][lane] = 0ull;
-    __syncwarp();
-    // the warp works off 32 deferred cells: one cell per lane, the full (screened, then exact / PTRS) path
-    auto drain = [&](int count) {
-      if (lane < count) {
-        const FcDeferred e = q[qn - count + lane];
-        const long long x = fc_deferred_cell<NCOL, WRITE_X>(a.level1, a.T_cal, a.N, a.gid_offset, a.T_star, a.x_out, e, wt * 32 + e.owner, key);
-        if (x) atomicAdd(&s_dx[warp][e.owner], (unsigned long long)x);
-      }
-      __syncwarp();
-      qn -= count;
-    };
-    auto cell = [&](float lamf, float dtf, bool alive, uint32_t ua, uint32_t ub, uint32_t gdraw, bool present) {
-      const float hf = alive ? T_star_f : fminf(fmaxf(dtf, 0.0f), T_star_f);
-      const float mf = lamf * hf;
-      int k = (mf < 24.0f) ? poisson_quick(mf, u24f(ua)) : -1;        // beyond ~24 the first 8 terms almost never decide
-      const bool defer = present && valid && k < 0;
-      if (!present || !valid) k = 0;
-      const unsigned m = __ballot_sync(0xffffffffu, defer);
-      if (defer) q[qn + __popc(m & ((1u << lane) - 1u))] = FcDeferred{gdraw, (uint32_t)lane, ua, ub};
-      qn += __popc(m);
-      if (k > 0) sx += k;
-      if (WRITE_X && present && valid && k >= 0) __stcs(a.x_out + (long long)gdraw * a.N + i, (long long)k);
-    };
+    int sx = 0, sz = 0, qn = 0;                        // quick-path counts are < 8 per cell; qn: queue length (warp uniform)
     const double* row = a.level1 + (2ll * pa * a.N + ic) * NCOL;
     for (int gp = pa; gp < pb; ++gp, row += 2 * stride) {
       const bool v1 = 2ll * gp + 1 < a.n_draws;        // only the very last pair can be half empty
@@ -333,14 +324,19 @@ __global__ void __launch_bounds__(256, CLV_FC_MINBLOCKS) k_forecast_reduce(Forec
       load_row_f32<NCOL>(row, T, lam0, dt0, al0);        // both rows in flight before the arithmetic starts
       if (v1) load_row_f32<NCOL>(row + stride, T, lam1, dt1, al1);
       const uint4 r = philox4x32_10_rk(gid, (uint32_t)gp, 0u, DOM_FORECAST, a.rk);
-      sz += (al0 ? 1 : 0) + (al1 ? 1 : 0);
-      cell(lam0, dt0, al0, r.x, r.y, 2u * (uint32_t)gp, true);
-      cell(lam1, dt1, al1, r.z, r.w, 2u * (uint32_t)gp + 1u, v1);
-      __syncwarp();
-      while (qn >= 32) drain(32);
+      long long* xc = WRITE_X ? a.x_out + (2ll * gp) * a.N + ic : nullptr;
+      fc_quick_cell<WRITE_X>(lam0, dt0, al0, T_star_f, r.x, 2u * (uint32_t)gp, (uint32_t)ic, valid, lane, q, qn, sx, sz, xc);
+      fc_quick_cell<WRITE_X>(lam1, dt1, al1, T_star_f, r.z, 2u * (uint32_t)gp + 1u, (uint32_t)ic, valid && v1, lane, q, qn, sx, sz,
+                             WRITE_X ? xc + a.N : nullptr);
+      if (qn >= 32) {                                    // full batches only: the remainder stays queued
+        __syncwarp();
+        const int rem = qn & 31;
+        fc_flush(q, rem, qn, g_list, g_count, g_cap, lane);
+        qn = rem;
+      }
     }
-    if (qn > 0) drain(qn);
-    sx += (long long)s_dx[warp][lane];
+    __syncwarp();
+    if (qn > 0) fc_flush(q, 0, qn, g_list, g_count, g_cap, lane);
     if (valid) {
       if (gridDim.y == 1) {
         sum_x[i] = (double)sx;
@@ -392,8 +388,6 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-struct FcQueued { uint32_t gdraw, owner; };
-
 // Producer-side cursor over the loads of a block: tiles blockIdx.x, blockIdx.x + gridDim.x, ..., pairs pa .. pb-1 of each, in
 // consumption order; load number n goes to stage n % FC_STAGES.  It lives in SHARED memory and only thread 0 touches it:
 // the hot loop carries none of it in registers.
@@ -416,37 +410,6 @@ __device__ __forceinline__ void fc_issue(FcCursor* c, const ForecastArgs& a, uns
   c->left -= 1;
   if (gp + 1 == pb) { c->gp = pa; c->tile += (int)gridDim.x; } else c->gp = gp + 1;
   c->st = (st + 1 == FC_STAGES) ? 0 : st + 1;
-}
-
-// quick path of one cell; a cell that needs more is queued (qn and the queue belong to the warp)
-template <bool WRITE_X>
-__device__ __forceinline__ void fc_quick_cell(double lam, double tau, double zf, double T, float T_star_f, uint32_t ua, uint32_t gdraw,
-                                              uint32_t cust, bool live, int lane, FcQueued* q, int& qn, int& sx, int& sz, long long* x_cell) {
-  const bool alive = zf > 0.5;
-  const float hf = alive ? T_star_f : fminf(fmaxf((float)(tau - T), 0.0f), T_star_f);
-  const float mf = (float)lam * hf;
-  const int k = (mf < 24.0f) ? poisson_quick(mf, u24f(ua)) : -1;
-  const bool defer = live && k < 0;
-  const unsigned m = __ballot_sync(0xffffffffu, defer);
-  if (defer) q[qn + __popc(m & ((1u << lane) - 1u))] = FcQueued{gdraw, cust};
-  qn += __popc(m);
-  if (live && k > 0) sx += k;
-  if (live && alive) ++sz;
-  if (WRITE_X && live && k >= 0) __stcs(x_cell, (long long)k);
-}
-
-// The warp moves q[first .. last) to the global list of deferred cells: one atomicAdd per batch, coalesced 8-byte stores.
-// Entries beyond the list's capacity are dropped and counted: the host then reruns the forecast with the register-fed kernel.
-__device__ __forceinline__ void fc_flush(const FcQueued* q, int first, int last, FcQueued* g_list, unsigned long long* g_count,
-                                         unsigned long long cap, int lane) {
-  unsigned long long base = 0;
-  if (lane == 0) base = atomicAdd(g_count, (unsigned long long)(last - first));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  for (int b = first + lane; b < last; b += 32) {
-    const unsigned long long pos = base + (unsigned long long)(b - first);
-    if (pos < cap) g_list[pos] = q[b];
-  }
-  __syncwarp();
 }
 
 // Main pass: every cell's quick path; cells that need more are listed in global memory for k_forecast_deferred.
@@ -512,9 +475,10 @@ __global__ void __launch_bounds__(FC_TILE, NCOL == 4 ? 4 : 3) k_forecast_tma(For
       first = false;
       if (++st == FC_STAGES) { st = 0; par ^= 1u; }
       long long* xc = WRITE_X ? a.x_out + (2ll * gp) * a.N + ic : nullptr;
-      fc_quick_cell<WRITE_X>(lam0, tz0.x, tz0.y, T, T_star_f, r.x, 2u * (uint32_t)gp, (uint32_t)ic, valid, lane, q, qn, sx, sz, xc);
-      fc_quick_cell<WRITE_X>(lam1, tz1.x, tz1.y, T, T_star_f, r.z, 2u * (uint32_t)gp + 1u, (uint32_t)ic, valid && v1, lane, q, qn, sx, sz,
-                             WRITE_X ? xc + a.N : nullptr);
+      fc_quick_cell<WRITE_X>((float)lam0, (float)(tz0.x - T), tz0.y > 0.5, T_star_f, r.x, 2u * (uint32_t)gp, (uint32_t)ic, valid, lane, q, qn,
+                             sx, sz, xc);
+      fc_quick_cell<WRITE_X>((float)lam1, (float)(tz1.x - T), tz1.y > 0.5, T_star_f, r.z, 2u * (uint32_t)gp + 1u, (uint32_t)ic, valid && v1,
+                             lane, q, qn, sx, sz, WRITE_X ? xc + a.N : nullptr);
       if (qn >= 32) {                        // full batches only: the remainder stays queued
         __syncwarp();
         const int rem = qn & 31;

