@@ -1754,8 +1754,10 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
   // (default: measured faster, profiles/r02_kernel_ab.txt) or TMA-fed (CLV_FC_KERNEL=tma; bivariate 32-byte rows only:
   // every bulk copy must be 16-byte aligned).  The list holds 1/8 of the cells; if that is ever too small the pass is
   // repeated with a list sized for the count.
-  static const bool use_tma = [] { const char* e = getenv("CLV_FC_KERNEL"); return e && std::string(e) == "tma"; }();
+  const char* fck = getenv("CLV_FC_KERNEL");
+  const bool use_tma = fck && std::string(fck) == "tma";
   unsigned long long cap = (unsigned long long)(C * nd * N) / 8 + 65536;
+  if (const char* e = getenv("CLV_FC_LIST_CAP")) cap = (unsigned long long)std::max(1ll, atoll(e));   // test hook: force the retry
   cudaError_t fe = cudaSuccess;
   for (int attempt = 0; attempt < 2 && fe == cudaSuccess; ++attempt) {
     FcQueued* d_list = nullptr;

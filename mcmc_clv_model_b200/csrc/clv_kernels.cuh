@@ -494,8 +494,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArg
   for (int t = tid; t < EXP_N; t += SWEEP_THREADS) s_tab[t] = c_exptab[t];
   for (int t = tid; t < NSTAT_MAX + 1; t += SWEEP_THREADS) s_acc[t] = 0ull;
   clear_stats(s_priv, nstat);
+  // a peer rank stopped (flag raised by an EARLIER level-2 kernel): do not sample on partial sums.  Read before the wait, off
+  // the critical path; the sweep right after the failed exchange still runs, on the unchanged parameters of the sweep before
+  const bool peer_stopped = a.error_flag && *(volatile const int*)a.error_flag == 2;
   pdl_wait();                                   // (beta, Sigma) of this sweep and the state of the previous one are complete
-  if (a.error_flag && *(volatile const int*)a.error_flag == 2) return;   // a peer rank stopped: do not sample on partial sums
+  if (peer_stopped) return;
   for (int t = tid; t < K * D; t += SWEEP_THREADS) s_beta[t] = cp.beta[t];
   __syncthreads();
   const uint32_t c3 = dom_word(DOM_SAMPLER, a.chain_offset + (uint32_t)chain);
@@ -1013,9 +1016,10 @@ __device__ __forceinline__ void level2_chain(const Level2Args& a, int chain, int
                      a.injected ? a.iw_norm + chain * ntril : nullptr, a.injected ? a.iw_chi2 + chain * D : nullptr,
                      a.injected ? a.beta_norm + chain * D * K : nullptr, lane);
   // ---- the statistics of the sweep kernel ------------------------------------------------------------------------------
+  const bool peer_stopped = *(volatile int*)a.error_flag == 2;   // raised by an earlier exchange; read off the critical path
   pdl_wait();
   if (!a.pdl_early) pdl_launch_dependents();
-  if (*(volatile int*)a.error_flag == 2) return;          // a peer stopped: leave the state as it is
+  if (peer_stopped) return;                               // a peer stopped: leave the state as it is
   if (a.world <= 1) {
     for (int t = lane; t < nstat; t += 32) {
       unsigned long long* p = &a.acc[chain * NSTAT_MAX + t];

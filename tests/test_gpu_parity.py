@@ -818,3 +818,25 @@ def test_fused_forecast_equals_forecast_of_the_stored_draws(cdnow_abe, D):
     xs, _ = _forecast(d["T_cal"][:n], list(out["level_1"]), 39.0, 77, False, 0.5)
     np.testing.assert_allclose(fused["mean_x_star"], xs.mean(axis=0), rtol=1e-13)
     assert res["x_star"][:, 7].min() > 60 and np.isfinite(fused2["mean_x_star"]).all()
+
+
+def test_resident_forecast_list_overflow_is_repeated_with_a_larger_list(cdnow_abe, monkeypatch):
+    """The two-pass resident forecast lists the cells that need more than the quick path; when the list is too small the
+    pass is repeated with one sized for the count (CLV_FC_LIST_CAP forces that here) -- same result."""
+    d = cdnow_abe
+    n = 2000
+    with Sampler(d["x"][:n], d["t_x"][:n], d["T_cal"][:n], np.ones((n, 1)), chains=2, seed=3) as s:
+        s.run_resident(30, 40, 1)
+        ref = s.forecast_resident(T_star=39.0, seed=9, want_x_star=True)
+        monkeypatch.setenv("CLV_FC_LIST_CAP", "7")
+        small = s.forecast_resident(T_star=39.0, seed=9, want_x_star=True)
+        monkeypatch.delenv("CLV_FC_LIST_CAP")
+        monkeypatch.setenv("CLV_FC_KERNEL", "tma")          # the TMA-fed main pass (cp.async.bulk ring): same x*
+        again = s.forecast_resident(T_star=39.0, seed=9, want_x_star=True)
+        monkeypatch.setenv("CLV_FC_LIST_CAP", "7")
+        again_small = s.forecast_resident(T_star=39.0, seed=9, want_x_star=True)
+    for k in ("mean_x_star", "p_alive", "x_star"):
+        np.testing.assert_array_equal(small[k], ref[k])
+        np.testing.assert_array_equal(again[k], ref[k])
+        np.testing.assert_array_equal(again_small[k], ref[k])
+    assert ref["x_star"].max() >= 8                          # some cells did take the second pass

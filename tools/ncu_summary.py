@@ -8,16 +8,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_md = os.path.join(ROOT, "profiles", f"{tag}_sweep_ncu_summary.md")
 out_js = os.path.join(ROOT, "profiles", f"{tag}_sweep_metrics.json")
 
-rows = list(csv.reader(l for l in open(launches) if not l.startswith("==")))
-hdr = rows[0]
-ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 agg = collections.OrderedDict()
-for r in rows[1:]:
-    if len(r) > vi:
-        agg.setdefault(re.sub(r"\(.*", "", r[ki]), []).append(float(r[vi].replace(",", "")))
+if os.path.exists(launches):
+    rows = list(csv.reader(l for l in open(launches) if not l.startswith("==")))
+    hdr = rows[0]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    for r in rows[1:]:
+        if len(r) > vi:
+            agg.setdefault(re.sub(r"\(.*", "", r[ki]), []).append(float(r[vi].replace(",", "")))
 STEP = ("k_sweep", "k_level2", "k_persistent")          # the kernels of one Gibbs sweep
 ONCE = ("k_split_columns", "k_init_quantities", "k_init_state", "k_derive_params", "k_stats_only")   # once per data set
-tot = sum(sum(v) for k, v in agg.items() if any(t in k for t in STEP))
+tot = sum(sum(v) for k, v in agg.items() if any(t in k for t in STEP)) or 1.0
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 r = list(csv.reader(io.StringIO(raw)))
