@@ -582,10 +582,14 @@ def forecast_block(args, local, peak):
     gbs = cells * 32 / (best * 1e-3) / 1e9                                  # one 32-byte level-1 row per cell
     forecast = {"config": f"C5: {nf} synthetic customers x {nd} posterior draws (kept by the sampler, resident in HBM: "
                           f"{cells * 32 / 1e9:.0f} GB), T_star=39",
-                "cells_per_sec": cells / (best * 1e-3), "kernel_ms": best, "kernel": "k_forecast_reduce<4>",
+                "cells_per_sec": cells / (best * 1e-3), "kernel_ms": best,
+                "kernel": "k_forecast_reduce<4> (every cell's quick path) + k_forecast_deferred<4> (the ~6 % of cells that need more) + k_scale",
                 "sampling_s": t_sample,
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                             "algorithmic_bytes_per_cell": 32},
+                             "algorithmic_bytes_per_cell": 32,
+                             # ncu --set full (profiles/r02_forecast_ncu_summary.md): 6.444 + 0.508 GB read, 0.016 GB written per 2e8 cells
+                             "traffic": cells * (6.443752e9 + 0.508303e9 + 0.0158e9) / 2e8,
+                             "traffic_source": "profiles/r02_forecast_ncu_summary.md (dram bytes per cell of both passes x cells)"},
                 "mean_x_star": float(fr["mean_x_star"].mean()), "mean_p_alive": float(fr["p_alive"].mean()),
                 "holdout_mean_x_star_generated": float(fc["x_star"].mean())}
     # the API path of draw_future_transactions (SURVEY 8d, C5 ii): host (n_draws, N, 4) f64 in, host (n_draws, N)
