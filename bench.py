@@ -360,7 +360,7 @@ def run_ours(args):
     peak, which = _peaks()
     hbm_gbs = BYTES_PER_UPDATE * n_loc / (k_ms * 1e-3) / 1e9
     roofline_hbm = {"bound": "hbm", "achieved": hbm_gbs, "peak": peak, "unit": "GB/s", "frac": hbm_gbs / peak,
-                    "traffic": None, "peak_source": which, "kernel": "k_sweep<2,FAST>", "kernel_ms": k_ms,
+                    "traffic": None, "peak_source": which, "kernel": "k_sweep2<2,FAST> (two customers per thread)", "kernel_ms": k_ms,
                     "algorithmic_bytes_per_customer_update": BYTES_PER_UPDATE,
                     "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * n_loc,
                     "note": "secondary roof: the sweep kernel is not HBM bound (see `roofline`)"}
@@ -378,7 +378,8 @@ def run_ours(args):
     smc = torch.cuda.get_device_properties(local).multi_processor_count
     mhz = clk.summary()["sm_mhz"] or 1965.0
     peak_issue = smc * 4 * mhz * 1e6                       # one warp-instruction per scheduler per clock
-    roofline = {"bound": "issue", "kernel": "k_sweep<2,FAST>", "kernel_ms": k_ms, "unit": "warp-inst/s", "peak": peak_issue,
+    kname = (pj or {}).get("kernel", "k_sweep2<2,FAST>").replace("void ", "").replace("(SweepArgs)", "")
+    roofline = {"bound": "issue", "kernel": kname, "kernel_ms": k_ms, "unit": "warp-inst/s", "peak": peak_issue,
                 "peak_source": f"{smc} SMs x 4 schedulers x {mhz:.0f} MHz (SM clock sampled in the timed region)",
                 "kernel_share_of_step": (sweep_ms / max(ms_ev, 1e-9)) if world == 1 else sweep_ms / max(sweep_ms + l2_ms, 1e-9),
                 "level2_kernel_us": 1e3 * l2_ms / max(n_timed, 1), "achieved": None, "frac": None, "traffic": roofline_hbm["traffic"]}

@@ -474,6 +474,194 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
   if (keep && valid) s_priv[(K * D + D * (D + 1) / 2) * SWEEP_THREADS + tid] += to_fx(lik, mc.ll_scale);
 }
 
+// ---- two customers per thread ---------------------------------------------------------------------------------------------
+// The Metropolis loop is a chain of dependent instructions per customer (Philox rounds, SFU, fp64 exp, accept) and the
+// sweep kernel issues on only ~68 % of its scheduler slots with the 8 warps per scheduler that 64 registers allow
+// (stalls: fixed-latency `wait`, pipe throttles).  sweep_tile2 gives every thread TWO independent customers (i and
+// i + 128 of a 256-customer tile) and walks them through the steps together, so each warp carries two independent
+// instruction streams for the scheduler to interleave.  Per customer the arithmetic is exactly sweep_tile's (same
+// functions, same order), so chains are bit-identical whichever variant runs.  Philox modes only (FAST / STRICT).
+template <int D, int MODE>
+struct Cust2 {
+  double ll, lm, cur, xd, omz, Tz, m0, m1, m2, tau, zf;
+  uint32_t gid;
+  long long i;
+  bool valid;
+};
+
+template <int D, int MODE>
+__device__ __forceinline__ void cust_begin(Cust2<D, MODE>& c, const SweepArgs& a, const ModelConst& mc, const double* s_beta,
+                                           const double* s_tab, const SweepStep& sw, long long cN, long long i, uint32_t c3,
+                                           double h00, double h01, double h11) {
+  const int K = mc.K;
+  const long long N = mc.N;
+  c.valid = i < N;
+  c.i = c.valid ? i : N - 1;                 // a lane beyond the end shadows the last customer; nothing of it is stored
+  c.gid = (uint32_t)(mc.gid_offset + c.i);
+  c.xd = (double)a.x[c.i];
+  const double tx = a.t_x[c.i], T = a.T_cal[c.i];
+  c.ll = a.ll[cN + c.i];
+  c.lm = a.lm[cN + c.i];
+  c.m0 = s_beta[0]; c.m1 = s_beta[1]; c.m2 = (D == 3) ? s_beta[2] : 0.0;
+  for (int k = 1; k < K; ++k) {
+    const double xk = a.Xc[(long long)(k - 1) * N + c.i];
+    c.m0 = fma(xk, s_beta[k * D + 0], c.m0);
+    c.m1 = fma(xk, s_beta[k * D + 1], c.m1);
+    if (D == 3) c.m2 = fma(xk, s_beta[k * D + 2], c.m2);
+  }
+  const double lam = exp_tab(c.ll, s_tab), mu = exp_tab(c.lm, s_tab);
+  const uint4 r = philox4x32_10_rk(c.gid, sw.sweep, 0u, c3, a.rk);
+  const double uz = u53(r.x, r.y), ut = u53(r.z, r.w);
+  const double ml = mu + lam;
+  const double e = exp_any(-(ml * (T - tx)), s_tab);
+  const double pa = (ml * e) / (ml * e + mu * (1.0 - e));
+  const bool alive = uz < pa;
+  const double mtx = fmin(700.0, ml * tx), mT = fmin(700.0, ml * T);
+  const double mix = (1.0 - ut) * exp_tab(-mtx, s_tab) + ut * exp_tab(-mT, s_tab);
+  const double lg = -log(alive ? ut : mix);
+  c.tau = (alive ? T : 0.0) + lg / (alive ? mu : ml);
+  c.zf = alive ? 1.0 : 0.0;
+  c.omz = 1.0 - c.zf;
+  c.Tz = alive ? T : c.tau;
+  c.cur = log_post(c.ll, c.lm, c.xd, c.omz, c.Tz, c.m0, c.m1, h00, h01, h11, s_tab);
+}
+
+template <int D, int MODE>
+__device__ __forceinline__ void cust_end(Cust2<D, MODE>& c, const SweepArgs& a, const ModelConst& mc, const ChainParams& cp,
+                                         const double* s_tab, long long* s_priv, const SweepStep& sw, int chain, long long cN, uint32_t c3) {
+  const int K = mc.K, S = mc.S;
+  const long long N = mc.N;
+  double le = 0.0, lik = 0.0;
+  if (c.valid) {
+    a.ll[cN + c.i] = c.ll;
+    a.lm[cN + c.i] = c.lm;
+    if (D == 3) {
+      double n, ns;
+      normal_pair_u53(philox4x32_10_rk(c.gid, sw.sweep, 1u + 2u * (uint32_t)S, c3, a.rk), &n, &ns);
+      const double post_mean = cp.eta_post_var * (a.log_s[c.i] / mc.omega2 + c.m2 / cp.Sigma[8]);
+      le = post_mean + cp.eta_sd * n;
+      a.le[cN + c.i] = le;
+    }
+    if (sw.store_zt) {
+      a.z[cN + c.i] = c.zf;
+      a.tau[cN + c.i] = c.tau;
+    }
+    if (sw.keep) {
+      const double lam_n = exp_tab(c.ll, s_tab), mu_n = exp_tab(c.lm, s_tab);
+      constexpr int NC = (D == 2) ? 4 : 5;
+      if (sw.draws) {
+        double* o = sw.draws + (((long long)chain * sw.chunk_cap + sw.slot) * N + c.i) * NC;
+        if (D == 2) {
+          reinterpret_cast<double2*>(o)[0] = make_double2(lam_n, mu_n);
+          reinterpret_cast<double2*>(o)[1] = make_double2(c.tau, c.zf);
+        } else {
+          o[0] = lam_n; o[1] = mu_n; o[2] = c.tau; o[3] = c.zf; o[4] = exp(le);
+        }
+      }
+      lik = c.xd * c.ll + c.omz * c.lm - (lam_n + mu_n) * c.Tz;
+      lik = fmin(fmax(lik, -1048576.0), 1048576.0);
+    }
+  }
+  accumulate_stats<D>(mc, a.Xc, N, c.i, c.valid, c.ll - mc.center[0], c.lm - mc.center[1], (D == 3) ? le - mc.center[2] : 0.0, s_priv);
+  if (sw.keep && c.valid) s_priv[(K * D + D * (D + 1) / 2) * SWEEP_THREADS + threadIdx.x] += to_fx(lik, mc.ll_scale);
+}
+
+template <int D, int MODE>
+__device__ __forceinline__ void sweep_tile2(const SweepArgs& a, const ModelConst& mc, const ChainParams& cp, const double* s_beta,
+                                            const double* s_tab, long long* s_priv, const SweepStep& sw, int chain, long long tile,
+                                            uint32_t c3) {
+  static_assert(MODE != MODE_INJECT, "two customers per thread: Philox modes only");
+  const int S = mc.S;
+  const long long cN = (long long)chain * mc.N;
+  const double h00 = -0.5 * cp.P00, h01 = -cp.P01, h11 = -0.5 * cp.P11;
+  const double t3s = (MODE == MODE_FAST) ? 1.7320508075688772 : 1.0;
+  const double s_l = cp.Sigma[0] * t3s, s_m = cp.Sigma[D + 1] * t3s;
+  Cust2<D, MODE> c[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    cust_begin<D, MODE>(c[j], a, mc, s_beta, s_tab, sw, cN, tile * (2 * SWEEP_THREADS) + j * SWEEP_THREADS + threadIdx.x, c3, h00, h01, h11);
+  uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(s_tab);
+  asm volatile("" : "+r"(tab_addr));
+  for (int s = 0; s < S; ++s) {
+    double pl[2], pm[2], prop[2];
+    uint32_t ur[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint4 A = philox4x32_10_rk(c[j].gid, sw.sweep, 1u + (uint32_t)s, c3, a.rk);
+      double tl, tm;
+      if (MODE == MODE_STRICT) {
+        tl = t3_strict(A.x, A.y);
+        tm = t3_strict(A.z, A.w);
+      } else {
+        tl = (double)t3_fast(A.x, A.y);
+        tm = (double)t3_fast(A.z, A.w);
+      }
+      ur[j] = low_bytes(A.x, A.y, A.z, A.w);
+      pl[j] = c[j].ll + s_l * tl;
+      pm[j] = c[j].lm + s_m * tm;
+    }
+    clip70_pair(pl[0], pm[0]);
+    clip70_pair(pl[1], pm[1]);
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      prop[j] = log_post_open(pl[j], pm[j], c[j].xd, c[j].omz, c[j].Tz, c[j].m0, c[j].m1, h00, h01, h11, tab_addr);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t u = ur[j];
+      const bool admissible = !(pm[j] > 5.0);
+      if (mh_accept<false>(prop[j] - c[j].cur, u32f(u), [&]() { return u32d(u); }) && admissible) {
+        c[j].ll = pl[j];
+        c[j].lm = pm[j];
+        c[j].cur = prop[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) cust_end<D, MODE>(c[j], a, mc, cp, s_tab, s_priv, sw, chain, cN, c3);
+}
+
+// the sweep kernel with two customers per thread (tiles of 256 customers)
+#ifndef CLV_MINBLOCKS2
+#define CLV_MINBLOCKS2 5
+#endif
+template <int D, int MODE>
+__global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS2) k_sweep2(SweepArgs a) {
+  extern __shared__ long long s_priv[];          // [(nstat + 1)][SWEEP_THREADS]
+  __shared__ double s_beta[MAXK * MAXD];
+  __shared__ double s_tab[EXP_N];
+  __shared__ unsigned long long s_acc[NSTAT_MAX + 1];
+  const ModelConst& mc = *a.mc;
+  const int chain = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int K = mc.K;
+  const int nstat = K * D + D * (D + 1) / 2;
+  const ChainParams& cp = a.params[chain];
+  if (a.pdl_early) pdl_launch_dependents();
+  for (int t = tid; t < EXP_N; t += SWEEP_THREADS) s_tab[t] = c_exptab[t];
+  for (int t = tid; t < NSTAT_MAX + 1; t += SWEEP_THREADS) s_acc[t] = 0ull;
+  clear_stats(s_priv, nstat);
+  const bool peer_stopped = a.error_flag && *(volatile const int*)a.error_flag == 2;
+  pdl_wait();
+  if (peer_stopped) return;
+  for (int t = tid; t < K * D; t += SWEEP_THREADS) s_beta[t] = cp.beta[t];
+  __syncthreads();
+  const uint32_t c3 = dom_word(DOM_SAMPLER, a.chain_offset + (uint32_t)chain);
+  SweepStep sw;
+  sw.sweep = a.sweep; sw.keep = a.slot >= 0; sw.store_zt = a.store_zt; sw.slot = a.slot; sw.chunk_cap = a.chunk_cap;
+  sw.draws = a.draws; sw.draw_index = a.draw_index;
+  const long long ntiles = (mc.N + 2 * SWEEP_THREADS - 1) / (2 * SWEEP_THREADS);
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    sweep_tile2<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, c3);
+  if (!a.pdl_early) pdl_launch_dependents();
+  flush_stats(s_priv, s_acc, nstat, sw.keep != 0);
+  __syncthreads();
+  for (int t = tid; t < nstat; t += SWEEP_THREADS)
+    if (s_acc[t]) atomicAdd(&a.acc[chain * NSTAT_MAX + t], s_acc[t]);
+  if (sw.keep && tid == 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(&a.loglik_acc[chain * a.loglik_stride + a.draw_index]),
+              s_acc[NSTAT_MAX]);
+}
+
 // FUSE_FC: the instantiation that also simulates x* of a kept draw (clv_set_fused_forecast).  A separate instantiation, so
 // that the out-of-line call in the keep branch costs the ordinary sweep kernel no register (it put a spill reload into
 // the Metropolis loop when it was a run-time option).

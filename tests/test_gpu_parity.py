@@ -601,9 +601,9 @@ def _device_fast_variates(seed, n, S):
     return variates
 
 
-@pytest.mark.parametrize("mode", ["stream", "persistent"])
+@pytest.mark.parametrize("mode", ["stream", "stream2", "persistent"])
 @pytest.mark.parametrize("D,cov", [(2, ["first_sales_scaled"]), (3, ["gender_F", "age_scaled"])])
-def test_fast_kernel_trajectory_vs_oracle_at_full_cdnow_size(cdnow_full, D, cov, mode):
+def test_fast_kernel_trajectory_vs_oracle_at_full_cdnow_size(cdnow_full, D, cov, mode, monkeypatch):
     """The TIMED kernel (rng="fast": fp32 SFU proposal variates, fp32-screened accept) at the size of BASELINE.json
     configs[1] / configs[2] (23 570 customers = 185 tiles; C2: K=2 bivariate, C3: K=3 trivariate): its FAST variates
     are pulled from the device and replayed through the oracle, and the whole production trajectory (z, tau, 20
@@ -616,13 +616,33 @@ def test_fast_kernel_trajectory_vs_oracle_at_full_cdnow_size(cdnow_full, D, cov,
     ora = ao.run_chain(cbs, ao.default_hyper(cbs.K, D),
                        PhiloxStreams(seed, 0, np.arange(n), S, D, cbs.K, level1_variates=_device_fast_variates(seed, n, S)),
                        mcmc=mcmc, burnin=burnin, thin=thin, D=D, n_mh_steps=S)
+    # "stream2": the sweep kernel with two customers per thread (k_sweep2; the default once customers x chains >= 100 000,
+    # i.e. the kernel bench.py times), forced here; "stream": one customer per thread (the default at this size)
+    monkeypatch.setenv("CLV_SWEEP_CPT", "2" if mode == "stream2" else "1")
     with Sampler(cbs.x, cbs.t_x, cbs.T_cal, X, cbs.log_s, model_dim=D, chains=1, n_mh_steps=S, seed=seed, rng="fast",
-                 sweep_mode=mode) as s:
+                 sweep_mode="stream" if mode == "stream2" else mode) as s:
         out = s.run(burnin, mcmc, thin)
     np.testing.assert_array_equal(out["level_1"][0][:, :, 3], ora["level_1"][:, :, 3])
     np.testing.assert_allclose(out["level_1"][0], ora["level_1"], rtol=RTOL)
     np.testing.assert_allclose(out["level_2"][0], ora["level_2"], rtol=RTOL, atol=1e-9)
     np.testing.assert_allclose(out["loglik_sum"][0] / n, ora["log_likelihood"], rtol=RTOL)
+
+
+def test_one_and_two_customers_per_thread_give_the_same_chain(cdnow_full, monkeypatch):
+    """k_sweep (one customer per thread) and k_sweep2 (two: the variant that runs when the problem fills the GPU) do the
+    same arithmetic per customer: 2 chains x 23 570 customers, strict and fast, trivariate too -- bit-identical draws."""
+    d = cdnow_full
+    n = d["x"].size
+    X = np.column_stack([np.ones(n), d["first_sales_scaled"], d["age_scaled"]])
+    for D, rng in ((2, "fast"), (2, "strict"), (3, "fast")):
+        res = []
+        for cpt in ("1", "2"):
+            monkeypatch.setenv("CLV_SWEEP_CPT", cpt)
+            with Sampler(d["x"], d["t_x"], d["T_cal"], X, d["log_s"] if D == 3 else None, model_dim=D, chains=2, seed=5, rng=rng,
+                         sweep_mode="stream") as s:
+                res.append(s.run(2, 4, 2))
+        for k in ("level_1", "level_2", "loglik_sum"):
+            np.testing.assert_array_equal(res[0][k], res[1][k], err_msg=f"{k} D={D} rng={rng}")
 
 
 def test_strict_trajectory_spanning_many_tiles_and_blocks(cdnow_full):
@@ -840,3 +860,27 @@ def test_resident_forecast_list_overflow_is_repeated_with_a_larger_list(cdnow_ab
         np.testing.assert_array_equal(again[k], ref[k])
         np.testing.assert_array_equal(again_small[k], ref[k])
     assert ref["x_star"].max() >= 8                          # some cells did take the second pass
+
+
+@pytest.mark.parametrize("D,cov", [(2, ["first_sales_scaled"]), (3, ["gender_F", "age_scaled"])])
+def test_injected_sweeps_at_full_cdnow_size_vs_oracle(cdnow_full, D, cov):
+    """Injected streams at the size of BASELINE.json configs[1] / [2] (23 570 customers, 185 tiles -- the reference-made
+    injected goldens hold a single tile): the CUDA sweep fed seeded variates against the oracle fed the same arrays
+    (the oracle is pinned to the reference's own `_run_chain` by tests/test_oracle_golden.py).  z bit-exact, continuous
+    1e-6, three sweeps, the statistics of the second and third ones reduced over all tiles by the kernel."""
+    from oracle.streams import random_replay_arrays
+    d = cdnow_full
+    n = d["x"].size
+    X = np.column_stack([np.ones(n)] + [d[c].astype(float) for c in cov])
+    cbs = ao.Cbs(x=d["x"].astype(np.int64), t_x=d["t_x"], T_cal=d["T_cal"], X=X, log_s=d["log_s"] if D == 3 else None)
+    S, T = 6, 3
+    hy = ao.default_hyper(cbs.K, D)
+    arrays = random_replay_arrays(np.random.default_rng(11 + D), T, n, S, D, cbs.K, hy["nu_00"] + n)
+    ora = ao.run_chain(cbs, hy, ReplayStreams(arrays), mcmc=T, burnin=0, thin=1, D=D, n_mh_steps=S)
+    with Sampler(cbs.x, cbs.t_x, cbs.T_cal, X, cbs.log_s, model_dim=D, chains=1, n_mh_steps=S, rng="injected") as s:
+        for t in range(T):
+            out = s.sweep_injected({k: v[t][None] for k, v in arrays.items()}, keep=True)
+            np.testing.assert_array_equal(out["level_1"][0][:, 3], ora["level_1"][t][:, 3], err_msg=f"z differs at sweep {t}")
+            np.testing.assert_allclose(out["level_1"][0], ora["level_1"][t], rtol=RTOL, err_msg=f"level_1 sweep {t}")
+            np.testing.assert_allclose(out["level_2"][0], ora["level_2"][t], rtol=RTOL, atol=1e-9, err_msg=f"level_2 sweep {t}")
+            np.testing.assert_allclose(out["loglik_sum"][0] / n, ora["log_likelihood"][t], rtol=RTOL)
