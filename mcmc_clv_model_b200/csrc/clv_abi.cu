@@ -691,9 +691,10 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   h->cpt = ((long long)h->N * h->chains >= 100000) ? 2 : 1;
   if (const char* env = getenv("CLV_SWEEP_CPT")) h->cpt = atoi(env) == 2 ? 2 : 1;
   {
-    const long long ntiles2 = (h->N + 2 * SWEEP_THREADS - 1) / (2 * SWEEP_THREADS);
-    // grid of the two-customer kernel (5 resident blocks per SM): 6 waves when that still leaves >= 4 tiles per block, else 4
-    long long per2 = (ntiles2 * h->chains >= 30ll * h->sm_count * 4) ? 30 : 20;
+    const long long ntiles2 = (h->N + CPT * SWEEP_THREADS - 1) / (CPT * SWEEP_THREADS);
+    // grid of the two-customer kernel (5 resident blocks per SM): 8 waves when that still leaves >= 4 tiles per block, else 4
+    // (1.25 M customers: 12 / 16 / 20 / 24 blocks per SM -> 204.0 / 206.0 / 202.2 / 205.2 us; 10 M: 24 / 30 / 40 / 60 -> 1521 / 1513 / 1508 / 1512 us)
+    long long per2 = (ntiles2 * h->chains >= 40ll * h->sm_count * 4) ? 40 : 20;
     if (const char* env = getenv("CLV_SWEEP_BLOCKS_PER_SM2")) per2 = std::max(1ll, atoll(env));
     h->grid2_x = (int)std::max<long long>(1, std::min(ntiles2, ((long long)h->sm_count * per2 + h->chains - 1) / h->chains));
   }

@@ -566,6 +566,10 @@ __device__ __forceinline__ void cust_end(Cust2<D, MODE>& c, const SweepArgs& a, 
   if (sw.keep && c.valid) s_priv[(K * D + D * (D + 1) / 2) * SWEEP_THREADS + threadIdx.x] += to_fx(lik, mc.ll_scale);
 }
 
+#ifndef CLV_CPT
+#define CLV_CPT 2
+#endif
+constexpr int CPT = CLV_CPT;
 template <int D, int MODE>
 __device__ __forceinline__ void sweep_tile2(const SweepArgs& a, const ModelConst& mc, const ChainParams& cp, const double* s_beta,
                                             const double* s_tab, long long* s_priv, const SweepStep& sw, int chain, long long tile,
@@ -576,17 +580,17 @@ __device__ __forceinline__ void sweep_tile2(const SweepArgs& a, const ModelConst
   const double h00 = -0.5 * cp.P00, h01 = -cp.P01, h11 = -0.5 * cp.P11;
   const double t3s = (MODE == MODE_FAST) ? 1.7320508075688772 : 1.0;
   const double s_l = cp.Sigma[0] * t3s, s_m = cp.Sigma[D + 1] * t3s;
-  Cust2<D, MODE> c[2];
+  Cust2<D, MODE> c[CPT];
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
-    cust_begin<D, MODE>(c[j], a, mc, s_beta, s_tab, sw, cN, tile * (2 * SWEEP_THREADS) + j * SWEEP_THREADS + threadIdx.x, c3, h00, h01, h11);
+  for (int j = 0; j < CPT; ++j)
+    cust_begin<D, MODE>(c[j], a, mc, s_beta, s_tab, sw, cN, tile * (CPT * SWEEP_THREADS) + j * SWEEP_THREADS + threadIdx.x, c3, h00, h01, h11);
   uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(s_tab);
   asm volatile("" : "+r"(tab_addr));
   for (int s = 0; s < S; ++s) {
-    double pl[2], pm[2], prop[2];
-    uint32_t ur[2];
+    double pl[CPT], pm[CPT], prop[CPT];
+    uint32_t ur[CPT];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < CPT; ++j) {
       const uint4 A = philox4x32_10_rk(c[j].gid, sw.sweep, 1u + (uint32_t)s, c3, a.rk);
       double tl, tm;
       if (MODE == MODE_STRICT) {
@@ -600,13 +604,13 @@ __device__ __forceinline__ void sweep_tile2(const SweepArgs& a, const ModelConst
       pl[j] = c[j].ll + s_l * tl;
       pm[j] = c[j].lm + s_m * tm;
     }
-    clip70_pair(pl[0], pm[0]);
-    clip70_pair(pl[1], pm[1]);
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+    for (int j = 0; j < CPT; ++j) clip70_pair(pl[j], pm[j]);
+#pragma unroll
+    for (int j = 0; j < CPT; ++j)
       prop[j] = log_post_open(pl[j], pm[j], c[j].xd, c[j].omz, c[j].Tz, c[j].m0, c[j].m1, h00, h01, h11, tab_addr);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < CPT; ++j) {
       const uint32_t u = ur[j];
       const bool admissible = !(pm[j] > 5.0);
       if (mh_accept<false>(prop[j] - c[j].cur, u32f(u), [&]() { return u32d(u); }) && admissible) {
@@ -617,10 +621,10 @@ __device__ __forceinline__ void sweep_tile2(const SweepArgs& a, const ModelConst
     }
   }
 #pragma unroll
-  for (int j = 0; j < 2; ++j) cust_end<D, MODE>(c[j], a, mc, cp, s_tab, s_priv, sw, chain, cN, c3);
+  for (int j = 0; j < CPT; ++j) cust_end<D, MODE>(c[j], a, mc, cp, s_tab, s_priv, sw, chain, cN, c3);
 }
 
-// the sweep kernel with two customers per thread (tiles of 256 customers)
+// the sweep kernel with CPT (= 2) customers per thread (tiles of 128 CPT customers)
 #ifndef CLV_MINBLOCKS2
 #define CLV_MINBLOCKS2 5
 #endif
@@ -649,7 +653,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS2) k_sweep2(SweepA
   SweepStep sw;
   sw.sweep = a.sweep; sw.keep = a.slot >= 0; sw.store_zt = a.store_zt; sw.slot = a.slot; sw.chunk_cap = a.chunk_cap;
   sw.draws = a.draws; sw.draw_index = a.draw_index;
-  const long long ntiles = (mc.N + 2 * SWEEP_THREADS - 1) / (2 * SWEEP_THREADS);
+  const long long ntiles = (mc.N + CPT * SWEEP_THREADS - 1) / (CPT * SWEEP_THREADS);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
     sweep_tile2<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, c3);
   if (!a.pdl_early) pdl_launch_dependents();
