@@ -111,6 +111,7 @@ struct clv_sampler {
   long long sweeps_done = 0, launches = 0;
   int grid_x = 1;
   int cpt = 1, grid2_x = 1;        // customers per thread of the sweep kernel (CLV_SWEEP_CPT) and the grid of the 2-customer variant
+  unsigned int* d_tile_ctr = nullptr; long long n_big = 0, n_small = 0; int grid2_dyn_x = 0;   // dynamic tiles of k_sweep2 (0: static)
   // comm
   nccl_comm_t comm = nullptr; int world = 1, rank = 0;
   // peer mailboxes (P2P all-reduce fused into k_level2)
@@ -457,6 +458,8 @@ SweepArgs base_args(clv_sampler* h) {
   a.error_flag = h->p2p ? h->d_err : nullptr;     // only sharded runs can be told to stop by a peer
   a.pdl_early = (h->pdl_mode == 3) ? 0 : 1;
   a.fc = nullptr;                                  // set by the run driver for sweeps that may keep a draw
+  a.tile_counter = (h->cpt == 2 && h->grid2_dyn_x > 0) ? h->d_tile_ctr : nullptr;
+  a.n_big = h->n_big; a.n_small = h->n_small;
   return a;
 }
 
@@ -491,7 +494,7 @@ cudaError_t launch_sweep_kernel(clv_sampler* h, const SweepArgs& a, int mode, bo
     return launch_kernel(k_sweep<D, MODE_FAST, true>, grid, block, sm, h->stream, pdl, a);
   }
   if (h->cpt == 2 && mode != MODE_INJECT) {      // two customers per thread: tiles of 256, its own grid
-    dim3 grid2(h->grid2_x, h->chains);
+    dim3 grid2(a.tile_counter ? h->grid2_dyn_x : h->grid2_x, h->chains);
     if (mode == MODE_STRICT) return launch_kernel(k_sweep2<D, MODE_STRICT>, grid2, block, sm, h->stream, pdl, a);
     return launch_kernel(k_sweep2<D, MODE_FAST>, grid2, block, sm, h->stream, pdl, a);
   }
@@ -698,8 +701,25 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
     if (const char* env = getenv("CLV_SWEEP_BLOCKS_PER_SM2")) per2 = std::max(1ll, atoll(env));
     h->grid2_x = (int)std::max<long long>(1, std::min(ntiles2, ((long long)h->sm_count * per2 + h->chains - 1) / h->chains));
   }
+  {
+    // dynamic tiles for k_sweep2 (CLV_SWEEP_DYNAMIC=0 switches to the static grid-stride split): a one-wave grid, and the last
+    // two rounds' worth of customers cut into 128-customer tiles
+    const char* env = getenv("CLV_SWEEP_DYNAMIC");
+    const bool dyn = CPT == 2 && !(env && atoi(env) == 0);
+    const long long resident = std::max<long long>(1, (long long)h->sm_count * CLV_MINBLOCKS2 / h->chains);
+    long long small_rounds = 1;          // measured at 1.25 M customers: 0 / 1 / 2 / 3 rounds -> 194.5 / 192.8 / 196.5 / 197.0 us (static: 201.3)
+    if (const char* e2 = getenv("CLV_SWEEP_SMALL_ROUNDS")) small_rounds = std::max(0ll, atoll(e2));
+    const long long small_cust = std::min<long long>(h->N / 4, resident * small_rounds * SWEEP_THREADS);   // at most a quarter of the shard
+    h->n_big = (h->N - small_cust) / (2 * SWEEP_THREADS);
+    h->n_small = (h->N - h->n_big * 2 * SWEEP_THREADS + SWEEP_THREADS - 1) / SWEEP_THREADS;
+    // only when a block has at least two tiles to draw: with one tile per block (many chains of a small data set) the counter
+    // and the finer tail only cost (56 x 2 357 customers: 37.2 vs 31.4 us per sweep)
+    h->grid2_dyn_x = (dyn && h->n_big + h->n_small >= 2 * resident) ? (int)resident : 0;
+    CKC(dmalloc(&h->d_tile_ctr, (size_t)2 * C));
+    CKC(cudaMemsetAsync(h->d_tile_ctr, 0, sizeof(unsigned int) * 2 * C, h->stream));
+  }
   if (h->pdl_mode == 0) {
-    const long long blocks = (long long)(h->cpt == 2 ? h->grid2_x : h->grid_x) * h->chains, resident = (h->cpt == 2 ? 5ll : 8ll) * h->sm_count;
+    const long long blocks = (long long)(h->cpt == 2 ? (h->grid2_dyn_x > 0 ? h->grid2_dyn_x : h->grid2_x) : h->grid_x) * h->chains, resident = (h->cpt == 2 ? 5ll : 8ll) * h->sm_count;
     h->pdl_mode = (blocks >= resident) ? 1 : 2;
   }
   h->stats_smem = (size_t)(h->K * h->D + h->D * (h->D + 1) / 2 + 1) * SWEEP_THREADS * sizeof(long long);
@@ -760,6 +780,7 @@ void clv_destroy(clv_sampler* h) {
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   if (h->d_acc3) dfree(h->d_acc3);
   if (h->d_barrier) dfree(h->d_barrier);
+  if (h->d_tile_ctr) dfree(h->d_tile_ctr);
   if (h->d_fc) dfree(h->d_fc);
   if (h->d_fc_sx) dfree(h->d_fc_sx);
   if (h->d_fc_sz) dfree(h->d_fc_sz);

@@ -124,6 +124,10 @@ struct SweepArgs {
   const FusedForecast* fc;     // nullable: simulate x* of every kept draw from the registers (clv_set_fused_forecast)
   const int* error_flag;       // device error flag (2: a peer rank stopped)
   int pdl_early;               // 1: let the next kernel of the stream become resident at once, 0: once this block's tiles are done
+  // k_sweep2 with dynamic tiles: blocks draw tile numbers from a counter; tiles [0, n_big) hold 256 customers (two per
+  // thread), tiles [n_big, n_big + n_small) the remaining customers 128 at a time (one per thread): short tiles last
+  unsigned int* tile_counter;  // [2][chains], alternating by sweep parity (nullable: static grid-stride tiles)
+  long long n_big, n_small;
   // injected variates (MODE_INJECT)
   const double *u_z, *e_tau, *u_tau, *t3_l, *t3_m, *u_acc, *n_eta;
 };
@@ -653,9 +657,29 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS2) k_sweep2(SweepA
   SweepStep sw;
   sw.sweep = a.sweep; sw.keep = a.slot >= 0; sw.store_zt = a.store_zt; sw.slot = a.slot; sw.chunk_cap = a.chunk_cap;
   sw.draws = a.draws; sw.draw_index = a.draw_index;
-  const long long ntiles = (mc.N + CPT * SWEEP_THREADS - 1) / (CPT * SWEEP_THREADS);
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-    sweep_tile2<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, c3);
+  if (a.tile_counter) {
+    // Dynamic tiles.  One synchronisation per sweep means the sweep ends when its LAST tile ends: with a static split the
+    // blocks that drew one tile more than the others run alone for a whole tile latency (~30 us with two customers per
+    // thread).  Here the blocks of the (one-wave) grid draw tile numbers from a counter, and the tail of the tile list is
+    // cut finer: the last customers go 128 at a time, one per thread -- half the latency per tile.
+    __shared__ unsigned int s_next;
+    unsigned int* ctr = a.tile_counter + (size_t)(a.sweep & 1u) * gridDim.y + chain;
+    if (blockIdx.x == 0 && tid == 0) a.tile_counter[(size_t)((a.sweep + 1u) & 1u) * gridDim.y + chain] = 0u;   // for the next sweep
+    const long long nt = a.n_big + a.n_small;
+    for (;;) {
+      if (tid == 0) s_next = atomicAdd(ctr, 1u);
+      __syncthreads();
+      const long long t = s_next;
+      __syncthreads();
+      if (t >= nt) break;
+      if (CPT == 2 && t >= a.n_big) sweep_tile<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, 2 * a.n_big + (t - a.n_big), c3);
+      else sweep_tile2<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, t, c3);
+    }
+  } else {
+    const long long ntiles = (mc.N + CPT * SWEEP_THREADS - 1) / (CPT * SWEEP_THREADS);
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      sweep_tile2<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, c3);
+  }
   if (!a.pdl_early) pdl_launch_dependents();
   flush_stats(s_priv, s_acc, nstat, sw.keep != 0);
   __syncthreads();
