@@ -719,7 +719,7 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
     CKC(cudaMemsetAsync(h->d_tile_ctr, 0, sizeof(unsigned int) * 2 * C, h->stream));
   }
   if (h->pdl_mode == 0) {
-    const long long blocks = (long long)(h->cpt == 2 ? (h->grid2_dyn_x > 0 ? h->grid2_dyn_x : h->grid2_x) : h->grid_x) * h->chains, resident = (h->cpt == 2 ? 5ll : 8ll) * h->sm_count;
+    const long long blocks = (long long)(h->cpt == 2 ? (h->grid2_dyn_x > 0 ? h->grid2_dyn_x : h->grid2_x) : h->grid_x) * h->chains, resident = (h->cpt == 2 ? (long long)CLV_MINBLOCKS2 : 8ll) * h->sm_count;
     h->pdl_mode = (blocks >= resident) ? 1 : 2;
   }
   h->stats_smem = (size_t)(h->K * h->D + h->D * (h->D + 1) / 2 + 1) * SWEEP_THREADS * sizeof(long long);

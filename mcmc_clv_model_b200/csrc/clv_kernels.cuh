@@ -36,6 +36,9 @@ struct ChainParams {
   double Sigma[MAXD * MAXD];
   double P00, P01, P11;      // entries of inv(Sigma) used by the level-1 target (bi:303-305; tri:419-426, Q4)
   double eta_post_var, eta_sd;  // tri:325-326
+  // the level-1 quadratic form as a sum of two squares, P/2 = R'R with R = [[qa, qb], [0, qc]], and the inverse of the 2x2
+  // block [[P00, P01], [P01, P11]] (s00, s01, s11): what the fp32-screened Metropolis step works with (E32, below)
+  double qa, qb, qc, s00, s01, s11;
   int status;                // 0 ok, 1 scale matrix not positive definite / non-finite
   int pad;
 };
@@ -253,6 +256,128 @@ __device__ __forceinline__ bool mh_accept(double d, float uf, ExactU exact_u) {
   return acc;
 }
 
+// ---- the Metropolis decision with the exponential part of the target in fp32 (CLV_E32, FAST mode) ------------------------
+// target(ll, lm) = x ll + (1-z) lm - d'Pd/2 - (e^ll + e^lm) Tz,  d = (ll, lm) - m   (bi:291-310).  Its fp64 evaluation costs
+// two table exps (18 DFMA-class instructions, 2 shared-memory loads, ~8 integer ones) plus 7 for the rest, and keeps 16
+// registers of per-customer constants alive in the loop.  The decision `exp(prop - cur) > u` only needs prop - cur to the
+// accuracy that separates it from ln u, so the hot path works on
+//     target = const - Q - E,   Q = (qa ll + qb lm - k0)^2 + (qc lm - k1)^2   (fp64, 5 instructions),   E = (e^ll + e^lm) Tz  (fp32),
+// where Q is the linear and the quadratic part with the square completed: P/2 = R'R, R = [[qa, qb], [0, qc]] (ChainParams),
+// (k0, k1) = R m', m' = m + P^-1 (x, 1-z) -- two constants per customer instead of four, and no fp64 multiply by x.  E comes
+// from the SFU (ex2.approx, 2 ulp) together with a RIGOROUS bound of its error, and the step is decided when the distance
+// of prop - cur from ln u exceeds the sum of the bounds.  Otherwise (~1e-4 of the steps) mh_exact() re-decides with the
+// fp64 expression log_post_open on the fp64 state, whose inputs wait in shared memory (stash), not in registers.  Every
+// decision therefore equals the one of the all-fp64 evaluation: the chain is bit-identical to CLV_E32=0 (same digest).
+//   error budget of the screen's value of prop - cur - ln u against the fp64 expression (eps = 2^-53):
+//   * E32 = (ex2(a L2E) + ex2(b L2E)) Tz32, a = (float)ll, b = (float)lm: ex2.approx 2^-22 relative; a, L2E and their
+//     product each rounded (3 x 2^-24 relative in the argument = 1.8e-7 |a| relative in the result); the sum, Tz32 and the
+//     product 3 x 2^-24: <= 4.2e-7 + 1.8e-7 max(|a|, |b|).  dE = Ep - Ec and dt = dL32 - dE add 2^-24 (|dE| + |dt|) <=
+//     1.2e-7 (Ep + Ec) + 6e-8 |dL32|.  Carried: tolE = E (1.3e-6 + 4e-7 max(|a|, |b|)) (margin > 2), 5e-7 E for the
+//     initial E (an fp64 value rounded once); dL32 = (float)(Qc - Qp): 6e-8 |dL32|; carried 3e-7 |dL32|.
+//   * fp64 rounding of Q and of the exact expression itself.  u = qa ll + qb lm - k0 cancels terms of size up to
+//     Tm = (|qa| + |qb| + |qc|)(70 + |m'0| + |m'1|): |du| <= eps (Tm + |u|), plus an offset common to prop and cur from the
+//     rounding of k (<= 4 eps Tm).  Within a sweep the current state obeys |u|, |v| <= B = sqrt(Q0 + E0 + 25 S): an
+//     accepted step raises Q + E by at most -ln u + tol < 24.5 (u >= 2^-33).  With Dm = max |u_p - u_c|: the error of
+//     Qc - Qp is <= 24 eps (Tm + B + Dm)(B + Dm); the exact expression's own rounding is <= 6 eps (70 x + 70 + E + 2 q),
+//     q = d'Pd/2 <= 2 (B + Dm)^2 + 2 Rm^2, Rm = |R P^-1 (x, 1-z)| (its E part is covered by tolE).  For Dm <= 3 B both
+//     are below 100 eps (Tm + 4B + Rm)(4B + Rm) + 420 eps x, which e32_begin requires to be < 2e-6 (else the customer's
+//     Tz32 is NaN for this sweep and the exact path decides every step: thousands of transactions, a nearly singular
+//     Sigma); for Dm > 3 B, |Qc - Qp| >= 0.22 Dm^2 and both errors are below 3e-7 |Qc - Qp| as long as Tm < 1e8 (also
+//     required) -- the relative term of the tolerance.  The 2e-6 sits in the floor 1.2e-5, which keeps the
+//     1e-5 (1 + |ln u|) of mh_accept for lg2.approx and the fp32 image of u.
+//   * Overflow / NaN anywhere make the comparison of the screen false and so lead to the exact path; so does a proposal
+//     with max(|a|, |b|) >= 69.5, which the exact path clips to +-70 (bi:323-324) -- the hot path never clips.
+#ifndef CLV_E32
+#define CLV_E32 1
+#endif
+// (ex2_ftz: clv_forecast.cuh)
+constexpr int E32_STASH = 5;      // doubles per customer in the stash: x, 1-z, Tz, m0, m1
+__device__ __forceinline__ double q_part(double ll, double lm, double qa, double qb, double qc, double k0, double k1) {
+  const double u = fma(qa, ll, fma(qb, lm, -k0)), v = fma(qc, lm, -k1);
+  return fma(u, u, v * v);
+}
+// fp32 image of E at (ll, lm), the bound of its error, and max(|a|, |b|)
+__device__ __forceinline__ void e_part32(double ll, double lm, float Tz32, float& E, float& tolE, float& amax) {
+  const float a = (float)ll, b = (float)lm;
+  E = (ex2_ftz(a * 1.44269504088896341f) + ex2_ftz(b * 1.44269504088896341f)) * Tz32;
+  amax = fmaxf(fabsf(a), fabsf(b));
+  tolE = E * fmaf(amax, 4e-7f, 1.3e-6f);
+}
+// the exact decision (bi:329-330 on the fp64 target) from the fp64 state; cur is -inf where log mu > 5 (bi:308-309).
+// stash: this customer's x, 1-z, Tz, m0, m1 at stride SWEEP_THREADS doubles.
+__device__ __noinline__ bool mh_exact(double ll, double lm, double pl, double pm, const double* stash, const ChainParams* cp,
+                                      const double* tab, uint32_t ur) {
+  const double xd = stash[0], omz = stash[SWEEP_THREADS], Tz = stash[2 * SWEEP_THREADS], m0 = stash[3 * SWEEP_THREADS],
+               m1 = stash[4 * SWEEP_THREADS];
+  const double h00 = -0.5 * cp->P00, h01 = -cp->P01, h11 = -0.5 * cp->P11;
+  const double cur = (lm > 5.0) ? -CUDART_INF : log_post_open(ll, lm, xd, omz, Tz, m0, m1, h00, h01, h11, tab);
+  const double prop = log_post_open(pl, pm, xd, omz, Tz, m0, m1, h00, h01, h11, tab);
+  const double d = prop - cur;
+  return (d >= 0.0) || exp(d) > u32d(ur);
+}
+// The state of one customer inside the Metropolis loop (13 registers) ...
+struct E32State {
+  double ll, lm, Qc, k0, k1;
+  float Ec, tEc, Tz32;
+};
+// ... its set-up: stores the exact path's inputs, completes the square, evaluates the current target's parts
+__device__ __forceinline__ void e32_begin(E32State& st, double ll, double lm, double lam, double mu, double xd, double omz,
+                                          double Tz, double m0, double m1, const ChainParams& cp, int S, double* stash) {
+  stash[0] = xd; stash[SWEEP_THREADS] = omz; stash[2 * SWEEP_THREADS] = Tz; stash[3 * SWEEP_THREADS] = m0;
+  stash[4 * SWEEP_THREADS] = m1;
+  const double qa = cp.qa, qb = cp.qb, qc = cp.qc;
+  const double d0 = fma(cp.s00, xd, cp.s01 * omz), d1 = fma(cp.s01, xd, cp.s11 * omz);      // P^-1 (x, 1-z)
+  const double n0 = m0 + d0, n1 = m1 + d1;                                                     // m'
+  st.ll = ll; st.lm = lm;
+  st.k0 = fma(qa, n0, qb * n1);
+  st.k1 = qc * n1;
+  st.Qc = q_part(ll, lm, qa, qb, qc, st.k0, st.k1);
+  st.Ec = (lm > 5.0) ? CUDART_NAN_F : (float)((lam + mu) * Tz);     // NaN: target -inf, the exact path decides
+  st.tEc = st.Ec * 5e-7f;
+  // the fp64 rounding guard of the error budget (fp32 arithmetic with 1 % margins; NaN / inf fail it)
+  const float Tm = 1.01f * (float)((fabs(qa) + fabs(qb) + fabs(qc)) * (70.0 + fabs(n0) + fabs(n1)));
+  const float Rm = 1.01f * (float)(fabs(fma(qa, d0, qb * d1)) + fabs(qc * d1));
+  const float B4 = 4.04f * sqrtf((float)st.Qc + st.Ec + 25.0f * (float)S);
+  const float W2 = B4 + Rm, W1 = Tm + W2;
+  const bool ok = fmaf(100.0f * W1, W2, 420.0f * fabsf((float)xd)) < 1.8e10f && Tm < 1e8f;
+  st.Tz32 = ok ? (float)Tz : CUDART_NAN_F;
+  asm volatile("" : "+f"(st.Tz32));             // opaque: ptxas would otherwise rebuild it inside the loop
+}
+// one Metropolis step (bi:312-335) in two halves, so that a caller with several customers per thread can interleave them
+struct E32Prop {
+  double pl, pm, Qp;
+  float Ep, tEp, amax;
+};
+__device__ __forceinline__ void e32_propose(const E32State& st, E32Prop& pr, double tl, double tm, double s_l, double s_m,
+                                            double qa, double qb, double qc) {
+  pr.pl = st.ll + s_l * tl;                     // bi:318-324 (clip: in the exact path)
+  pr.pm = st.lm + s_m * tm;
+  pr.Qp = q_part(pr.pl, pr.pm, qa, qb, qc, st.k0, st.k1);
+  e_part32(pr.pl, pr.pm, st.Tz32, pr.Ep, pr.tEp, pr.amax);
+}
+__device__ __forceinline__ void e32_decide(E32State& st, E32Prop& pr, uint32_t ur, double qa, double qb, double qc,
+                                           const double* stash, const ChainParams* cp, const double* tab) {
+  const float dL32 = (float)(st.Qc - pr.Qp);
+  const float dt = dL32 - (pr.Ep - st.Ec);
+  const float lg = lg2_ftz(u32f(ur));
+  const float gap = fmaf(lg, -0.69314718055994531f, dt);                       // prop - cur - ln u
+  float tol = (pr.tEp + st.tEc) + fmaf(fabsf(dL32), 3e-7f, 1.2e-5f);
+  tol = fmaf(fabsf(lg), 7e-6f, tol);                                            // 1e-5 |ln u|
+  bool acc = gap > 0.0f;
+  if (!(fabsf(gap) > tol && pr.amax < 69.5f)) {                                 // NaN / inf anywhere: not decided here
+    pr.pl = fmin(fmax(pr.pl, -70.0), 70.0);
+    pr.pm = fmin(fmax(pr.pm, -70.0), 70.0);
+    pr.Qp = q_part(pr.pl, pr.pm, qa, qb, qc, st.k0, st.k1);
+    e_part32(pr.pl, pr.pm, st.Tz32, pr.Ep, pr.tEp, pr.amax);
+    acc = mh_exact(st.ll, st.lm, pr.pl, pr.pm, stash, cp, tab, ur);
+  }
+  // a proposal with log mu > 5 has target -inf and is never accepted (bi:308-309); cur itself can be -inf only at the
+  // start (Ec = NaN), and then every admissible proposal is accepted by the exact path (d = +inf)
+  if (acc && !(pr.pm > 5.0)) {
+    st.ll = pr.pl; st.lm = pr.pm; st.Qc = pr.Qp; st.Ec = pr.Ep; st.tEc = pr.tEp;
+  }
+}
+
 // np.clip(v, -70, 70) of bi:323-324 for both proposals; the test runs on the high words so the common case costs a few
 // integer ops and one rarely taken branch (|v| >= 70 needs a t3 variate beyond ~47: about 1 proposal in 50,000).
 // Tried and dropped: leaving the loop for a clipping copy of the step instead of the call -- ptxas merges the copies
@@ -326,7 +451,7 @@ struct SweepStep {
 template <int D, int MODE, bool FUSE_FC = false>
 __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst& mc, const ChainParams& cp,
                                            const double* s_beta, const double* s_tab, long long* s_priv,
-                                           const SweepStep& sw, int chain, long long tile, uint32_t c3) {
+                                           const SweepStep& sw, int chain, long long tile, uint32_t c3, double* s_stash) {
   const int tid = threadIdx.x;
   const int K = mc.K, S = mc.S;
   const long long N = mc.N;
@@ -389,6 +514,21 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
     const double omz = 1.0 - zf;
     const double Tz = alive ? T : tau;          // z*T_cal + (1-z)*tau, bi:298
     // ---- S Metropolis steps (bi:312-335) -------------------------------------------------------
+    constexpr bool E32 = (CLV_E32 != 0) && MODE == MODE_FAST;   // fp32 E part + exact re-decision (e32_decide)
+    if constexpr (E32) {
+      E32State st;
+      double* stash = s_stash + tid;
+      e32_begin(st, ll, lm, lam, mu, xd, omz, Tz, m0, m1, cp, S, stash);
+      const double qa = cp.qa, qb = cp.qb, qc = cp.qc;
+      for (int s = 0; s < S; ++s) {
+        const uint4 A = philox4x32_10_rk(gid, sw.sweep, 1u + (uint32_t)s, c3, a.rk);   // word layout: clv_rng.cuh
+        E32Prop pr;
+        e32_propose(st, pr, (double)t3_fast(A.x, A.y), (double)t3_fast(A.z, A.w), s_l, s_m, qa, qb, qc);
+        e32_decide(st, pr, low_bytes(A.x, A.y, A.z, A.w), qa, qb, qc, stash, &cp, s_tab);
+      }
+      ll = st.ll;
+      lm = st.lm;
+    } else {
     double cur = log_post(ll, lm, xd, omz, Tz, m0, m1, h00, h01, h11, s_tab);
     uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(s_tab);
     asm volatile("" : "+r"(tab_addr));                 // opaque: keeps ptxas from rebuilding it inside the loop
@@ -432,6 +572,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
       if (MODE != MODE_INJECT) A = philox4x32_10_rk(gid, sw.sweep, 1u + (uint32_t)s, c3, a.rk);   // word layout: clv_rng.cuh
       mh_step(s, A.x, A.y, A.z, A.w);
     }
+    }
     a.ll[cN + i] = ll;
     a.lm[cN + i] = lm;
     // ---- eta (tri:306-333, 524-526) ------------------------------------------------------------
@@ -467,7 +608,10 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
         }
       }
       if (FUSE_FC && a.fc) fused_forecast_cell(a.fc, gid, (long long)chain * a.loglik_stride + sw.draw_index, lam_n, tau, zf, T, cN + i);
-      lik = xd * ll + omz * lm - (lam_n + mu_n) * Tz;         // bi:423-427
+      // (E32: x, 1-z, Tz come back from the stash, so they do not occupy registers across the Metropolis loop)
+      const double xk = E32 ? s_stash[tid] : xd, ok = E32 ? s_stash[SWEEP_THREADS + tid] : omz,
+                   Tk = E32 ? s_stash[2 * SWEEP_THREADS + tid] : Tz;
+      lik = xk * ll + ok * lm - (lam_n + mu_n) * Tk;         // bi:423-427
       lik = fmin(fmax(lik, -1048576.0), 1048576.0);
     }
     yc0 = ll - mc.center[0];
@@ -488,32 +632,34 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
 template <int D, int MODE>
 struct Cust2 {
   double ll, lm, cur, xd, omz, Tz, m0, m1, m2, tau, zf;
+  E32State st;               // E32: the Metropolis loop's state (ll, lm live there; x, 1-z, Tz, m0, m1 in the stash)
   uint32_t gid;
   long long i;
   bool valid;
 };
 
 template <int D, int MODE>
-__device__ __forceinline__ void cust_begin(Cust2<D, MODE>& c, const SweepArgs& a, const ModelConst& mc, const double* s_beta,
-                                           const double* s_tab, const SweepStep& sw, long long cN, long long i, uint32_t c3,
-                                           double h00, double h01, double h11) {
+__device__ __forceinline__ void cust_begin(Cust2<D, MODE>& c, const SweepArgs& a, const ModelConst& mc, const ChainParams& cp,
+                                           const double* s_beta, const double* s_tab, const SweepStep& sw, int chain,
+                                           long long cN, long long i, uint32_t c3, double h00, double h01, double h11,
+                                           double* stash) {
   const int K = mc.K;
   const long long N = mc.N;
   c.valid = i < N;
   c.i = c.valid ? i : N - 1;                 // a lane beyond the end shadows the last customer; nothing of it is stored
   c.gid = (uint32_t)(mc.gid_offset + c.i);
-  c.xd = (double)a.x[c.i];
+  const double xd = (double)a.x[c.i];
   const double tx = a.t_x[c.i], T = a.T_cal[c.i];
-  c.ll = a.ll[cN + c.i];
-  c.lm = a.lm[cN + c.i];
-  c.m0 = s_beta[0]; c.m1 = s_beta[1]; c.m2 = (D == 3) ? s_beta[2] : 0.0;
+  const double ll = a.ll[cN + c.i], lm = a.lm[cN + c.i];
+  double m0 = s_beta[0], m1 = s_beta[1];
+  c.m2 = (D == 3) ? s_beta[2] : 0.0;
   for (int k = 1; k < K; ++k) {
     const double xk = a.Xc[(long long)(k - 1) * N + c.i];
-    c.m0 = fma(xk, s_beta[k * D + 0], c.m0);
-    c.m1 = fma(xk, s_beta[k * D + 1], c.m1);
+    m0 = fma(xk, s_beta[k * D + 0], m0);
+    m1 = fma(xk, s_beta[k * D + 1], m1);
     if (D == 3) c.m2 = fma(xk, s_beta[k * D + 2], c.m2);
   }
-  const double lam = exp_tab(c.ll, s_tab), mu = exp_tab(c.lm, s_tab);
+  const double lam = exp_tab(ll, s_tab), mu = exp_tab(lm, s_tab);
   const uint4 r = philox4x32_10_rk(c.gid, sw.sweep, 0u, c3, a.rk);
   const double uz = u53(r.x, r.y), ut = u53(r.z, r.w);
   const double ml = mu + lam;
@@ -525,17 +671,45 @@ __device__ __forceinline__ void cust_begin(Cust2<D, MODE>& c, const SweepArgs& a
   const double lg = -log(alive ? ut : mix);
   c.tau = (alive ? T : 0.0) + lg / (alive ? mu : ml);
   c.zf = alive ? 1.0 : 0.0;
-  c.omz = 1.0 - c.zf;
-  c.Tz = alive ? T : c.tau;
-  c.cur = log_post(c.ll, c.lm, c.xd, c.omz, c.Tz, c.m0, c.m1, h00, h01, h11, s_tab);
+  const double omz = 1.0 - c.zf;
+  const double Tz = alive ? T : c.tau;
+  if constexpr ((CLV_E32 != 0) && MODE == MODE_FAST) {
+    // z and tau are final here: they leave now (state arrays, columns 2-3 of a kept draw's row), so that nothing but the
+    // Metropolis state is alive in the loop
+    if (c.valid) {
+      if (sw.store_zt) {
+        a.z[cN + c.i] = c.zf;
+        a.tau[cN + c.i] = c.tau;
+      }
+      if (sw.keep && sw.draws) {
+        constexpr int NC = (D == 2) ? 4 : 5;
+        double* o = sw.draws + (((long long)chain * sw.chunk_cap + sw.slot) * N + c.i) * NC;
+        if (D == 2) reinterpret_cast<double2*>(o)[1] = make_double2(c.tau, c.zf);
+        else { o[2] = c.tau; o[3] = c.zf; }
+      }
+    }
+    e32_begin(c.st, ll, lm, lam, mu, xd, omz, Tz, m0, m1, cp, mc.S, stash);
+  } else {
+    c.ll = ll; c.lm = lm; c.xd = xd; c.omz = omz; c.Tz = Tz; c.m0 = m0; c.m1 = m1;
+    c.cur = log_post(ll, lm, xd, omz, Tz, m0, m1, h00, h01, h11, s_tab);
+  }
 }
 
 template <int D, int MODE>
 __device__ __forceinline__ void cust_end(Cust2<D, MODE>& c, const SweepArgs& a, const ModelConst& mc, const ChainParams& cp,
-                                         const double* s_tab, long long* s_priv, const SweepStep& sw, int chain, long long cN, uint32_t c3) {
+                                         const double* s_tab, long long* s_priv, const SweepStep& sw, int chain, long long cN, uint32_t c3,
+                                         long long i, const double* stash) {
   const int K = mc.K, S = mc.S;
   const long long N = mc.N;
   double le = 0.0, lik = 0.0;
+  constexpr bool E32 = (CLV_E32 != 0) && MODE == MODE_FAST;
+  if constexpr (E32) {
+    c.ll = c.st.ll; c.lm = c.st.lm;
+    c.xd = stash[0]; c.omz = stash[SWEEP_THREADS]; c.Tz = stash[2 * SWEEP_THREADS];
+    c.valid = i < N;                             // recomputed, not carried through the loop
+    c.i = c.valid ? i : N - 1;
+    c.gid = (uint32_t)(mc.gid_offset + c.i);
+  }
   if (c.valid) {
     a.ll[cN + c.i] = c.ll;
     a.lm[cN + c.i] = c.lm;
@@ -546,7 +720,7 @@ __device__ __forceinline__ void cust_end(Cust2<D, MODE>& c, const SweepArgs& a, 
       le = post_mean + cp.eta_sd * n;
       a.le[cN + c.i] = le;
     }
-    if (sw.store_zt) {
+    if (!E32 && sw.store_zt) {
       a.z[cN + c.i] = c.zf;
       a.tau[cN + c.i] = c.tau;
     }
@@ -557,9 +731,10 @@ __device__ __forceinline__ void cust_end(Cust2<D, MODE>& c, const SweepArgs& a, 
         double* o = sw.draws + (((long long)chain * sw.chunk_cap + sw.slot) * N + c.i) * NC;
         if (D == 2) {
           reinterpret_cast<double2*>(o)[0] = make_double2(lam_n, mu_n);
-          reinterpret_cast<double2*>(o)[1] = make_double2(c.tau, c.zf);
+          if (!E32) reinterpret_cast<double2*>(o)[1] = make_double2(c.tau, c.zf);
         } else {
-          o[0] = lam_n; o[1] = mu_n; o[2] = c.tau; o[3] = c.zf; o[4] = exp(le);
+          o[0] = lam_n; o[1] = mu_n; o[4] = exp(le);
+          if (!E32) { o[2] = c.tau; o[3] = c.zf; }
         }
       }
       lik = c.xd * c.ll + c.omz * c.lm - (lam_n + mu_n) * c.Tz;
@@ -577,60 +752,82 @@ constexpr int CPT = CLV_CPT;
 template <int D, int MODE>
 __device__ __forceinline__ void sweep_tile2(const SweepArgs& a, const ModelConst& mc, const ChainParams& cp, const double* s_beta,
                                             const double* s_tab, long long* s_priv, const SweepStep& sw, int chain, long long tile,
-                                            uint32_t c3) {
+                                            uint32_t c3, double* s_stash) {
   static_assert(MODE != MODE_INJECT, "two customers per thread: Philox modes only");
+  constexpr bool E32 = (CLV_E32 != 0) && MODE == MODE_FAST;
   const int S = mc.S;
   const long long cN = (long long)chain * mc.N;
   const double h00 = -0.5 * cp.P00, h01 = -cp.P01, h11 = -0.5 * cp.P11;
   const double t3s = (MODE == MODE_FAST) ? 1.7320508075688772 : 1.0;
   const double s_l = cp.Sigma[0] * t3s, s_m = cp.Sigma[D + 1] * t3s;
   Cust2<D, MODE> c[CPT];
+  // customer j of this thread keeps its exact-path inputs at s_stash[(f CPT + j) 128 + tid], f = 0..4
 #pragma unroll
   for (int j = 0; j < CPT; ++j)
-    cust_begin<D, MODE>(c[j], a, mc, s_beta, s_tab, sw, cN, tile * (CPT * SWEEP_THREADS) + j * SWEEP_THREADS + threadIdx.x, c3, h00, h01, h11);
-  uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(s_tab);
-  asm volatile("" : "+r"(tab_addr));
-  for (int s = 0; s < S; ++s) {
-    double pl[CPT], pm[CPT], prop[CPT];
-    uint32_t ur[CPT];
+    cust_begin<D, MODE>(c[j], a, mc, cp, s_beta, s_tab, sw, chain, cN, tile * (CPT * SWEEP_THREADS) + j * SWEEP_THREADS + threadIdx.x,
+                        c3, h00, h01, h11, s_stash + (size_t)j * E32_STASH * SWEEP_THREADS + threadIdx.x);
+  if constexpr (E32) {
+    const double qa = cp.qa, qb = cp.qb, qc = cp.qc;
+    for (int s = 0; s < S; ++s) {
+      E32Prop pr[CPT];
+      uint32_t ur[CPT];
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      const uint4 A = philox4x32_10_rk(c[j].gid, sw.sweep, 1u + (uint32_t)s, c3, a.rk);
-      double tl, tm;
-      if (MODE == MODE_STRICT) {
-        tl = t3_strict(A.x, A.y);
-        tm = t3_strict(A.z, A.w);
-      } else {
-        tl = (double)t3_fast(A.x, A.y);
-        tm = (double)t3_fast(A.z, A.w);
+      for (int j = 0; j < CPT; ++j) {
+        const uint4 A = philox4x32_10_rk(c[j].gid, sw.sweep, 1u + (uint32_t)s, c3, a.rk);
+        ur[j] = low_bytes(A.x, A.y, A.z, A.w);
+        e32_propose(c[j].st, pr[j], (double)t3_fast(A.x, A.y), (double)t3_fast(A.z, A.w), s_l, s_m, qa, qb, qc);
       }
-      ur[j] = low_bytes(A.x, A.y, A.z, A.w);
-      pl[j] = c[j].ll + s_l * tl;
-      pm[j] = c[j].lm + s_m * tm;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j)
+        e32_decide(c[j].st, pr[j], ur[j], qa, qb, qc, s_stash + (size_t)j * E32_STASH * SWEEP_THREADS + threadIdx.x, &cp, s_tab);
     }
+  } else {
+    uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(s_tab);
+    asm volatile("" : "+r"(tab_addr));
+    for (int s = 0; s < S; ++s) {
+      double pl[CPT], pm[CPT], prop[CPT];
+      uint32_t ur[CPT];
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) clip70_pair(pl[j], pm[j]);
+      for (int j = 0; j < CPT; ++j) {
+        const uint4 A = philox4x32_10_rk(c[j].gid, sw.sweep, 1u + (uint32_t)s, c3, a.rk);
+        double tl, tm;
+        if (MODE == MODE_STRICT) {
+          tl = t3_strict(A.x, A.y);
+          tm = t3_strict(A.z, A.w);
+        } else {
+          tl = (double)t3_fast(A.x, A.y);
+          tm = (double)t3_fast(A.z, A.w);
+        }
+        ur[j] = low_bytes(A.x, A.y, A.z, A.w);
+        pl[j] = c[j].ll + s_l * tl;
+        pm[j] = c[j].lm + s_m * tm;
+      }
 #pragma unroll
-    for (int j = 0; j < CPT; ++j)
-      prop[j] = log_post_open(pl[j], pm[j], c[j].xd, c[j].omz, c[j].Tz, c[j].m0, c[j].m1, h00, h01, h11, tab_addr);
+      for (int j = 0; j < CPT; ++j) clip70_pair(pl[j], pm[j]);
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      const uint32_t u = ur[j];
-      const bool admissible = !(pm[j] > 5.0);
-      if (mh_accept<false>(prop[j] - c[j].cur, u32f(u), [&]() { return u32d(u); }) && admissible) {
-        c[j].ll = pl[j];
-        c[j].lm = pm[j];
-        c[j].cur = prop[j];
+      for (int j = 0; j < CPT; ++j)
+        prop[j] = log_post_open(pl[j], pm[j], c[j].xd, c[j].omz, c[j].Tz, c[j].m0, c[j].m1, h00, h01, h11, tab_addr);
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const uint32_t u = ur[j];
+        const bool admissible = !(pm[j] > 5.0);
+        if (mh_accept<false>(prop[j] - c[j].cur, u32f(u), [&]() { return u32d(u); }) && admissible) {
+          c[j].ll = pl[j];
+          c[j].lm = pm[j];
+          c[j].cur = prop[j];
+        }
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < CPT; ++j) cust_end<D, MODE>(c[j], a, mc, cp, s_tab, s_priv, sw, chain, cN, c3);
+  for (int j = 0; j < CPT; ++j)
+    cust_end<D, MODE>(c[j], a, mc, cp, s_tab, s_priv, sw, chain, cN, c3, tile * (CPT * SWEEP_THREADS) + j * SWEEP_THREADS + threadIdx.x,
+                      s_stash + (size_t)j * E32_STASH * SWEEP_THREADS + threadIdx.x);
 }
 
 // the sweep kernel with CPT (= 2) customers per thread (tiles of 128 CPT customers)
 #ifndef CLV_MINBLOCKS2
-#define CLV_MINBLOCKS2 5
+#define CLV_MINBLOCKS2 4
 #endif
 template <int D, int MODE>
 __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS2) k_sweep2(SweepArgs a) {
@@ -638,6 +835,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS2) k_sweep2(SweepA
   __shared__ double s_beta[MAXK * MAXD];
   __shared__ double s_tab[EXP_N];
   __shared__ unsigned long long s_acc[NSTAT_MAX + 1];
+  __shared__ double s_stash[E32_STASH * CPT * SWEEP_THREADS];     // the exact path's inputs (E32)
   const ModelConst& mc = *a.mc;
   const int chain = blockIdx.y;
   const int tid = threadIdx.x;
@@ -672,13 +870,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS2) k_sweep2(SweepA
       const long long t = s_next;
       __syncthreads();
       if (t >= nt) break;
-      if (CPT == 2 && t >= a.n_big) sweep_tile<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, 2 * a.n_big + (t - a.n_big), c3);
-      else sweep_tile2<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, t, c3);
+      if (CPT == 2 && t >= a.n_big) sweep_tile<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, 2 * a.n_big + (t - a.n_big), c3, s_stash);
+      else sweep_tile2<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, t, c3, s_stash);
     }
   } else {
     const long long ntiles = (mc.N + CPT * SWEEP_THREADS - 1) / (CPT * SWEEP_THREADS);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-      sweep_tile2<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, c3);
+      sweep_tile2<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, c3, s_stash);
   }
   if (!a.pdl_early) pdl_launch_dependents();
   flush_stats(s_priv, s_acc, nstat, sw.keep != 0);
@@ -699,6 +897,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArg
   __shared__ double s_beta[MAXK * MAXD];
   __shared__ double s_tab[EXP_N];
   __shared__ unsigned long long s_acc[NSTAT_MAX + 1];
+  __shared__ double s_stash[E32_STASH * SWEEP_THREADS];           // the exact path's inputs (E32)
   const ModelConst& mc = *a.mc;
   const int chain = blockIdx.y;
   const int tid = threadIdx.x;
@@ -723,7 +922,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_sweep(SweepArg
   sw.draws = a.draws; sw.draw_index = a.draw_index;
   const long long ntiles = (mc.N + SWEEP_THREADS - 1) / SWEEP_THREADS;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-    sweep_tile<D, MODE, FUSE_FC>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, c3);
+    sweep_tile<D, MODE, FUSE_FC>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, c3, s_stash);
   if (!a.pdl_early) pdl_launch_dependents();
   flush_stats(s_priv, s_acc, nstat, sw.keep != 0);
   __syncthreads();
@@ -915,6 +1114,17 @@ __device__ inline void derive_params(ChainParams& cp, double omega2) {
     cp.eta_post_var = 1.0 / post_precision;
     cp.eta_sd = sqrt(cp.eta_post_var);
   }
+  // E32 constants (three independent long operations; a non-positive-definite block gives NaN, which sends every
+  // decision of the screen to the exact path)
+  const double ra = rsqrt(0.5 * cp.P00);
+  cp.qa = 0.5 * cp.P00 * ra;
+  cp.qb = 0.5 * cp.P01 * ra;
+  const double c2 = fma(-cp.qb, cp.qb, 0.5 * cp.P11);
+  cp.qc = c2 * rsqrt(c2);
+  const double rd = 1.0 / fma(cp.P00, cp.P11, -cp.P01 * cp.P01);
+  cp.s00 = cp.P11 * rd;
+  cp.s01 = -cp.P01 * rd;
+  cp.s11 = cp.P00 * rd;
 }
 
 template <int D>
@@ -1319,6 +1529,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(Per
   __shared__ double s_tab[EXP_N];
   __shared__ unsigned long long s_acc[NSTAT_MAX + 1];
   __shared__ ChainParams s_cp;
+  __shared__ double s_stash[E32_STASH * SWEEP_THREADS];           // the exact path's inputs (E32)
   __shared__ Level2Scratch sc;
   __shared__ Level2Const lc;
   __shared__ Level2Variates lv[2];         // variates of sweep s live in lv[s & 1]; drawn one sweep ahead by warp 1
@@ -1384,7 +1595,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS) k_persistent(Per
     sw.sweep = sweep; sw.keep = kept; sw.store_zt = (pa.store_zt_last && it + 1 == pa.n_sweeps);
     sw.slot = kept ? draw - pa.chunk_base : 0; sw.chunk_cap = a.chunk_cap; sw.draws = a.draws; sw.draw_index = draw;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-      sweep_tile<D, MODE>(a, mc, s_cp, s_beta, s_tab, s_priv, sw, chain, tile, c3);
+      sweep_tile<D, MODE>(a, mc, s_cp, s_beta, s_tab, s_priv, sw, chain, tile, c3, s_stash);
     flush_stats(s_priv, s_acc, nstat, kept);
     __syncthreads();
     for (int t = tid; t < nstat; t += SWEEP_THREADS)
