@@ -394,17 +394,20 @@ __device__ __forceinline__ void clip70_pair(double& a, double& b) {
 // Level-2 sufficient statistics.  Every thread owns one column of the dynamic shared array s_priv[(stat)][128]
 // (int64 fixed point) and adds its customers' terms there, tile after tile; flush_stats() reduces the columns once per
 // block and sweep.  All sums are integers => the result does not depend on any of this.
+// XC_STASH: the first covariates of a customer wait in shared memory between the prologue of its tile (where they enter the
+// prior means) and the statistics at its end, instead of being fetched from global memory twice (k_sweep2)
+constexpr int XC_STASH = 4;
 template <int D>
 __device__ __forceinline__ void accumulate_stats(const ModelConst& mc, const double* __restrict__ Xc, long long N,
                                                  long long i, bool valid, double yc0, double yc1, double yc2,
-                                                 long long* s_priv) {
+                                                 long long* s_priv, const double* xs = nullptr, int xs_stride = 0) {
   if (!valid) return;
   const double sc = mc.fx_scale;
   const int K = mc.K;
   const double y[3] = {yc0, yc1, yc2};
   long long* col = s_priv + threadIdx.x;
   for (int k = 0; k < K; ++k) {
-    const double xk = (k == 0) ? 1.0 : Xc[(long long)(k - 1) * N + i];
+    const double xk = (k == 0) ? 1.0 : (xs && k <= XC_STASH) ? xs[(k - 1) * xs_stride] : Xc[(long long)(k - 1) * N + i];
 #pragma unroll
     for (int d = 0; d < D; ++d) col[(k * D + d) * SWEEP_THREADS] += to_fx(xk * y[d], sc);
   }
@@ -629,6 +632,10 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
 // i + 128 of a 256-customer tile) and walks them through the steps together, so each warp carries two independent
 // instruction streams for the scheduler to interleave.  Per customer the arithmetic is exactly sweep_tile's (same
 // functions, same order), so chains are bit-identical whichever variant runs.  Philox modes only (FAST / STRICT).
+#ifndef CLV_CPT
+#define CLV_CPT 2
+#endif
+constexpr int CPT = CLV_CPT;
 template <int D, int MODE>
 struct Cust2 {
   double ll, lm, cur, xd, omz, Tz, m0, m1, m2, tau, zf;
@@ -637,23 +644,46 @@ struct Cust2 {
   long long i;
   bool valid;
 };
+// a customer's inputs, fetched for all customers of the thread before any of them is used (the loads overlap)
+struct Cust2In {
+  double xd, tx, T, ll, lm, xc[XC_STASH];
+};
+template <int D>
+__device__ __forceinline__ void cust_load(Cust2In& in, const SweepArgs& a, const ModelConst& mc, long long cN, long long i) {
+  const long long N = mc.N;
+  const long long ii = (i < N) ? i : N - 1;   // a lane beyond the end shadows the last customer; nothing of it is stored
+  in.xd = (double)a.x[ii];
+  in.tx = a.t_x[ii];
+  in.T = a.T_cal[ii];
+  in.ll = a.ll[cN + ii];
+  in.lm = a.lm[cN + ii];
+#pragma unroll
+  for (int k = 0; k < XC_STASH; ++k) in.xc[k] = (k + 1 < mc.K) ? a.Xc[(long long)k * N + ii] : 0.0;
+}
 
 template <int D, int MODE>
-__device__ __forceinline__ void cust_begin(Cust2<D, MODE>& c, const SweepArgs& a, const ModelConst& mc, const ChainParams& cp,
-                                           const double* s_beta, const double* s_tab, const SweepStep& sw, int chain,
-                                           long long cN, long long i, uint32_t c3, double h00, double h01, double h11,
-                                           double* stash) {
+__device__ __forceinline__ void cust_begin(Cust2<D, MODE>& c, const Cust2In& in, const SweepArgs& a, const ModelConst& mc,
+                                           const ChainParams& cp, const double* s_beta, const double* s_tab, const SweepStep& sw,
+                                           int chain, long long cN, long long i, uint32_t c3, double h00, double h01, double h11,
+                                           double* stash, double* xs) {
   const int K = mc.K;
   const long long N = mc.N;
   c.valid = i < N;
-  c.i = c.valid ? i : N - 1;                 // a lane beyond the end shadows the last customer; nothing of it is stored
+  c.i = c.valid ? i : N - 1;
   c.gid = (uint32_t)(mc.gid_offset + c.i);
-  const double xd = (double)a.x[c.i];
-  const double tx = a.t_x[c.i], T = a.T_cal[c.i];
-  const double ll = a.ll[cN + c.i], lm = a.lm[cN + c.i];
+  const double xd = in.xd, tx = in.tx, T = in.T, ll = in.ll, lm = in.lm;
   double m0 = s_beta[0], m1 = s_beta[1];
   c.m2 = (D == 3) ? s_beta[2] : 0.0;
-  for (int k = 1; k < K; ++k) {
+#pragma unroll
+  for (int k = 1; k <= XC_STASH; ++k)
+    if (k < K) {
+      const double xk = in.xc[k - 1];
+      xs[(k - 1) * (CPT * SWEEP_THREADS)] = xk;
+      m0 = fma(xk, s_beta[k * D + 0], m0);
+      m1 = fma(xk, s_beta[k * D + 1], m1);
+      if (D == 3) c.m2 = fma(xk, s_beta[k * D + 2], c.m2);
+    }
+  for (int k = XC_STASH + 1; k < K; ++k) {
     const double xk = a.Xc[(long long)(k - 1) * N + c.i];
     m0 = fma(xk, s_beta[k * D + 0], m0);
     m1 = fma(xk, s_beta[k * D + 1], m1);
@@ -698,7 +728,7 @@ __device__ __forceinline__ void cust_begin(Cust2<D, MODE>& c, const SweepArgs& a
 template <int D, int MODE>
 __device__ __forceinline__ void cust_end(Cust2<D, MODE>& c, const SweepArgs& a, const ModelConst& mc, const ChainParams& cp,
                                          const double* s_tab, long long* s_priv, const SweepStep& sw, int chain, long long cN, uint32_t c3,
-                                         long long i, const double* stash) {
+                                         long long i, const double* stash, const double* xs) {
   const int K = mc.K, S = mc.S;
   const long long N = mc.N;
   double le = 0.0, lik = 0.0;
@@ -741,18 +771,15 @@ __device__ __forceinline__ void cust_end(Cust2<D, MODE>& c, const SweepArgs& a, 
       lik = fmin(fmax(lik, -1048576.0), 1048576.0);
     }
   }
-  accumulate_stats<D>(mc, a.Xc, N, c.i, c.valid, c.ll - mc.center[0], c.lm - mc.center[1], (D == 3) ? le - mc.center[2] : 0.0, s_priv);
+  accumulate_stats<D>(mc, a.Xc, N, c.i, c.valid, c.ll - mc.center[0], c.lm - mc.center[1], (D == 3) ? le - mc.center[2] : 0.0, s_priv, xs,
+                      CPT * SWEEP_THREADS);
   if (sw.keep && c.valid) s_priv[(K * D + D * (D + 1) / 2) * SWEEP_THREADS + threadIdx.x] += to_fx(lik, mc.ll_scale);
 }
 
-#ifndef CLV_CPT
-#define CLV_CPT 2
-#endif
-constexpr int CPT = CLV_CPT;
 template <int D, int MODE>
 __device__ __forceinline__ void sweep_tile2(const SweepArgs& a, const ModelConst& mc, const ChainParams& cp, const double* s_beta,
                                             const double* s_tab, long long* s_priv, const SweepStep& sw, int chain, long long tile,
-                                            uint32_t c3, double* s_stash) {
+                                            uint32_t c3, double* s_stash, double* s_xc) {
   static_assert(MODE != MODE_INJECT, "two customers per thread: Philox modes only");
   constexpr bool E32 = (CLV_E32 != 0) && MODE == MODE_FAST;
   const int S = mc.S;
@@ -761,11 +788,19 @@ __device__ __forceinline__ void sweep_tile2(const SweepArgs& a, const ModelConst
   const double t3s = (MODE == MODE_FAST) ? 1.7320508075688772 : 1.0;
   const double s_l = cp.Sigma[0] * t3s, s_m = cp.Sigma[D + 1] * t3s;
   Cust2<D, MODE> c[CPT];
-  // customer j of this thread keeps its exact-path inputs at s_stash[(f CPT + j) 128 + tid], f = 0..4
+  // customer j of this thread keeps its exact-path inputs at s_stash[(f CPT + j) 128 + tid], f = 0..4, and its first
+  // covariates at s_xc[(k CPT + j) 128 + tid]
+  {
+    Cust2In in[CPT];
 #pragma unroll
-  for (int j = 0; j < CPT; ++j)
-    cust_begin<D, MODE>(c[j], a, mc, cp, s_beta, s_tab, sw, chain, cN, tile * (CPT * SWEEP_THREADS) + j * SWEEP_THREADS + threadIdx.x,
-                        c3, h00, h01, h11, s_stash + (size_t)j * E32_STASH * SWEEP_THREADS + threadIdx.x);
+    for (int j = 0; j < CPT; ++j)
+      cust_load<D>(in[j], a, mc, cN, tile * (CPT * SWEEP_THREADS) + j * SWEEP_THREADS + threadIdx.x);
+#pragma unroll
+    for (int j = 0; j < CPT; ++j)
+      cust_begin<D, MODE>(c[j], in[j], a, mc, cp, s_beta, s_tab, sw, chain, cN, tile * (CPT * SWEEP_THREADS) + j * SWEEP_THREADS + threadIdx.x,
+                          c3, h00, h01, h11, s_stash + (size_t)j * E32_STASH * SWEEP_THREADS + threadIdx.x,
+                          s_xc + j * SWEEP_THREADS + threadIdx.x);
+  }
   if constexpr (E32) {
     const double qa = cp.qa, qb = cp.qb, qc = cp.qc;
     for (int s = 0; s < S; ++s) {
@@ -822,7 +857,7 @@ __device__ __forceinline__ void sweep_tile2(const SweepArgs& a, const ModelConst
 #pragma unroll
   for (int j = 0; j < CPT; ++j)
     cust_end<D, MODE>(c[j], a, mc, cp, s_tab, s_priv, sw, chain, cN, c3, tile * (CPT * SWEEP_THREADS) + j * SWEEP_THREADS + threadIdx.x,
-                      s_stash + (size_t)j * E32_STASH * SWEEP_THREADS + threadIdx.x);
+                      s_stash + (size_t)j * E32_STASH * SWEEP_THREADS + threadIdx.x, s_xc + j * SWEEP_THREADS + threadIdx.x);
 }
 
 // the sweep kernel with CPT (= 2) customers per thread (tiles of 128 CPT customers)
@@ -836,6 +871,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS2) k_sweep2(SweepA
   __shared__ double s_tab[EXP_N];
   __shared__ unsigned long long s_acc[NSTAT_MAX + 1];
   __shared__ double s_stash[E32_STASH * CPT * SWEEP_THREADS];     // the exact path's inputs (E32)
+  __shared__ double s_xc[XC_STASH * CPT * SWEEP_THREADS];         // the first covariates of the tile's customers
   const ModelConst& mc = *a.mc;
   const int chain = blockIdx.y;
   const int tid = threadIdx.x;
@@ -860,23 +896,28 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS2) k_sweep2(SweepA
     // blocks that drew one tile more than the others run alone for a whole tile latency (~30 us with two customers per
     // thread).  Here the blocks of the (one-wave) grid draw tile numbers from a counter, and the tail of the tile list is
     // cut finer: the last customers go 128 at a time, one per thread -- half the latency per tile.
-    __shared__ unsigned int s_next;
+    // The number of a block's NEXT tile is drawn when the current tile starts and published when it ends, so the atomic's
+    // round trip hides behind the tile and one barrier per tile suffices (two slots, alternating).
+    __shared__ unsigned int s_next[2];
     unsigned int* ctr = a.tile_counter + (size_t)(a.sweep & 1u) * gridDim.y + chain;
     if (blockIdx.x == 0 && tid == 0) a.tile_counter[(size_t)((a.sweep + 1u) & 1u) * gridDim.y + chain] = 0u;   // for the next sweep
     const long long nt = a.n_big + a.n_small;
-    for (;;) {
-      if (tid == 0) s_next = atomicAdd(ctr, 1u);
-      __syncthreads();
-      const long long t = s_next;
-      __syncthreads();
+    if (tid == 0) s_next[0] = atomicAdd(ctr, 1u);
+    __syncthreads();
+    for (int p = 0;; p ^= 1) {
+      const long long t = s_next[p];
       if (t >= nt) break;
+      unsigned int nxt = 0u;
+      if (tid == 0) nxt = atomicAdd(ctr, 1u);
       if (CPT == 2 && t >= a.n_big) sweep_tile<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, 2 * a.n_big + (t - a.n_big), c3, s_stash);
-      else sweep_tile2<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, t, c3, s_stash);
+      else sweep_tile2<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, t, c3, s_stash, s_xc);
+      if (tid == 0) s_next[p ^ 1] = nxt;
+      __syncthreads();
     }
   } else {
     const long long ntiles = (mc.N + CPT * SWEEP_THREADS - 1) / (CPT * SWEEP_THREADS);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-      sweep_tile2<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, c3, s_stash);
+      sweep_tile2<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, tile, c3, s_stash, s_xc);
   }
   if (!a.pdl_early) pdl_launch_dependents();
   flush_stats(s_priv, s_acc, nstat, sw.keep != 0);
