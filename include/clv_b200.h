@@ -146,7 +146,8 @@ int clv_run(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* 
 int clv_run_resident(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, double* level2, double* loglik,
                      clv_progress_cb cb, void* user, int64_t trace);
 int clv_resident_draws(clv_sampler* h, const double** level1_dev, int64_t* n_draws);
-/* Advance n sweeps without storing draws (burn-in, benchmarks).  Asynchronous unless sync != 0. */
+/* Advance n sweeps without storing draws (burn-in, benchmarks).  Asynchronous unless sync != 0; a synchronous call
+ * also leaves z / tau of its last sweep in the state arrays clv_get_state reads. */
 int clv_advance(clv_sampler* h, int64_t n_sweeps, int sync);
 /* Same, synchronous, bracketed by CUDA events on the handle's stream: *elapsed_ms = device time of the n sweeps. */
 int clv_advance_timed(clv_sampler* h, int64_t n_sweeps, double* elapsed_ms);

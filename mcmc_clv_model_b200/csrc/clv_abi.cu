@@ -719,7 +719,7 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
     CKC(cudaMemsetAsync(h->d_tile_ctr, 0, sizeof(unsigned int) * 2 * C, h->stream));
   }
   if (h->pdl_mode == 0) {
-    const long long blocks = (long long)(h->cpt == 2 ? (h->grid2_dyn_x > 0 ? h->grid2_dyn_x : h->grid2_x) : h->grid_x) * h->chains, resident = (h->cpt == 2 ? (long long)CLV_MINBLOCKS2 : 8ll) * h->sm_count;
+    const long long blocks = (long long)(h->cpt == 2 ? (h->grid2_dyn_x > 0 ? h->grid2_dyn_x : h->grid2_x) : h->grid_x) * h->chains, resident = (long long)(h->cpt == 2 ? CLV_MINBLOCKS2 : CLV_MINBLOCKS) * h->sm_count;
     h->pdl_mode = (blocks >= resident) ? 1 : 2;
   }
   h->stats_smem = (size_t)(h->K * h->D + h->D * (h->D + 1) / 2 + 1) * SWEEP_THREADS * sizeof(long long);
@@ -1275,7 +1275,8 @@ int clv_advance(clv_sampler* h, int64_t n_sweeps, int sync) {
   // cooperative launches are bounded so that a runaway kernel cannot outlive the watchdog of a shared box
   for (int64_t done = 0; done < n_sweeps;) {
     const long long n = std::min<long long>(n_sweeps - done, 20000);
-    if (int r = run_segment(h, rc, n, false)) return r;
+    // a synchronous call leaves z / tau of its last sweep in the state arrays (clv_get_state)
+    if (int r = run_segment(h, rc, n, sync != 0 && done + n == n_sweeps)) return r;
     done += n;
   }
   if (sync) return check_device_error(h);

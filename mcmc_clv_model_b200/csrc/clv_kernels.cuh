@@ -22,10 +22,13 @@ constexpr int MAXD = 3;
 constexpr int NSTAT_MAX = MAXK * MAXD + 6;
 constexpr int SWEEP_THREADS = 128;
 constexpr int P2P_MAX_WORLD = 16;
-// 8 resident blocks of 128 threads per SM (<= 64 registers): measured 25% faster than the 80-register build,
-// the sweep being latency/issue bound (profiles/r01_kernel_ab.txt)
+// Resident blocks of 128 threads per SM for the one-customer kernels (k_sweep, k_persistent).  Round 1 ran them at 8 (64
+// registers: 25 % faster than 80 when this was the kernel of the 10 M-customer sweep, profiles/r01_kernel_ab.txt).  They now
+// serve the small problems (customers x chains < 100 000: at most 5 blocks per SM exist), where a sweep is bound by the
+// latency of one customer's dependent steps and the spills of the 64-register build sit on that path: 4 blocks per SM
+// (<= 128 registers, no spill) is 3-6 % faster there (C1 13.2 -> 12.4, C2 17.4 -> 16.6, C3 19.2 -> 18.6 us per sweep).
 #ifndef CLV_MINBLOCKS
-#define CLV_MINBLOCKS 8
+#define CLV_MINBLOCKS 4
 #endif
 
 enum : int { MODE_FAST = 0, MODE_STRICT = 1, MODE_INJECT = 2 };

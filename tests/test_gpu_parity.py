@@ -884,3 +884,58 @@ def test_injected_sweeps_at_full_cdnow_size_vs_oracle(cdnow_full, D, cov):
             np.testing.assert_allclose(out["level_1"][0], ora["level_1"][t], rtol=RTOL, err_msg=f"level_1 sweep {t}")
             np.testing.assert_allclose(out["level_2"][0], ora["level_2"][t], rtol=RTOL, atol=1e-9, err_msg=f"level_2 sweep {t}")
             np.testing.assert_allclose(out["loglik_sum"][0] / n, ora["log_likelihood"][t], rtol=RTOL)
+
+
+@pytest.mark.parametrize("cpt", ["1", "2"])
+@pytest.mark.parametrize("case", ["regular_sigma", "near_singular_sigma"])
+def test_fast_kernel_exact_path_and_guards_on_adversarial_rows(cpt, case, monkeypatch):
+    """The fp32-screened Metropolis decision (CLV_E32) must ALWAYS equal the fp64 expression of the reference: rows that
+    fail the screen's rounding guard (x = 6e7 transactions; a nearly singular Sigma, where every customer fails it),
+    proposals beyond the +-70 clip, log mu crossing 5 (target -inf, bi:308-309) and states that start there.  Trivariate
+    order (level 1 first, so the Sigma given to set_state is the one the Metropolis steps see); the kernel's own FAST
+    variates are replayed through the oracle from the same state: z bit-exact, continuous 1e-6, after each of 3 sweeps."""
+    rs = np.random.RandomState(11)
+    n, S, D, seed = 700, 20, 3, 77
+    T = np.full(n, 39.0)
+    x = rs.poisson(3.0, n).astype(np.int64)
+    t_x = np.where(x > 0, rs.uniform(1.0, 38.0, n), 0.0)
+    x[:10] = 60_000_000                       # 420 x > the guard's budget: always the exact path
+    t_x[:10] = 35.0
+    X = np.column_stack([np.ones(n), rs.normal(size=n)])
+    log_s = rs.normal(3.5, 0.6, n)
+    cbs = ao.Cbs(x=x, t_x=t_x, T_cal=T, X=X, log_s=log_s)
+    hyper = ao.default_hyper(2, D)
+    st = ao.init_state(cbs, hyper, D)
+    ll0 = rs.normal(-2.5, 1.0, n)
+    lm0 = rs.normal(-3.5, 1.0, n)
+    ll0[:10] = np.log(6e7 / 39.0)
+    ll0[10:20] = 69.95                         # proposals cross +70: clipped by the exact path
+    lm0[20:24] = 4.999                         # proposals cross log mu = 5: never accepted
+    lm0[24:28] = 5.001                         # current target -inf: the first admissible proposal is accepted
+    lm0[28:30] = 6.0
+    ll0[30:34] = -69.9
+    if case == "regular_sigma":
+        Sigma = np.array([[1.3, 0.2, 0.1], [0.2, 2.1, -0.3], [0.1, -0.3, 0.8]])
+    else:
+        Sigma = np.array([[2e-13, 1e-14, 0.0], [1e-14, 3e-13, 0.0], [0.0, 0.0, 0.7]])
+    beta = np.array([[-2.5, -3.5, 3.5], [0.1, -0.2, 0.05]])
+    st["lam"], st["mu"] = np.exp(ll0), np.exp(lm0)
+    st["beta"], st["Sigma"] = beta.copy(), Sigma.copy()
+    src = PhiloxStreams(seed, 0, np.arange(n), S, D, 2, level1_variates=_device_fast_variates(seed, n, S))
+    monkeypatch.setenv("CLV_SWEEP_CPT", cpt)
+    with Sampler(x, t_x, T, X, log_s, model_dim=D, chains=1, n_mh_steps=S, seed=seed, rng="fast", sweep_mode="stream") as s:
+        s.set_state(0, log_lambda=np.log(st["lam"]), log_mu=np.log(st["mu"]), log_eta=np.zeros(n), beta=beta, Sigma=Sigma)
+        for step in range(1, 4):
+            src.begin_sweep(step)
+            with np.errstate(all="ignore"):
+                ao.sweep(cbs, st, hyper, src, D, S)
+            s.advance(1)
+            dev = s.get_state(0)
+            np.testing.assert_array_equal(dev["z"], st["z"].astype(float), err_msg=f"z, sweep {step}")
+            np.testing.assert_allclose(dev["log_lambda"], np.log(st["lam"]), rtol=RTOL, atol=1e-9, err_msg=f"sweep {step}")
+            np.testing.assert_allclose(dev["log_mu"], np.log(st["mu"]), rtol=RTOL, atol=1e-9, err_msg=f"sweep {step}")
+            np.testing.assert_allclose(dev["tau"], st["tau"], rtol=RTOL, err_msg=f"sweep {step}")
+            np.testing.assert_allclose(dev["beta"], st["beta"], rtol=RTOL, atol=1e-9)
+            np.testing.assert_allclose(dev["Sigma"], st["Sigma"], rtol=RTOL, atol=1e-12)
+    if case == "regular_sigma":
+        assert np.log(st["lam"])[10:20].max() < 69.0 and (np.log(st["mu"])[24:30] <= 5.0).all()   # the chain did leave those corners

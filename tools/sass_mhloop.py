@@ -19,27 +19,22 @@ for a, t in ins:
     mm = re.search(r"BRA\S* (?:\S+, )?0x([0-9a-f]+)", t)
     if mm and int(mm.group(1), 16) < a:
         back.append((a, int(mm.group(1), 16)))
-a, b = min(((a, b) for a, b in back if b < cos[0] < a), key=lambda t: t[0] - t[1])
+# the Metropolis loop: the innermost backward branch whose body holds 2 x cpt MUFU.COS (two t3 variates per customer and step)
+a, b = min(((a, b) for a, b in back if sum(1 for c in cos if b <= c <= a) == 2 * cpt), key=lambda t: t[0] - t[1])
 body = [(x, t) for x, t in ins if b <= x <= a]
-# the rarely executed regions: the clip calls and the exact exp() of the accept tie zone (between the DSETP that follows
-# the fp32 screen and the BSYNC that closes it)
+# the rarely executed regions: every forward branch of the loop body that jumps over a CALL skips one (the exact fp64
+# re-decision of the accept tie zone with its clip to +-70: ~1e-4 of the steps; in the CLV_E32=0 / one-customer builds also
+# the separate clip calls)
 def opcode(t):
     return (t.split()[1] if t.startswith("@") else t.split()[0]).split(".")[0]
 rare = set()
-# every tie zone: from the DSETP.GE (d >= 0) that follows a failed fp32 screen to the DSETP.GT (exp(d) > u) that closes it
-pos = 0
-while True:
-    tie0 = next((x for x, t in body if x > pos and "DSETP.GE" in t), None)
-    tie1 = next((x for x, t in body if tie0 and x > tie0 and t.startswith("DSETP.GT")), None)
-    if not (tie0 and tie1):
-        break
-    rare |= {x for x, t in body if tie0 < x < tie1}
-    pos = tie1
-# every clip: from the branch that skips it to the last CALL of the group
 calls = [x for x, t in body if "CALL" in t]
-for cx in calls:
-    lo = max((x for x, t in body if x < cx and "BRA" in t and x not in rare), default=cx)
-    rare |= {x for x, t in body if lo < x <= cx + 0x30}
+for x, t in body:
+    mm = re.search(r"BRA\S* (?:\S+, )?0x([0-9a-f]+)", t)
+    if mm:
+        tgt = int(mm.group(1), 16)
+        if tgt > x and any(x < cx < tgt for cx in calls):
+            rare |= {y for y, _ in body if x < y < tgt}
 hot = [(x, t) for x, t in body if x not in rare]
 groups = collections.OrderedDict([
     ("Philox4x32-10 (IMAD.WIDE + LOP3 + PRMT)", lambda t: opcode(t) in ("LOP3", "PRMT") or "IMAD.WIDE" in t),
@@ -47,7 +42,7 @@ groups = collections.OrderedDict([
     ("fp32 + SFU (FFMA / FMUL / FADD / FSETP / MUFU / conversions)", lambda t: opcode(t) in ("FFMA", "FMUL", "FADD", "FSETP", "MUFU", "I2FP", "F2F", "I2F")),
     ("selects / predicates (FSEL / SEL / PLOP3 / ISETP / VIMNMX)", lambda t: opcode(t) in ("FSEL", "SEL", "PLOP3", "ISETP", "VIMNMX")),
     ("constant / uniform loads (LDC / LDCU)", lambda t: opcode(t) in ("LDC", "LDCU")),
-    ("shared-memory table (LDS + address)", lambda t: opcode(t) in ("LDS", "IADD3")),
+    ("shared / local memory (LDS / STS / LDL / STL + address)", lambda t: opcode(t) in ("LDS", "STS", "LDL", "STL", "IADD3")),
     ("moves / integer housekeeping / branches", lambda t: True)])
 cnt = collections.Counter()
 for x, t in hot:
@@ -59,12 +54,13 @@ out = os.path.join(ROOT, "profiles", f"{tag}_sweep_mhloop_sass.md" if cpt == 2 e
 with open(out, "w") as f:
     f.write(f"# {tag}: SASS of the Metropolis loop of `{'k_sweep2' if cpt == 2 else 'k_sweep'}<2,FAST>` (cuobjdump -sass of the committed build)\n\n")
     f.write(f"`{name}`: loop 0x{b:04x} .. 0x{a:04x}, {len(body)} instructions in the loop body ({cpt} customer(s) per thread and trip), of which "
-            f"{len(body) - len(hot)} sit in the rarely taken regions (the clip of a proposal beyond +-70: 1 step in 50 000; the exact fp64 "
-            f"`exp` of the accept tie zone: ~1e-5 of the steps), leaving {len(hot)} instructions per trip = **{len(hot) / cpt:.0f} instructions per "
+            f"{len(body) - len(hot)} sit in the rarely taken regions (the exact fp64 re-decision of the accept tie zone, which also clips a "
+            f"proposal beyond +-70: ~1e-4 of the steps), leaving {len(hot)} instructions per trip = **{len(hot) / cpt:.0f} instructions per "
             f"customer Metropolis step** on the hot path:\n\n| group | instructions per trip |\n|---|---|\n")
     for g in groups:
         f.write(f"| {g} | {cnt[g]} |\n")
-    f.write(f"\nLocal-memory instructions in the loop: {sum(1 for x, t in body if 'LDL' in t or 'STL' in t)} (no spill).\n\n```\n")
+    nloc = sum(1 for x, t in body if 'LDL' in t or 'STL' in t)
+    f.write(f"\nLocal-memory instructions in the loop: {nloc} ({'no spill' if nloc == 0 else 'register spills at the 64 registers of 8 blocks per SM'}).\n\n```\n")
     for x, t in body:
         f.write(f"{x:04x}{' r' if x in rare else '  '} {t}\n")
     f.write("```\n(`r` marks the rarely executed regions.)\n")
