@@ -705,13 +705,13 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
     // dynamic tiles for k_sweep2 (CLV_SWEEP_DYNAMIC=0 switches to the static grid-stride split): a one-wave grid, and the last
     // two rounds' worth of customers cut into 128-customer tiles
     const char* env = getenv("CLV_SWEEP_DYNAMIC");
-    const bool dyn = CPT == 2 && !(env && atoi(env) == 0);
+    const bool dyn = CPT >= 2 && !(env && atoi(env) == 0);
     const long long resident = std::max<long long>(1, (long long)h->sm_count * CLV_MINBLOCKS2 / h->chains);
     long long small_rounds = 1;          // measured at 1.25 M customers: 0 / 1 / 2 / 3 rounds -> 194.5 / 192.8 / 196.5 / 197.0 us (static: 201.3)
     if (const char* e2 = getenv("CLV_SWEEP_SMALL_ROUNDS")) small_rounds = std::max(0ll, atoll(e2));
     const long long small_cust = std::min<long long>(h->N / 4, resident * small_rounds * SWEEP_THREADS);   // at most a quarter of the shard
-    h->n_big = (h->N - small_cust) / (2 * SWEEP_THREADS);
-    h->n_small = (h->N - h->n_big * 2 * SWEEP_THREADS + SWEEP_THREADS - 1) / SWEEP_THREADS;
+    h->n_big = (h->N - small_cust) / (CPT * SWEEP_THREADS);
+    h->n_small = (h->N - h->n_big * CPT * SWEEP_THREADS + SWEEP_THREADS - 1) / SWEEP_THREADS;
     // only when a block has at least two tiles to draw: with one tile per block (many chains of a small data set) the counter
     // and the finer tail only cost (56 x 2 357 customers: 37.2 vs 31.4 us per sweep)
     h->grid2_dyn_x = (dyn && h->n_big + h->n_small >= 2 * resident) ? (int)resident : 0;

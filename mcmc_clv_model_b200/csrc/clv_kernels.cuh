@@ -351,8 +351,9 @@ struct E32Prop {
   double pl, pm, Qp;
   float Ep, tEp, amax;
 };
-__device__ __forceinline__ void e32_propose(const E32State& st, E32Prop& pr, double tl, double tm, double s_l, double s_m,
+__device__ __forceinline__ void e32_propose(const E32State& st, E32Prop& pr, float tl32, float tm32, double s_l, double s_m,
                                             double qa, double qb, double qc) {
+  const double tl = (double)tl32, tm = (double)tm32;
   pr.pl = st.ll + s_l * tl;                     // bi:318-324 (clip: in the exact path)
   pr.pm = st.lm + s_m * tm;
   pr.Qp = q_part(pr.pl, pr.pm, qa, qb, qc, st.k0, st.k1);
@@ -405,21 +406,26 @@ __device__ __forceinline__ void accumulate_stats(const ModelConst& mc, const dou
                                                  long long i, bool valid, double yc0, double yc1, double yc2,
                                                  long long* s_priv, const double* xs = nullptr, int xs_stride = 0) {
   if (!valid) return;
+  // to_fx(xk y, sc) = rn((xk y) sc): sc is a power of two, so rn(xk (y sc)) is the same integer -- the responses are
+  // scaled once per customer instead of once per term
   const double sc = mc.fx_scale;
   const int K = mc.K;
   const double y[3] = {yc0, yc1, yc2};
+  const double ys[3] = {yc0 * sc, yc1 * sc, yc2 * sc};
   long long* col = s_priv + threadIdx.x;
+  // (a 64-bit shared-memory atomicAdd would be one instruction in source but compiles to an ATOMS.CAS loop: plain
+  // load / add / store on the thread's own column it is)
   for (int k = 0; k < K; ++k) {
     const double xk = (k == 0) ? 1.0 : (xs && k <= XC_STASH) ? xs[(k - 1) * xs_stride] : Xc[(long long)(k - 1) * N + i];
 #pragma unroll
-    for (int d = 0; d < D; ++d) col[(k * D + d) * SWEEP_THREADS] += to_fx(xk * y[d], sc);
+    for (int d = 0; d < D; ++d) col[(k * D + d) * SWEEP_THREADS] += __double2ll_rn(xk * ys[d]);
   }
   int t = K * D;
 #pragma unroll
   for (int d = 0; d < D; ++d)
 #pragma unroll
     for (int e = d; e < D; ++e) {
-      col[t * SWEEP_THREADS] += to_fx(y[d] * y[e], sc);
+      col[t * SWEEP_THREADS] += __double2ll_rn(ys[d] * y[e]);
       ++t;
     }
 }
@@ -529,7 +535,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, const ModelConst&
       for (int s = 0; s < S; ++s) {
         const uint4 A = philox4x32_10_rk(gid, sw.sweep, 1u + (uint32_t)s, c3, a.rk);   // word layout: clv_rng.cuh
         E32Prop pr;
-        e32_propose(st, pr, (double)t3_fast(A.x, A.y), (double)t3_fast(A.z, A.w), s_l, s_m, qa, qb, qc);
+        e32_propose(st, pr, t3_fast(A.x, A.y), t3_fast(A.z, A.w), s_l, s_m, qa, qb, qc);
         e32_decide(st, pr, low_bytes(A.x, A.y, A.z, A.w), qa, qb, qc, stash, &cp, s_tab);
       }
       ll = st.ll;
@@ -813,7 +819,7 @@ __device__ __forceinline__ void sweep_tile2(const SweepArgs& a, const ModelConst
       for (int j = 0; j < CPT; ++j) {
         const uint4 A = philox4x32_10_rk(c[j].gid, sw.sweep, 1u + (uint32_t)s, c3, a.rk);
         ur[j] = low_bytes(A.x, A.y, A.z, A.w);
-        e32_propose(c[j].st, pr[j], (double)t3_fast(A.x, A.y), (double)t3_fast(A.z, A.w), s_l, s_m, qa, qb, qc);
+        e32_propose(c[j].st, pr[j], t3_fast(A.x, A.y), t3_fast(A.z, A.w), s_l, s_m, qa, qb, qc);
       }
 #pragma unroll
       for (int j = 0; j < CPT; ++j)
@@ -912,7 +918,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, CLV_MINBLOCKS2) k_sweep2(SweepA
       if (t >= nt) break;
       unsigned int nxt = 0u;
       if (tid == 0) nxt = atomicAdd(ctr, 1u);
-      if (CPT == 2 && t >= a.n_big) sweep_tile<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, 2 * a.n_big + (t - a.n_big), c3, s_stash);
+      if (CPT >= 2 && t >= a.n_big) sweep_tile<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, CPT * a.n_big + (t - a.n_big), c3, s_stash);
       else sweep_tile2<D, MODE>(a, mc, cp, s_beta, s_tab, s_priv, sw, chain, t, c3, s_stash, s_xc);
       if (tid == 0) s_next[p ^ 1] = nxt;
       __syncthreads();

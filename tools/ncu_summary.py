@@ -54,7 +54,7 @@ with open(out_md, "w") as f:
         share = (f"{100 * sum(v) / tot:.1f} %" if any(t in k for t in STEP) else
                  "(once per data set)" if any(t in k for t in ONCE) else "(not part of a step)")
         f.write(f"| `{k}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {sum(v) / 1e6:.3f} | {share} |\n")
-    f.write("\n## `k_sweep<2,FAST>` (full set)\n\n| metric | value |\n|---|---|\n")
+    f.write(f"\n## `{js['kernel']}` (full set)\n\n| metric | value |\n|---|---|\n")
     f.write(f"| duration | {js['duration_us']:.1f} us |\n| DRAM read / write per launch | {dr / 1e6:.1f} MB / {dw / 1e6:.1f} MB = {(dr + dw) / ncust:.1f} B per customer (algorithmic 84 B) |\n")
     f.write(f"| warp instructions per warp per sweep | {js['warp_instructions_per_warp_sweep']:.0f} (20 MH steps) |\n")
     for n in names[2:]:
