@@ -703,11 +703,11 @@ int clv_create(clv_sampler** out, const clv_config* cfg) {
   }
   {
     // dynamic tiles for k_sweep2 (CLV_SWEEP_DYNAMIC=0 switches to the static grid-stride split): a one-wave grid, and the last
-    // two rounds' worth of customers cut into 128-customer tiles
+    // rounds' worth of customers cut into 128-customer tiles
     const char* env = getenv("CLV_SWEEP_DYNAMIC");
     const bool dyn = CPT >= 2 && !(env && atoi(env) == 0);
     const long long resident = std::max<long long>(1, (long long)h->sm_count * CLV_MINBLOCKS2 / h->chains);
-    long long small_rounds = 1;          // measured at 1.25 M customers: 0 / 1 / 2 / 3 rounds -> 194.5 / 192.8 / 196.5 / 197.0 us (static: 201.3)
+    long long small_rounds = 2;          // E32 kernel, 1 vs 2 rounds: 1.25 M 173.3 / 171.3 us, 2.5 M 335.0 / 331.7, 10 M 1268.8 / 1260.8 (profiles/r02_kernel_ab.txt)
     if (const char* e2 = getenv("CLV_SWEEP_SMALL_ROUNDS")) small_rounds = std::max(0ll, atoll(e2));
     const long long small_cust = std::min<long long>(h->N / 4, resident * small_rounds * SWEEP_THREADS);   // at most a quarter of the shard
     h->n_big = (h->N - small_cust) / (CPT * SWEEP_THREADS);
