@@ -297,13 +297,16 @@ def run_ours(args):
     # ---- synthetic C4 shard (device generator; global ids => identical customers for any GPU count) ----
     cols = generate_cbs_arrays(n_loc, C4_BETA, C4_GAMMA, T_cal=C4_T_CAL, T_star=39.0, seed=C4_SEED, gid_offset=lo,
                                device=local, with_truth=True)
-    pinned = {k: _pin(cols[k]) for k in ("x", "t_x", "T_cal", "X")}
+    # the frame as mcmc_draw_parameters hands it over: x, t_x, T_cal and the covariate COLUMNS (the intercept of bi:468-470
+    # is implicit: clv_set_data_columns)
+    pinned = {k: _pin(cols[k]) for k in ("x", "t_x", "T_cal")}
+    pinned_cov = [_pin(cols["X"][:, k]) for k in range(1, K_COV)]
 
     def make(rng="fast", src=None):
         # CBS columns from host memory -> device; exact init statistics on the device (+ NCCL when sharded)
-        src = src or {k: v[0] for k, v in pinned.items()}
+        src = src or dict({k: v[0] for k, v in pinned.items()}, cov=[v[0] for v in pinned_cov])
         comm = (broadcast_unique_id(Sampler.comm_unique_id), rank, world) if world > 1 else None
-        s = Sampler(src["x"], src["t_x"], src["T_cal"], src["X"], model_dim=2, chains=1,
+        s = Sampler(src["x"], src["t_x"], src["T_cal"], src["cov"], model_dim=2, chains=1,
                     n_mh_steps=S_MH, seed=args.seed, rng=rng, device=local, n_global=n_tot, gid_offset=lo, comm=comm)
         if world > 1 and args.collective == "p2p":
             from mcmc_clv_model_b200.distributed import connect_p2p
@@ -417,13 +420,14 @@ def run_ours(args):
     sw.close()
     e2e_runs = [e2e_once(None) for _ in range(2)]
     e2e_s, small = min(e2e_runs)
-    h2d = n_loc * (4 + 8 + 8 + 8 * K_COV)
+    h2d = n_loc * (4 + 8 + 8 + 8 * (K_COV - 1))
     d2h = n_loc * 32 + small
     e2e = {"value": n_tot * args.steps / e2e_s, "unit": "customer-updates/s", "h2d_bytes_per_step": h2d / args.steps,
            "d2h_bytes_per_step": d2h / args.steps, "seconds": e2e_s, "seconds_all_runs": [r[0] for r in e2e_runs],
-           "what": "best of two timed runs of: clv_create + clv_set_data (page-locked host CBS -> device) + clv_init_state + clv_run(K sweeps, 1 kept "
+           "what": "best of two timed runs of: clv_create + clv_set_data_columns (page-locked host CBS columns -> device) + clv_init_state + clv_run(K sweeps, 1 kept "
                    "level-1 draw -> host) + clv_destroy, i.e. everything mcmc_draw_parameters does after the DataFrame is unpacked"}
-    pageable = {k: np.array(cols[k], copy=True) for k in ("x", "t_x", "T_cal", "X")}     # ordinary NumPy arrays, as the API receives them
+    pageable = {k: np.array(cols[k], copy=True) for k in ("x", "t_x", "T_cal")}          # ordinary NumPy arrays, as the API receives them
+    pageable["cov"] = [np.array(cols["X"][:, k], copy=True) for k in range(1, K_COV)]
     e2e_p_runs = [e2e_once(pageable)[0] for _ in range(2)]
     e2e_p = min(e2e_p_runs)
     e2e_pageable = {"value": n_tot * args.steps / e2e_p, "unit": "customer-updates/s", "seconds": e2e_p, "seconds_all_runs": e2e_p_runs,

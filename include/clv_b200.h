@@ -100,6 +100,11 @@ const char* clv_last_error(const clv_sampler* h);
  * log_s: column "log_s" (tri:329), NULL for D=2. */
 int clv_set_data(clv_sampler* h, const int32_t* x, const double* t_x, const double* T_cal,
                  const double* X, const double* log_s);
+/* The same frame handed over column by column, the way the DataFrame of bi:459-470 holds it: cov[k] (k = 0 .. K-2) is the
+ * column named covariates[k] (n_local doubles); the intercept column the reference prepends (bi:468-470) is implicit.
+ * No row-major matrix has to be assembled on the host and the intercept's 8 B per customer never cross PCIe. */
+int clv_set_data_columns(clv_sampler* h, const int32_t* x, const double* t_x, const double* T_cal,
+                         const double* const* cov, const double* log_s);
 /* hyper dict of bi:474-479 / tri:622-626: beta0 K x D, A0 K x K, nu0, gamma0 D x D.
  * Row 0 of beta0 is overwritten from the init statistics exactly as bi:373-374 / tri:497-499 do. */
 int clv_set_hyper(clv_sampler* h, const double* beta0, const double* A0, double nu0, const double* gamma0);

@@ -63,6 +63,7 @@ SIGNATURES = {
     "clv_destroy": (None, [C.c_void_p]),
     "clv_last_error": (C.c_char_p, [C.c_void_p]),
     "clv_set_data": (C.c_int, [C.c_void_p, c_int32_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "clv_set_data_columns": (C.c_int, [C.c_void_p, c_int32_p, c_double_p, c_double_p, C.POINTER(c_double_p), c_double_p]),
     "clv_set_hyper": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_double, c_double_p]),
     "clv_init_state": (C.c_int, [C.c_void_p, C.POINTER(InitStats)]),
     "clv_get_init_stats": (C.c_int, [C.c_void_p, C.POINTER(InitStats), c_double_p]),

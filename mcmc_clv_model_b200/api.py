@@ -37,26 +37,25 @@ def _seed_value(seed):
 
 
 def _design(cal_cbs, covariates, validate):
-    import pandas as pd  # the entry points take DataFrames, like the reference
+    """The columns the sampler reads.  The reference copies the frame and prepends an intercept column to build an (N, K)
+    matrix (bi:467-470); here the caller's frame is only READ (so it cannot be mutated either) and the covariate columns
+    go to the device as they are -- the intercept is implicit in the kernels (clv_set_data_columns)."""
     if covariates is None:
         covariates = []
+    covariates = list(covariates)
     if validate:                                                    # bi:461-465 (tri does not validate)
         for col in ("x", "t_x", "T_cal"):
             if col not in cal_cbs:
                 raise ValueError(f"cal_cbs missing required column '{col}'")
         if not all(col in cal_cbs for col in covariates):
             raise ValueError("some covariate columns not in cal_cbs")
-    cbs = cal_cbs.copy().reset_index(drop=True)                     # bi:467: caller's frame is never mutated
-    cbs["intercept"] = 1.0
-    cols = ["intercept"] + list(covariates)
-    X = cbs[cols].to_numpy(float)
-    assert isinstance(cbs, pd.DataFrame)
-    return cbs, np.ascontiguousarray(X)
+    return [cal_cbs[c].to_numpy(dtype=float) for c in covariates]   # KeyError for a missing column, as cbs[cols] (tri:617)
 
 
 def _run(cal_cbs, covariates, mcmc, burnin, thin, chains, seed, trace, n_mh_steps, D, rng, compat, devices,
          hyper=None, return_samplers=False):
-    cbs, X = _design(cal_cbs, covariates, validate=(D == 2))
+    X = _design(cal_cbs, covariates, validate=(D == 2))
+    cbs = cal_cbs
     x = cbs["x"].to_numpy()
     t_x = cbs["t_x"].to_numpy(float)
     T_cal = cbs["T_cal"].to_numpy(float)
@@ -66,7 +65,7 @@ def _run(cal_cbs, covariates, mcmc, burnin, thin, chains, seed, trace, n_mh_step
     devices = list(devices) if devices is not None else _env_devices()
     chains = int(chains)
     seed_v = _seed_value(seed)
-    K = X.shape[1]
+    K = len(X) + 1
     hyper = hyper or default_hyper(K, D)
     tot = int(burnin) + int(mcmc)
 
@@ -96,7 +95,7 @@ def _run(cal_cbs, covariates, mcmc, burnin, thin, chains, seed, trace, n_mh_step
     else:
         with ThreadPoolExecutor(len(groups)) as ex:
             outs = list(ex.map(work, groups))
-    N = X.shape[0]
+    N = len(x)
     lvl1, lvl2, lls = [], [], []
     for o in outs:
         for c in range(o["level_2"].shape[0]):

@@ -799,17 +799,44 @@ void clv_destroy(clv_sampler* h) {
   delete h;
 }
 
-int clv_set_data(clv_sampler* h, const int32_t* x, const double* t_x, const double* T_cal, const double* X,
-                 const double* log_s) {
-  if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
-  if (!x || !t_x || !T_cal || !X) return fail(h, CLV_ERR_ARG, "clv_set_data: null column");
-  if (h->D == 3 && !log_s) return fail(h, CLV_ERR_ARG, "clv_set_data: log_s is required for the trivariate model");
+// the columns every model needs (x, t_x, T_cal, log_s): enqueued on the handle's stream, not synchronised
+static int upload_cbs_columns(clv_sampler* h, const int32_t* x, const double* t_x, const double* T_cal, const double* log_s) {
   CK(h, cudaSetDevice(h->cfg.device)); t_alloc_stream = h->stream; ensure_pool(h->cfg.device);
   const size_t N = (size_t)h->N;
   CK(h, cudaMemcpyAsync(h->d_x, x, N * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CK(h, copy_to_device_staged(h->d_tx, t_x, N * sizeof(double), h->stream));
   CK(h, copy_to_device_staged(h->d_T, T_cal, N * sizeof(double), h->stream));
   if (h->D == 3) CK(h, cudaMemcpyAsync(h->d_logs, log_s, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return CLV_OK;
+}
+
+// The frame column by column (a DataFrame's own layout): covariate k lands in its SoA column directly -- no row-major
+// matrix on the host, no intercept column over PCIe (8 B per customer), no split kernel.
+int clv_set_data_columns(clv_sampler* h, const int32_t* x, const double* t_x, const double* T_cal, const double* const* cov,
+                         const double* log_s) {
+  if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
+  if (!x || !t_x || !T_cal || (h->K > 1 && !cov)) return fail(h, CLV_ERR_ARG, "clv_set_data_columns: null column");
+  for (int k = 0; k + 1 < h->K; ++k)
+    if (!cov[k]) return fail(h, CLV_ERR_ARG, "clv_set_data_columns: covariate column %d is null", k);
+  if (h->D == 3 && !log_s) return fail(h, CLV_ERR_ARG, "clv_set_data_columns: log_s is required for the trivariate model");
+  if (int rc = upload_cbs_columns(h, x, t_x, T_cal, log_s)) return rc;
+  const size_t N = (size_t)h->N;
+  for (int k = 0; k + 1 < h->K; ++k)
+    CK(h, copy_to_device_staged(h->d_Xc + (size_t)k * N, cov[k], N * sizeof(double), h->stream));
+  cudaError_t es = cudaStreamSynchronize(h->stream);
+  if (es != cudaSuccess) return fail(h, CLV_ERR_CUDA, "clv_set_data_columns failed: %s", cudaGetErrorString(es));
+  h->have_data = true;
+  h->inited = false;
+  return CLV_OK;
+}
+
+int clv_set_data(clv_sampler* h, const int32_t* x, const double* t_x, const double* T_cal, const double* X,
+                 const double* log_s) {
+  if (!h) return fail(nullptr, CLV_ERR_ARG, "null handle");
+  if (!x || !t_x || !T_cal || !X) return fail(h, CLV_ERR_ARG, "clv_set_data: null column");
+  if (h->D == 3 && !log_s) return fail(h, CLV_ERR_ARG, "clv_set_data: log_s is required for the trivariate model");
+  if (int rc = upload_cbs_columns(h, x, t_x, T_cal, log_s)) return rc;
+  const size_t N = (size_t)h->N;
   double* d_rows = nullptr;
   int bad_intercept = 0;
   if (h->K > 1) {
@@ -865,6 +892,21 @@ static int device_init_stats(clv_sampler* h, clv_init_stats* out, std::vector<do
   const double n = (double)h->cfg.n_global;
   std::vector<double> tot(NQ_MAX, 0.0);
   double max_abs_x = 1.0;
+  // K <= 5: the register-accumulating instantiation (same totals bit for bit); CLV_INIT_GENERIC=1 forces the general kernel
+  const char* genv = getenv("CLV_INIT_GENERIC");
+  const bool generic_only = genv && atoi(genv) != 0;
+  auto launch_q = [&]() {
+    const dim3 grid(h->sm_count * 8), block(256);
+    switch (generic_only ? 0 : K) {
+      case 1: k_init_quantities_t<1><<<grid, block, 0, h->stream>>>(a); break;
+      case 2: k_init_quantities_t<2><<<grid, block, 0, h->stream>>>(a); break;
+      case 3: k_init_quantities_t<3><<<grid, block, 0, h->stream>>>(a); break;
+      case 4: k_init_quantities_t<4><<<grid, block, 0, h->stream>>>(a); break;
+      case 5: k_init_quantities_t<5><<<grid, block, 0, h->stream>>>(a); break;
+      default: k_init_quantities<<<grid, block, 0, h->stream>>>(a);
+    }
+    h->launches++;
+  };
   auto run_phase = [&](int phase, int nq) -> int {
     std::vector<unsigned long long> hmax(nq);
     std::vector<long long> hsum(2 * nq);
@@ -872,8 +914,7 @@ static int device_init_stats(clv_sampler* h, clv_init_stats* out, std::vector<do
     a.mode = 0;
     CK(h, cudaMemsetAsync(d_max, 0, sizeof(unsigned long long) * NQ_MAX, h->stream));
     CK(h, cudaMemsetAsync(d_sum, 0, sizeof(long long) * NQ_MAX * 2, h->stream));
-    k_init_quantities<<<h->sm_count * 8, 256, 0, h->stream>>>(a);
-    h->launches++;
+    launch_q();
     CK(h, cudaGetLastError());
     if (h->comm) {
       int r = g_nccl.AllReduce(d_max, d_max, (size_t)nq, 5 /*ncclUint64*/, 2 /*ncclMax*/, h->comm, h->stream);
@@ -891,8 +932,7 @@ static int device_init_stats(clv_sampler* h, clv_init_stats* out, std::vector<do
       if (phase == 0 && q >= 3) max_abs_x = std::max(max_abs_x, std::sqrt(m));   // diagonal pairs give max |X_k|^2
     }
     a.mode = 1;
-    k_init_quantities<<<h->sm_count * 8, 256, 0, h->stream>>>(a);
-    h->launches++;
+    launch_q();
     CK(h, cudaGetLastError());
     if (h->comm) {
       int r = g_nccl.AllReduce(d_sum, d_sum, (size_t)nq * 2, NCCL_INT64, NCCL_SUM, h->comm, h->stream);

@@ -49,10 +49,20 @@ class Sampler:
         x = np.ascontiguousarray(x, dtype=np.int32)
         t_x = np.ascontiguousarray(t_x, dtype=np.float64)
         T_cal = np.ascontiguousarray(T_cal, dtype=np.float64)
-        X = np.ascontiguousarray(X, dtype=np.float64)
-        if X.ndim != 2 or X.shape[0] != x.size:
-            raise ValueError("X must be (N, K)")
-        N, K = X.shape
+        cov_cols = None
+        if isinstance(X, (list, tuple)):
+            # the covariate columns themselves, as a DataFrame holds them (the intercept of bi:468-470 is implicit): they go
+            # to the device one by one (clv_set_data_columns); no (N, K) matrix is assembled on the host
+            cov_cols = [np.ascontiguousarray(c, dtype=np.float64) for c in X]
+            if any(c.ndim != 1 or c.size != x.size for c in cov_cols):
+                raise ValueError("every covariate column must have N entries")
+            N, K = x.size, len(cov_cols) + 1
+            X = None
+        else:
+            X = np.ascontiguousarray(X, dtype=np.float64)
+            if X.ndim != 2 or X.shape[0] != x.size:
+                raise ValueError("X must be (N, K)")
+            N, K = X.shape
         D = int(model_dim)
         if D == 3:
             if log_s is None:
@@ -71,13 +81,20 @@ class Sampler:
                        gid_offset=int(gid_offset), seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
         L.check(self.lib.clv_create(C.byref(self.h), C.byref(cfg)))
         try:
-            try:
-                L.check(self.lib.clv_set_data(self.h, x.ctypes.data_as(L.c_int32_p), L.dptr(t_x), L.dptr(T_cal),
-                                              L.dptr(X), L.dptr(log_s)), self.h)
-            except L.ClvError as e:        # the intercept column is validated on the device during the upload
-                if "intercept" in str(e):
-                    raise ValueError("column 0 of X must be the intercept (all ones)") from None
-                raise
+            if cov_cols is not None:
+                ptrs = (L.c_double_p * max(len(cov_cols), 1))(*[L.dptr(c) for c in cov_cols])
+                L.check(self.lib.clv_set_data_columns(self.h, x.ctypes.data_as(L.c_int32_p), L.dptr(t_x), L.dptr(T_cal),
+                                                      ptrs, L.dptr(log_s)), self.h)
+                if init_stats == "host" or esum is not None:            # the host statistics take the matrix
+                    X = np.column_stack([np.ones(N)] + cov_cols)
+            else:
+                try:
+                    L.check(self.lib.clv_set_data(self.h, x.ctypes.data_as(L.c_int32_p), L.dptr(t_x), L.dptr(T_cal),
+                                                  L.dptr(X), L.dptr(log_s)), self.h)
+                except L.ClvError as e:        # the intercept column is validated on the device during the upload
+                    if "intercept" in str(e):
+                        raise ValueError("column 0 of X must be the intercept (all ones)") from None
+                    raise
             hy = hyper or default_hyper(K, D)
             b0 = np.ascontiguousarray(hy["beta_0"], dtype=np.float64)
             a0 = np.ascontiguousarray(hy["A_0"], dtype=np.float64)

@@ -53,6 +53,20 @@ def test_argument_validation_without_device():
     assert lib.clv_create(C.byref(h), C.byref(bad)) == -1
 
 
+def test_column_wise_design_is_validated_on_the_host():
+    """Covariate columns (clv_set_data_columns): wrong lengths are refused before any device work, and a null handle /
+    null column comes back as an error code, not a crash."""
+    import numpy as np
+    from mcmc_clv_model_b200 import Sampler
+    x, t, T = np.array([0, 1, 2]), np.array([0.0, 3.0, 9.0]), np.full(3, 30.0)
+    with pytest.raises(ValueError, match="covariate column"):
+        Sampler(x, t, T, [np.zeros(2)])
+    with pytest.raises(ValueError, match="covariate column"):
+        Sampler(x, t, T, [np.zeros((3, 1))])
+    lib = L.load()
+    assert lib.clv_set_data_columns(None, None, None, None, None, None) == -1
+
+
 def _has_gpu():
     try:
         import torch

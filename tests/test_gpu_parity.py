@@ -193,18 +193,20 @@ def test_forecast_large_mean_distribution():
 
 
 @pytest.mark.parametrize("D", [2, 3])
-def test_device_init_statistics_equal_host_exact_sums(cdnow_full, D):
+def test_device_init_statistics_equal_host_exact_sums(cdnow_full, monkeypatch, D):
     """clv_init_state(NULL): the device's exact integer sums == hostmath's, bit for bit."""
     from mcmc_clv_model_b200.hostmath import init_statistics
     d = cdnow_full
     X = np.column_stack([np.ones(d["x"].size), d["first_sales_scaled"], d["gender_F"].astype(float), d["age_scaled"]])
     log_s = d["log_s"] if D == 3 else None
     host = init_statistics(d["x"], d["t_x"], d["T_cal"], X, log_s, d["x"].size)
-    with Sampler(d["x"], d["t_x"], d["T_cal"], X, log_s, model_dim=D, chains=1) as s:
-        dev = s.init_stats
-    for k in ("lam_init", "mean_mu_init", "mean_log_s", "omega2", "max_abs_x"):
-        assert dev[k] == host[k], (k, dev[k], host[k])
-    np.testing.assert_array_equal(dev["xtx"], host["xtx"])
+    for generic in ("0", "1"):        # K <= 5: sums kept in registers (k_init_quantities_t) / the general kernel
+        monkeypatch.setenv("CLV_INIT_GENERIC", generic)
+        with Sampler(d["x"], d["t_x"], d["T_cal"], X, log_s, model_dim=D, chains=1) as s:
+            dev = s.init_stats
+        for k in ("lam_init", "mean_mu_init", "mean_log_s", "omega2", "max_abs_x"):
+            assert dev[k] == host[k], (k, dev[k], host[k], generic)
+        np.testing.assert_array_equal(dev["xtx"], host["xtx"])
     # and close to the reference's plain NumPy means (bi:368-374)
     lam = d["x"].mean() / np.mean(np.where(d["t_x"] == 0, d["T_cal"], d["t_x"]))
     assert abs(dev["lam_init"] / lam - 1) < 1e-13
@@ -939,3 +941,53 @@ def test_fast_kernel_exact_path_and_guards_on_adversarial_rows(cpt, case, monkey
             np.testing.assert_allclose(dev["Sigma"], st["Sigma"], rtol=RTOL, atol=1e-12)
     if case == "regular_sigma":
         assert np.log(st["lam"])[10:20].max() < 69.0 and (np.log(st["mu"])[24:30] <= 5.0).all()   # the chain did leave those corners
+
+
+@pytest.mark.parametrize("n", [1, 2, 33, 127, 128, 129, 255, 256, 257, 641])
+def test_tiny_and_ragged_customer_counts_vs_oracle(cdnow_full, monkeypatch, n):
+    """Customer counts around the tile edges (128 customers per tile in the one-customer kernel, 256 in the
+    two-customer one) down to a single customer: every sweep path -- k_sweep, k_sweep2 (forced with CLV_SWEEP_CPT)
+    and the cooperative kernel -- against the oracle's replay of the strict Philox variates, bivariate and
+    trivariate.  The rows are the first n customers WITH repeat purchases followed by their neighbours, so that
+    the reference's initial state (bi:367-374: mean(x) / mean(t_x)) exists at n = 1."""
+    d = cdnow_full
+    order = np.argsort(d["x"] == 0, kind="stable")[:n]            # x > 0 first, input order otherwise
+    if n > 2:
+        order = np.sort(np.concatenate([order[: n // 2], np.flatnonzero(d["x"] == 0)[: n - n // 2]]))
+    X = np.column_stack([np.ones(n), d["first_sales_scaled"][order]])
+    cbs = ao.Cbs(x=d["x"][order].astype(np.int64), t_x=d["t_x"][order], T_cal=d["T_cal"][order], X=X, log_s=d["log_s"][order])
+    seed, S = 31, 20
+    for D in ((2,) if n == 1 else (2, 3)):                        # var(log_s) of one customer is undefined (tri:494)
+        ora = ao.run_chain(cbs, ao.default_hyper(2, D), PhiloxStreams(seed, 0, np.arange(n), S, D, 2), mcmc=3, burnin=1,
+                           thin=1, D=D, n_mh_steps=S)
+        for cpt, mode in (("1", "stream"), ("2", "stream"), ("1", "persistent")):
+            monkeypatch.setenv("CLV_SWEEP_CPT", cpt)
+            with Sampler(cbs.x, cbs.t_x, cbs.T_cal, X, cbs.log_s if D == 3 else None, model_dim=D, chains=1, n_mh_steps=S,
+                         seed=seed, rng="strict", sweep_mode=mode) as s:
+                out = s.run(1, 3, 1)
+            msg = f"n={n} D={D} cpt={cpt} {mode}"
+            np.testing.assert_array_equal(out["level_1"][0][:, :, 3], ora["level_1"][:, :, 3], err_msg=msg)
+            np.testing.assert_allclose(out["level_1"][0], ora["level_1"], rtol=RTOL, err_msg=msg)
+            np.testing.assert_allclose(out["level_2"][0], ora["level_2"], rtol=RTOL, atol=1e-9, err_msg=msg)
+
+
+@pytest.mark.parametrize("D,cov", [(2, []), (2, ["first_sales_scaled", "age_scaled"]), (3, ["gender_F", "age_scaled", "first_sales_scaled"]),
+                                   (2, ["first_sales_scaled", "age_scaled", "gender_F", "first_sales_scaled", "age_scaled", "gender_F"])])
+def test_column_wise_data_entry_equals_the_matrix_entry(cdnow_full, D, cov):
+    """clv_set_data_columns (the covariate columns as the DataFrame holds them, intercept implicit -- what the drop-in
+    entry points use) against clv_set_data (the (N, K) design matrix of bi:468-470): same initialisation statistics and
+    the same chains, bit for bit; K = 1 (no covariate) to K = 7 (the general initialisation kernel)."""
+    d = cdnow_full
+    n = d["x"].size
+    cols = [d[c].astype(float) for c in cov]
+    X = np.column_stack([np.ones(n)] + cols)
+    log_s = d["log_s"] if D == 3 else None
+    outs = []
+    for design in (X, cols):
+        with Sampler(d["x"], d["t_x"], d["T_cal"], design, log_s, model_dim=D, chains=2, seed=11) as s:
+            outs.append((s.init_stats, s.run(2, 3, 1)))
+    for k in ("lam_init", "mean_mu_init", "mean_log_s", "omega2", "max_abs_x"):
+        assert outs[0][0][k] == outs[1][0][k], k
+    np.testing.assert_array_equal(outs[0][0]["xtx"], outs[1][0]["xtx"])
+    for k in ("level_1", "level_2", "loglik_sum"):
+        np.testing.assert_array_equal(outs[0][1][k], outs[1][1][k], err_msg=k)
