@@ -545,12 +545,16 @@ def configs_block(local, with_cpu=True):
         fn = mcmc_draw_parameters if which == "bivariate" else mcmc_draw_parameters_rfm_m
         n = len(df)
         fn(df, covariates=cov, mcmc=40, burnin=40, thin=1, chains=chains, seed=1, trace=0)           # warm-up of the call path
-        t0 = time.perf_counter()
-        draws = fn(df, covariates=cov, mcmc=4000, burnin=10000, thin=1, chains=chains, seed=42, trace=0)
-        wall = time.perf_counter() - t0
+        walls, draws = [], None
+        for _ in range(2):              # best of two: 1.2 - 7.5 GB land in fresh NumPy arrays, page-fault bound and noisy (C2: 0.72 - 1.6 s)
+            del draws
+            t0 = time.perf_counter()
+            draws = fn(df, covariates=cov, mcmc=4000, burnin=10000, thin=1, chains=chains, seed=42, trace=0)
+            walls.append(time.perf_counter() - t0)
+        wall = min(walls)
         l2 = np.asarray(draws["level_2"])
         gb = sum(a.nbytes for a in draws["level_1"]) / 1e9
-        e = {"what": what, "wall_s": wall, "customer_updates_per_sec": n * chains * 14000 / wall, "level_1_to_host_GB": gb,
+        e = {"what": what, "wall_s": wall, "wall_s_all_runs": walls, "customer_updates_per_sec": n * chains * 14000 / wall, "level_1_to_host_GB": gb,
              "min_ess_bulk": min_ess(l2, "bulk"), "min_ess_geyer": min_ess(l2, "geyer"),
              "log_likelihood": float(draws["log_likelihood"]), "level_2_mean": [float(v) for v in l2.mean(axis=(0, 1))]}
         e["ess_per_sec"] = e["min_ess_bulk"] / wall

@@ -116,6 +116,7 @@ struct ForecastArgs {
   long long* x_out;              // [n_draws][N] (nullable)
   double* spend_out;             // [n_draws][N] (nullable)
   PhiloxRoundKeys rk;            // round keys of `seed` (launch constants; filled by the host)
+  long long pair_lo, pair_hi;    // k_forecast_reduce: draw pairs [pair_lo, pair_hi) of this launch (pair_hi == 0: all)
 };
 
 // Forecast uniforms: one Philox block serves the two draws 2g, 2g+1 of a customer (global draw index, chain-major):
@@ -303,9 +304,11 @@ __global__ void __launch_bounds__(256, CLV_FC_MINBLOCKS) k_forecast_reduce(Forec
   __shared__ FcQueued s_q[FC_WARPS][FC_QCAP];
   const float T_star_f = (float)a.T_star;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int npairs = (int)((a.n_draws + 1) >> 1);
-  const int per = (npairs + gridDim.y - 1) / gridDim.y;
-  const int pa = blockIdx.y * per, pb = min(npairs, pa + per);
+  // the launch's range of draw pairs (the whole forecast, or one chunk of it: the host overlaps the second pass of a
+  // chunk with the main pass of the next), cut into gridDim.y ranges
+  const int p_lo = a.pair_hi > 0 ? (int)a.pair_lo : 0, p_hi = a.pair_hi > 0 ? (int)a.pair_hi : (int)((a.n_draws + 1) >> 1);
+  const int per = (p_hi - p_lo + gridDim.y - 1) / gridDim.y;
+  const int pa = p_lo + blockIdx.y * per, pb = min(p_hi, pa + per);
   const long long stride = a.N * NCOL;                 // doubles between consecutive draws of one customer
   FcQueued* q = s_q[warp];
   const long long nwt = (a.N + 31) / 32;               // warp tiles of 32 consecutive customers
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(256, CLV_FC_MINBLOCKS) k_forecast_reduce(Forec
     __syncwarp();
     if (qn > 0) fc_flush(q, 0, qn, g_list, g_count, g_cap, lane);
     if (valid) {
-      if (gridDim.y == 1) {
+      if (gridDim.y == 1 && a.pair_hi == 0) {
         sum_x[i] = (double)sx;
         sum_z[i] = (double)sz;
       } else {

@@ -864,6 +864,34 @@ def test_resident_forecast_list_overflow_is_repeated_with_a_larger_list(cdnow_ab
     assert ref["x_star"].max() >= 8                          # some cells did take the second pass
 
 
+@pytest.mark.parametrize("D", [2, 3])
+def test_resident_forecast_in_chunks_equals_one_pass(cdnow_abe, monkeypatch, D):
+    """The resident forecast can run in chunks of draw pairs, the second pass of a chunk on a side stream beside the main
+    pass of the next (CLV_FC_CHUNKS; an A/B knob, measured no faster): same x*, same sums, for an odd number of draws,
+    with and without x* written out, and when a chunk's list overflows (repeated in one pass)."""
+    d = cdnow_abe
+    n = 2357
+    log_s = d["log_s"][:n] if D == 3 else None
+    with Sampler(d["x"][:n], d["t_x"][:n], d["T_cal"][:n], np.ones((n, 1)), log_s, model_dim=D, chains=3, seed=4) as s:
+        s.run_resident(30, 37, 1)                             # 3 x 37 = 111 draws: 56 pairs, the last one half empty
+        monkeypatch.setenv("CLV_FC_CHUNKS", "1")
+        ref = s.forecast_resident(T_star=39.0, seed=9, want_x_star=True)
+        ref_sums = s.forecast_resident(T_star=39.0, seed=9)
+        outs = []
+        for chunks, side, cap in (("2", "1", None), ("5", "2", None), ("56", "1", None), ("7", "1", "70")):
+            monkeypatch.setenv("CLV_FC_CHUNKS", chunks)
+            monkeypatch.setenv("CLV_FC_SIDE_BLOCKS", side)
+            if cap: monkeypatch.setenv("CLV_FC_LIST_CAP", cap)
+            outs.append((s.forecast_resident(T_star=39.0, seed=9, want_x_star=True), s.forecast_resident(T_star=39.0, seed=9)))
+    for full, sums in outs:
+        for k in ("mean_x_star", "p_alive", "x_star"):
+            np.testing.assert_array_equal(full[k], ref[k], err_msg=k)
+        for k in ("mean_x_star", "p_alive"):
+            np.testing.assert_array_equal(sums[k], ref_sums[k], err_msg=k)
+            np.testing.assert_array_equal(sums[k], ref[k], err_msg=k)
+    assert ref["x_star"].max() >= 8
+
+
 @pytest.mark.parametrize("D,cov", [(2, ["first_sales_scaled"]), (3, ["gender_F", "age_scaled"])])
 def test_injected_sweeps_at_full_cdnow_size_vs_oracle(cdnow_full, D, cov):
     """Injected streams at the size of BASELINE.json configs[1] / [2] (23 570 customers, 185 tiles -- the reference-made
