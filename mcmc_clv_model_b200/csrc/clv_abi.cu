@@ -1855,6 +1855,7 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
   int chunks = 1;
   if (const char* e = getenv("CLV_FC_CHUNKS")) chunks = (int)std::max(1ll, std::min<long long>(atoll(e), std::min<long long>(npairs, 64)));
   if (use_tma) chunks = 1;
+  chunks = std::max(1, std::min(chunks, 64));
   int side_blocks = 1;                            // blocks per SM of a second pass that runs beside a main pass
   if (const char* e = getenv("CLV_FC_SIDE_BLOCKS")) side_blocks = (int)std::max(1ll, std::min(8ll, atoll(e)));
   cudaError_t fe = cudaSuccess;
@@ -1897,7 +1898,7 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
       launch_deferred(a, d_list, d_cnt, gd, h->stream);
     } else {
       if (gy > 1 || attempt > 0 || chunks > 1) { cudaMemsetAsync(d_mx, 0, sizeof(double) * N, h->stream); cudaMemsetAsync(d_pa, 0, sizeof(double) * N, h->stream); }
-      std::vector<cudaEvent_t> ev(chunks, nullptr);
+      cudaEvent_t ev[64] = {};                      // chunks <= 64
       for (int c = 0; c < chunks; ++c) {
         ForecastArgs ac = a;
         if (chunks > 1) { ac.pair_lo = npairs * c / chunks; ac.pair_hi = npairs * (c + 1) / chunks; }
@@ -1928,7 +1929,7 @@ int clv_forecast_resident(clv_sampler* h, double T_star, uint64_t seed, int64_t*
           launch_deferred(a, list, cnt, gd, h->stream);
         }
       }
-      for (auto& e : ev) if (e) cudaEventDestroy(e);
+      for (int c = 0; c < chunks; ++c) if (ev[c]) cudaEventDestroy(ev[c]);
     }
     std::vector<unsigned long long> listed_c(chunks, 0ull);
     fe = cudaMemcpyAsync(listed_c.data(), d_cnt, sizeof(unsigned long long) * chunks, cudaMemcpyDeviceToHost, h->stream);
