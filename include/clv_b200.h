@@ -297,6 +297,9 @@ int clv_debug_lockstep_advance(clv_sampler** shards, int n_shards, int64_t n_swe
 /* ---- test hook: the parallel host memcpy behind the staged transfers (no device involved): copies `bytes` from src to
  * dst on the library's copy threads, returns the number of threads that took part. */
 int clv_debug_host_copy(void* dst, const void* src, int64_t bytes);
+/* Test hook: the first-touch threads clv_run starts on the caller's level-1 array (one `lock or byte, 0` per page: takes the
+ * write fault, leaves the data as it is), here on any buffer; returns when every page has been touched. */
+int clv_debug_first_touch(void* buf, int64_t bytes, int threads);
 
 /* ---- micro-benchmarks used by bench.py for the issue-rate roofline -------------------------- */
 /* Measures, on `device`, sustained warp-instruction throughput of dependent-free loops of

@@ -105,6 +105,7 @@ SIGNATURES = {
     "clv_standardize": (C.c_int, [C.c_int, C.c_int64, c_double_p, C.c_double, c_double_p, c_double_p, c_double_p]),
     "clv_recode": (C.c_int, [C.c_int, C.c_int64, c_int32_p, c_double_p, C.c_int, c_double_p]),
     "clv_debug_host_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "clv_debug_first_touch": (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),
     "clv_debug_lockstep_advance": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64]),
     "clv_debug_variates": (C.c_int, [C.c_int, C.c_uint64, C.c_uint32, C.c_int32, C.c_int, C.c_int64, c_double_p, c_double_p, c_double_p]),
     "clv_measure_issue_peaks": (C.c_int, [C.c_int, c_double_p]),

@@ -3,9 +3,11 @@
 // and (customer-sharded mode) all-reduces the int64 level-2 statistics over NCCL each sweep.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <emmintrin.h>
 #include <math_constants.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -277,6 +279,26 @@ double i128_scaled(__int128 t, int bits) {
 // Here the copy is cut into pieces that travel through a small ring of page-locked buffers (DMA at PCIe speed), and a
 // few worker threads move each piece between the ring and the caller's array in parallel (first-touch page faults
 // included).  The level-1 draws of the reference's full-data run are 12 GB; this is what bounds that run.
+// memcpy with non-temporal stores: the destination of a staged transfer (the caller's array, or a ring slot the copy
+// engine reads next) is not read again by this core, so its lines need not be fetched before they are overwritten
+// (write-allocate makes a plain memcpy move 3 bytes per byte copied) nor displace the cache.  CLV_COPY_NT=0: plain memcpy.
+static void copy_stream_stores(char* dst, const char* src, size_t n) {
+  static const bool plain = [] { const char* e = getenv("CLV_COPY_NT"); return e && atoi(e) == 0; }();
+  if (plain || n < 4096) { memcpy(dst, src, n); return; }
+  const size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+  memcpy(dst, src, head);
+  dst += head; src += head; n -= head;
+  const size_t blocks = n / 64;
+  for (size_t i = 0; i < blocks; ++i, src += 64, dst += 64) {
+    const __m128i a = _mm_loadu_si128((const __m128i*)src), b = _mm_loadu_si128((const __m128i*)(src + 16));
+    const __m128i c = _mm_loadu_si128((const __m128i*)(src + 32)), d = _mm_loadu_si128((const __m128i*)(src + 48));
+    _mm_stream_si128((__m128i*)dst, a); _mm_stream_si128((__m128i*)(dst + 16), b);
+    _mm_stream_si128((__m128i*)(dst + 32), c); _mm_stream_si128((__m128i*)(dst + 48), d);
+  }
+  _mm_sfence();
+  memcpy(dst, src, n - blocks * 64);
+}
+
 class HostCopyPool {
  public:
   static HostCopyPool& get() { static HostCopyPool p; return p; }
@@ -284,7 +306,7 @@ class HostCopyPool {
   // memcpy split over the workers and the calling thread; returns when all parts are done
   void copy(void* dst, const void* src, size_t bytes) {
     const int parts = bytes < (2u << 20) ? 1 : threads();
-    if (parts == 1) { memcpy(dst, src, bytes); return; }
+    if (parts == 1) { copy_stream_stores((char*)dst, (const char*)src, bytes); return; }
     const size_t per = ((bytes + parts - 1) / parts + 4095) & ~(size_t)4095;
     {
       std::lock_guard<std::mutex> g(m_);
@@ -294,7 +316,7 @@ class HostCopyPool {
       }
     }
     cv_.notify_all();
-    memcpy(dst, src, std::min(per, bytes));
+    copy_stream_stores((char*)dst, (const char*)src, std::min(per, bytes));
     std::unique_lock<std::mutex> g(m_);
     done_cv_.wait(g, [&] { return pending_ == 0; });
   }
@@ -302,9 +324,9 @@ class HostCopyPool {
  private:
   struct Job { char* dst; const char* src; size_t len; };
   HostCopyPool() {
-    int n = (int)std::thread::hardware_concurrency() / 2;
+    int n = std::min((int)std::thread::hardware_concurrency() / 2, 8);
     if (const char* env = getenv("CLV_COPY_THREADS")) n = atoi(env);
-    n = std::max(1, std::min(n, 8));
+    n = std::max(1, std::min(n, 32));
     for (int t = 1; t < n; ++t) workers_.emplace_back([this] { run(); });
   }
   ~HostCopyPool() {
@@ -322,7 +344,7 @@ class HostCopyPool {
         j = jobs_.back();
         jobs_.pop_back();
       }
-      memcpy(j.dst, j.src, j.len);
+      copy_stream_stores(j.dst, j.src, j.len);
       {
         std::lock_guard<std::mutex> g(m_);
         if (--pending_ == 0) done_cv_.notify_all();
@@ -393,6 +415,64 @@ bool is_page_locked(const void* p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return at.type == cudaMemoryTypeHost;
+}
+
+// First touch of a caller's output array, ahead of the copies.  The level-1 draws of a run land in a FRESH array
+// (np.empty; NumPy advises huge pages for it): the first write to every page makes the kernel allocate and ZERO it, in the
+// thread that writes -- here the copy threads, in the middle of the transfer.  Measured on the C2 shape x 4 chains (12 GB of
+// draws, tools/d2h_probe.py): 1.15 s into a fresh array, 0.57 s into the same array again, 0.38 s without level-1 output:
+// zeroing 12 GB costs more than sampling.  While the GPU runs the burn-in the host has nothing to do, so a few threads
+// touch the pages in the order the run will fill them.  The touch is `lock or byte, 0`: it takes the write fault but
+// leaves the byte as it is, atomically -- a copy that has already delivered data there (the toucher fell behind) loses
+// nothing.  The threads stop when the run ends.
+class FirstToucher {
+ public:
+  FirstToucher() = default;
+  FirstToucher(const FirstToucher&) = delete;
+  FirstToucher& operator=(const FirstToucher&) = delete;
+  ~FirstToucher() { stop(); }
+  // ranges are taken in the given order by n_threads threads
+  void start(std::vector<std::pair<char*, size_t>> ranges, int n_threads) {
+    ranges_ = std::move(ranges);
+    if (ranges_.empty() || n_threads < 1) return;
+    for (int t = 0; t < n_threads; ++t)
+      th_.emplace_back([this] {
+        for (;;) {
+          const size_t i = next_.fetch_add(1);
+          if (i >= ranges_.size()) return;
+          char* p = ranges_[i].first;
+          char* const end = p + ranges_[i].second;
+          for (; p < end; p += 4096) {
+            if (stop_.load(std::memory_order_relaxed)) return;
+            __atomic_fetch_or((unsigned char*)p, (unsigned char)0, __ATOMIC_RELAXED);
+          }
+        }
+      });
+  }
+  void stop() {
+    stop_.store(true);
+    finish();
+  }
+  void finish() {                       // wait until every range has been touched (or stop() was called)
+    for (auto& t : th_) t.join();
+    th_.clear();
+  }
+
+ private:
+  std::vector<std::pair<char*, size_t>> ranges_;
+  std::vector<std::thread> th_;
+  std::atomic<size_t> next_{0};
+  std::atomic<bool> stop_{false};
+};
+
+static int first_touch_threads() {
+  int nt = std::max(1, std::min(8, (int)std::thread::hardware_concurrency() / 2));
+  if (const char* te = getenv("CLV_FIRST_TOUCH_THREADS")) nt = std::max(1, std::min(32, atoi(te)));
+  return nt;
+}
+static bool first_touch_wanted(const void* p, size_t bytes) {
+  const char* fe = getenv("CLV_FIRST_TOUCH");
+  return !(fe && atoi(fe) == 0) && p && bytes >= staging_min_bytes() && !is_page_locked(p);
 }
 
 // device -> pageable host, ordered after everything already in `stream`; returns when the data is in `dst`
@@ -1408,6 +1488,21 @@ static int run_impl(clv_sampler* h, int64_t burnin, int64_t mcmc, int64_t thin, 
     h->fc_draws = n_draws;
   }
   const long long total = burnin + mcmc;
+  // the caller's level-1 array gets its first touch ahead of the copies, while the sweeps run (CLV_FIRST_TOUCH=0: off).
+  // Only when there is time for it: a burn-in before the first kept draw, or an array of a GB and more (a short run without
+  // burn-in -- the bench's end-to-end call: 320 MB kept at the first sweep -- is 1 % faster without the extra threads).
+  FirstToucher toucher;
+  if (level1) {
+    const size_t chain_bytes = (size_t)n_draws * N * nc * sizeof(double);
+    if ((burnin > 0 || chain_bytes * (size_t)C >= ((size_t)1 << 30)) && first_touch_wanted(level1, chain_bytes * (size_t)C)) {
+      const size_t piece = 8u << 20;
+      std::vector<std::pair<char*, size_t>> ranges;      // in the order of the flushes: piece by piece, every chain
+      for (size_t off = 0; off < chain_bytes; off += piece)
+        for (long long c = 0; c < C; ++c)
+          ranges.emplace_back((char*)level1 + (size_t)c * chain_bytes + off, std::min(piece, chain_bytes - off));
+      toucher.start(std::move(ranges), first_touch_threads());
+    }
+  }
   int buf = 0;
   long long chunk_base = 0;
   bool used[2] = {false, false};
@@ -1736,6 +1831,18 @@ static int forecast_host(const clv_forecast_config* cfg, const double* level1, c
   CK(nullptr, cudaSetDevice(cfg->device)); t_alloc_stream = nullptr; ensure_pool(cfg->device);
   if (int r = upload_rk()) return r;
   const long long N = cfg->n_customers, nd = cfg->n_draws_total, nc = cfg->ncol;
+  // fresh output arrays get their first touch (page allocation + zeroing) from host threads while the first rows travel
+  FirstToucher toucher;
+  {
+    const size_t out_bytes = (size_t)nd * N * 8, piece = 8u << 20;
+    std::vector<std::pair<char*, size_t>> ranges;
+    if (first_touch_wanted(x_star, out_bytes))
+      for (size_t off = 0; off < out_bytes; off += piece) {
+        ranges.emplace_back((char*)x_star + off, std::min(piece, out_bytes - off));
+        if (want_spend && !is_page_locked(spend)) ranges.emplace_back((char*)spend + off, std::min(piece, out_bytes - off));
+      }
+    if (!ranges.empty()) toucher.start(std::move(ranges), first_touch_threads());
+  }
   const size_t free_b = available_bytes(cfg->device);
   const long long per_draw = N * (nc * 8 + 8 + (want_spend ? 8 : 0) + (inject ? 16 : 0));
   long long chunk = std::max<long long>(1, std::min<long long>(nd, (long long)(free_b * 0.35) / std::max<long long>(1, per_draw)));
@@ -2354,6 +2461,18 @@ int clv_debug_host_copy(void* dst, const void* src, int64_t bytes) {
   HostCopyPool& pool = HostCopyPool::get();
   pool.copy(dst, src, (size_t)bytes);
   return pool.threads();
+}
+
+// ---- test hook: the first-touch threads of clv_run on a caller's buffer (returns when every page has been touched) ----
+int clv_debug_first_touch(void* buf, int64_t bytes, int threads) {
+  if (!buf || bytes < 0 || threads < 1) return fail(nullptr, CLV_ERR_ARG, "clv_debug_first_touch: bad argument");
+  FirstToucher t;
+  std::vector<std::pair<char*, size_t>> ranges;
+  const size_t piece = 1u << 20;
+  for (size_t off = 0; off < (size_t)bytes; off += piece) ranges.emplace_back((char*)buf + off, std::min(piece, (size_t)bytes - off));
+  t.start(std::move(ranges), threads);
+  t.finish();
+  return CLV_OK;
 }
 
 // ---- issue-rate peaks ---------------------------------------------------------------------------

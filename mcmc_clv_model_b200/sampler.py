@@ -165,14 +165,20 @@ class Sampler:
         L.check(self.lib.clv_p2p_connect(self.h, blob, int(rank), int(world)), self.h)
 
     # ---- sweeps ------------------------------------------------------------------------------
-    def run(self, burnin, mcmc, thin, store_level1=True, trace=0, progress=None, pinned=False):
+    def run(self, burnin, mcmc, thin, store_level1=True, trace=0, progress=None, pinned=False, out=None):
         """burnin + mcmc sweeps; returns dict(level_1 [chains] of (n_draws,N,ncol) | None,
         level_2 (chains,n_draws,P), loglik_sum (chains,n_draws) = per-draw SUM over local customers).
         pinned=True page-locks the level-1 output (worth it only when the draws do not fit one device chunk and
-        are streamed out while the sweeps continue)."""
+        are streamed out while the sweeps continue).  out: a caller-provided C-contiguous float64 array of shape
+        (chains, n_draws, N, ncol) for the level-1 draws (e.g. one reused over several runs)."""
         n_draws = (int(mcmc) - 1) // int(thin) + 1
         shape = (self.chains, n_draws, self.N, self.ncol)
-        lvl1 = (_pinned_empty(shape) if pinned else np.empty(shape)) if store_level1 else None
+        if out is not None:
+            if not store_level1 or out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+                raise ValueError(f"out must be a C-contiguous float64 array of shape {shape}")
+            lvl1 = out
+        else:
+            lvl1 = (_pinned_empty(shape) if pinned else np.empty(shape)) if store_level1 else None
         lvl2 = np.empty((self.chains, n_draws, self.P))
         ll = np.empty((self.chains, n_draws))
         cb = L.PROGRESS_CB(lambda user, step, total: progress(int(step), int(total))) if progress else C.cast(None, L.PROGRESS_CB)

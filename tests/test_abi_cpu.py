@@ -193,3 +193,26 @@ def test_parallel_host_copy_pool():
     [t.join() for t in th]
     for i in range(4):
         np.testing.assert_array_equal(outs[i], src[i * 1000:i * 1000 + outs[i].size])
+
+
+def test_first_touch_threads_leave_the_data_alone():
+    """clv_run touches the pages of the caller's level-1 array ahead of the copies (`lock or byte, 0`: the write fault is
+    taken, the byte keeps its value).  No device needed: a buffer that already holds data stays intact, also while
+    another thread keeps writing to it, and a fresh buffer reads as zeros afterwards."""
+    import threading
+    lib = L.load()
+    rng = np.random.default_rng(1)
+    src = rng.integers(0, 256, (48 << 20) + 123, dtype=np.uint8)
+    dst = src.copy()
+    assert lib.clv_debug_first_touch(dst.ctypes.data, dst.size, 4) == 0
+    np.testing.assert_array_equal(dst, src)
+    for _ in range(3):                   # a copy delivers data while the touchers run over the same pages: nothing is lost
+        dst.fill(0)
+        th = threading.Thread(target=lambda: [lib.clv_debug_first_touch(dst.ctypes.data, dst.size, 4) for _ in range(4)])
+        th.start()
+        np.copyto(dst, src)
+        th.join()
+        np.testing.assert_array_equal(dst, src)
+    fresh = np.empty(64 << 20, dtype=np.uint8)
+    assert lib.clv_debug_first_touch(fresh[5:].ctypes.data, fresh.size - 5, 3) == 0
+    assert lib.clv_debug_first_touch(None, 1, 1) == -1

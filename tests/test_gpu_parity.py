@@ -1019,3 +1019,22 @@ def test_column_wise_data_entry_equals_the_matrix_entry(cdnow_full, D, cov):
     np.testing.assert_array_equal(outs[0][0]["xtx"], outs[1][0]["xtx"])
     for k in ("level_1", "level_2", "loglik_sum"):
         np.testing.assert_array_equal(outs[0][1][k], outs[1][1][k], err_msg=k)
+
+
+def test_caller_provided_level1_array(cdnow_abe):
+    """Sampler.run(out=...): the level-1 draws land in the caller's array (reusable over runs); same values as the
+    array the run allocates itself; a wrong shape / dtype / layout is refused before any device work."""
+    d = cdnow_abe
+    n = 1200
+    args = (d["x"][:n], d["t_x"][:n], d["T_cal"][:n], [d["first_sales_scaled"][:n].astype(float)])
+    with Sampler(*args, chains=2, seed=8) as s:
+        ref = s.run(3, 6, 2)
+    buf = np.full((2, 3, n, 4), np.nan)
+    with Sampler(*args, chains=2, seed=8) as s:
+        out = s.run(3, 6, 2, out=buf)
+        assert out["level_1"] is buf
+        for bad in (np.empty((2, 3, n, 5)), np.empty((2, 3, n, 4), dtype=np.float32), np.empty((2, 3, 4, n)).transpose(0, 1, 3, 2)):
+            with pytest.raises(ValueError, match="out must be"):
+                s.run(3, 6, 2, out=bad)
+    np.testing.assert_array_equal(buf, ref["level_1"])
+    np.testing.assert_array_equal(out["level_2"], ref["level_2"])
