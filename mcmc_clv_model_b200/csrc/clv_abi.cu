@@ -435,19 +435,23 @@ class FirstToucher {
   void start(std::vector<std::pair<char*, size_t>> ranges, int n_threads) {
     ranges_ = std::move(ranges);
     if (ranges_.empty() || n_threads < 1) return;
-    for (int t = 0; t < n_threads; ++t)
-      th_.emplace_back([this] {
-        for (;;) {
-          const size_t i = next_.fetch_add(1);
-          if (i >= ranges_.size()) return;
-          char* p = ranges_[i].first;
-          char* const end = p + ranges_[i].second;
-          for (; p < end; p += 4096) {
-            if (stop_.load(std::memory_order_relaxed)) return;
-            __atomic_fetch_or((unsigned char*)p, (unsigned char)0, __ATOMIC_RELAXED);
+    try {
+      for (int t = 0; t < n_threads; ++t)
+        th_.emplace_back([this] {
+          for (;;) {
+            const size_t i = next_.fetch_add(1);
+            if (i >= ranges_.size()) return;
+            char* p = ranges_[i].first;
+            char* const end = p + ranges_[i].second;
+            for (; p < end; p += 4096) {
+              if (stop_.load(std::memory_order_relaxed)) return;
+              __atomic_fetch_or((unsigned char*)p, (unsigned char)0, __ATOMIC_RELAXED);
+            }
           }
-        }
-      });
+        });
+    } catch (...) {
+      // no more threads to be had: the ones that started carry on, the copies take the remaining faults themselves
+    }
   }
   void stop() {
     stop_.store(true);
