@@ -469,8 +469,13 @@ class FirstToucher {
   std::atomic<bool> stop_{false};
 };
 
+// Half of this process's share of the cores, at most 8 (measured on a 16-core box: 6 / 8 / 12 / 16 threads give the same
+// times).  Under torchrun the ranks of a node share its cores (LOCAL_WORLD_SIZE): the thread that launches the sweeps must
+// keep a core to itself, or the burn-in it is supposed to overlap with slows down.
 static int first_touch_threads() {
-  int nt = std::max(1, std::min(8, (int)std::thread::hardware_concurrency() / 2));
+  int ranks = 1;
+  if (const char* lw = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(lw));
+  int nt = std::max(1, std::min(8, (int)std::thread::hardware_concurrency() / (2 * ranks)));
   if (const char* te = getenv("CLV_FIRST_TOUCH_THREADS")) nt = std::max(1, std::min(32, atoi(te)));
   return nt;
 }
